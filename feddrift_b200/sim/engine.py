@@ -1,0 +1,211 @@
+"""DriftSim — the device-resident continual-FL engine (the B200-native replacement of
+``run_fedavg_distributed_pytorch.sh`` + ``main_fedavg.py`` + Server/ClientManager FSM).
+
+The reference launches ``mpirun -np N+1`` once per time step, ships every model to every rank every
+round as pickles, trains with eager per-client optimizers and evaluates with per-batch ``.item()`` syncs
+(SURVEY §3).  Here ONE process owns the whole experiment:
+
+* all time steps' data live in HBM (``DriftData`` tensors), all model slots in a :class:`ModelBank` row
+  arena, all per-(client, model) optimizer state in a :class:`ClientArena`;
+* a drift algorithm (``sim/algos.py``) turns its state machine into a *training plan*: the dense weight
+  tensor ``W[t', m, c]`` (which past time steps' data of client c train model m), sampling/weighting
+  modes, test-model routing and optional ensemble weights — all device tensors;
+* a whole block of rounds (broadcast → E local steps per (client, model) → per-cluster weighted
+  aggregation → evaluation of every client on train/test data) runs in ONE launch of the fused
+  persistent kernel ``fed_round_small`` (small MLPs) with zero host synchronisation; per-round metrics
+  are accumulated on device and flushed to the wandb-compatible sink once per block;
+* host logic only runs at time-step boundaries (clustering decisions on a tiny accuracy matrix) or at
+  the sparse per-round hooks some algorithms need (CFL split checks, AUE weight refresh every 10 rounds).
+
+Models that are not small MLPs run through ``sim/generic.py`` (bank-bound ``nn.Module`` + fused arena
+optimizer + K1 aggregation kernel) behind the same interface.
+"""
+from __future__ import annotations
+
+import os
+import time
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..data.drift import DriftData, generate_drift_data
+from ..drift.evaluator import Evaluator
+from ..models import utils as mutils
+from ..models.utils import create_model
+from ..parallel.arena import ClientArena, ModelBank
+from ..utils.metrics import MetricsSink, get_sink
+from . import checkpoint as ckpt
+
+DEFAULTS = dict(
+    model="fnn", dataset="sea", client_num_in_total=10, client_num_per_round=10, batch_size=500,
+    client_optimizer="adam", lr=0.01, wd=0.001, epochs=5, comm_round=200, frequency_of_the_test=1,
+    total_train_iteration=10, curr_train_iteration=0, drift_together=0, report_client=1, retrain_data="win-1",
+    concept_drift_algo="softcluster", concept_drift_algo_arg="H_A_C_1_10_0", ensemble_window=4, concept_num=4,
+    change_points="A", time_stretch=1, reset_models=0, noise_prob=0.0, dummy_arg=0, sample_num=100, ci=0,
+    is_mobile=0, gpu_num_per_server=1, data_dir=None, checkpoint_dir=None, rounds_per_launch=0,
+)
+
+
+def make_args(**kw) -> SimpleNamespace:
+    d = dict(DEFAULTS)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+class DriftSim:
+    def __init__(self, args, data: Optional[DriftData] = None, device=None, sink: Optional[MetricsSink] = None,
+                 algo=None):
+        self.args = args
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda" if torch.cuda.is_available() else "cpu")
+        self.sink = sink if sink is not None else get_sink()
+        seed = int(getattr(args, "dummy_arg", 0))
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        mutils.torch_seed = seed
+        self.rng = np.random.RandomState(seed)
+        if data is None:
+            data = generate_drift_data(args.dataset, args.total_train_iteration, args.client_num_in_total,
+                                       args.sample_num, args.noise_prob, args.time_stretch, args.change_points,
+                                       bool(args.drift_together), seed=0, data_dir=getattr(args, "data_dir", None))
+        self.data_host = data
+        self.data = data.to(self.device)
+        self.C = data.client_num
+        from .algos import make_algo
+        self.algo = algo if algo is not None else make_algo(args, self)
+        self.M = self.algo.num_model_slots()
+        template = create_model(args.model, data.class_num, data.feature_num)
+        self.bank = ModelBank(template, self.M, self.device)
+        self.spec = self.bank.mlp
+        self.evaluator = Evaluator(self.bank, self.data, args.batch_size)
+        self.t = -1
+        self.round_in_step = 0
+        self.global_round = 0
+        self.history: List[Dict] = []
+        self._small: Optional[Dict] = None
+        self.clients = ClientArena(self.C, self.M, self.bank.P, self.device,
+                                   adam=(args.client_optimizer != "sgd"))
+        self.timings = {"cluster_s": 0.0, "rounds_s": 0.0}
+
+    # ------------------------------------------------------------------ experiment driver
+    def run(self, start_iteration: int = 0, end_iteration: Optional[int] = None) -> Dict:
+        end = self.args.total_train_iteration if end_iteration is None else end_iteration
+        for t in range(start_iteration, end):
+            self.run_time_step(t)
+        return self.summary()
+
+    def run_time_step(self, t: int, rounds: Optional[int] = None) -> Dict:
+        self.begin_time_step(t)
+        R = self.args.comm_round if rounds is None else rounds
+        out = self.run_rounds(R)
+        self.end_time_step()
+        return out
+
+    def begin_time_step(self, t: int) -> None:
+        """Clustering / state machine for time step t (runs BEFORE round 0 with models trained at t-1 —
+        ``FedAvgEnsAggregatorSoftCluster.py:46-118``) and optimizer-state reset (new process in the reference)."""
+        t0 = time.perf_counter()
+        self.t = t
+        self.args.curr_train_iteration = t
+        self.round_in_step = 0
+        if getattr(self.args, "reset_models", 0) and t > 0:
+            for m in range(self.M):
+                self.bank.reinit(m)
+        self.clients.reset_optimizer()
+        self.algo.begin_step(t)
+        self._small = None
+        self.timings["cluster_s"] += time.perf_counter() - t0
+
+    def end_time_step(self) -> None:
+        self.algo.end_step(self.t)
+        cdir = getattr(self.args, "checkpoint_dir", None)
+        if cdir:
+            ckpt.save(self, os.path.join(cdir, f"step_{self.t:04d}.fdck"))
+
+    # ------------------------------------------------------------------ rounds
+    def _small_state(self) -> Dict:
+        """Device-side argument block of the fused round kernel for the current time step."""
+        if self._small is None:
+            a, s, plan = self.args, self.spec, self.algo.plan(self.t)
+            X = self.data.X.reshape(self.data.steps, self.C, self.data.X.shape[2], -1)
+            self._small = dict(
+                kind=s["kind"], din=s["in"], hid=s["hidden"], dout=s["out"],
+                X=X, Y=self.data.Y.to(torch.int32) if self.device.type == "cuda" else self.data.Y,
+                nsamp=self.data.nsamp, batch_size=a.batch_size,
+                W=plan["W"].to(self.device), theta=self.bank.theta,
+                opt_m=self.clients.m, opt_v=self.clients.v, opt_vmax=self.clients.vmax, opt_step=self.clients.step,
+                lr=a.lr, wd=a.wd if a.client_optimizer != "sgd" else 0.0, epochs=a.epochs,
+                optimizer=("sgd" if a.client_optimizer == "sgd" else "adam"),
+                seed=int(a.dummy_arg) * 7919 + 13 + 1000003 * self.t, round0=0, t_cur=self.t,
+                recluster_hard=bool(plan.get("recluster_hard", False)),
+                sample_mode=plan.get("sample_mode", "pool"), n_mode=plan.get("n_mode", "batches"),
+            )
+            for k in ("feat_mask", "train_index", "train_count", "ens_mode", "ens_w", "eval_train_model",
+                      "eval_test_model", "optimizer", "lr"):
+                if plan.get(k) is not None:
+                    self._small[k] = plan[k]
+            if self._small["optimizer"] == "sgd":
+                self._small["wd"] = 0.0
+            if self.bank.stride != self.bank.P:
+                self._small["theta_stride"] = self.bank.stride
+        return self._small
+
+    def run_rounds(self, rounds: int) -> Dict:
+        """Run ``rounds`` FL rounds of the current time step; returns the last round's aggregate metrics."""
+        t0 = time.perf_counter()
+        done, last = 0, {}
+        while done < rounds:
+            block = self.algo.block_size(self.round_in_step, rounds - done)
+            rpl = int(getattr(self.args, "rounds_per_launch", 0) or 0)
+            if rpl > 0:
+                block = min(block, rpl)
+            if self.spec is not None and self.algo.fused_ok():
+                st = self._small_state()
+                st["round0"] = self.round_in_step
+                out = ops.fed_round_small(st, block)
+                if st.get("recluster_hard"):
+                    self.algo.absorb_weights(self.t, st["W"])
+            else:
+                from .generic import run_rounds_generic
+                out = run_rounds_generic(self, block)
+            last = self._flush_metrics(out, self.round_in_step, block)
+            self.round_in_step += block
+            self.global_round += block
+            done += block
+            self.algo.after_block(self.t, self.round_in_step)
+        self.timings["rounds_s"] += time.perf_counter() - t0
+        return last
+
+    def _flush_metrics(self, out: Dict[str, torch.Tensor], r0: int, n: int) -> Dict:
+        """One D2H copy per block; emits the reference's wandb keys for every tested round."""
+        met = out["metrics"].detach().to("cpu", torch.float64).numpy()  # [n, C, 4]
+        cnt = out["counts"].detach().to("cpu", torch.float64).numpy()   # [C, 2]
+        a = self.args
+        ntr, nte = max(cnt[:, 0].sum(), 1.0), max(cnt[:, 1].sum(), 1.0)
+        last: Dict = {}
+        for i in range(n):
+            r = r0 + i
+            if not (r % a.frequency_of_the_test == 0 or r == a.comm_round - 1):
+                continue
+            tr_acc, tr_loss = met[i, :, 0].sum() / ntr, met[i, :, 1].sum() / ntr
+            te_acc, te_loss = met[i, :, 2].sum() / nte, met[i, :, 3].sum() / nte
+            if a.report_client:
+                for c in range(self.C):
+                    self.sink.log({f"Train/Acc-CL-{c}": (met[i, c, 0] / cnt[c, 0]) if cnt[c, 0] else -1, "round": r})
+                    self.sink.log({f"Test/Acc-CL-{c}": (met[i, c, 2] / cnt[c, 1]) if cnt[c, 1] else -1, "round": r})
+            self.sink.log({"Train/Acc": tr_acc, "round": r})
+            self.sink.log({"Train/Loss": tr_loss, "round": r})
+            self.sink.log({"Test/Acc": te_acc, "round": r})
+            self.sink.log({"Test/Loss": te_loss, "round": r})
+            last = {"round": r, "train_acc": tr_acc, "train_loss": tr_loss, "test_acc": te_acc,
+                    "test_loss": te_loss, "iteration": self.t}
+        if last:
+            self.history.append(last)
+        return last
+
+    def summary(self) -> Dict:
+        return {"history": self.history, "summary": dict(self.sink.run.summary), "timings": dict(self.timings),
+                "rounds": self.global_round}

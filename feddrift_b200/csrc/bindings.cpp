@@ -1,0 +1,314 @@
+// pybind / torch bindings for the feddrift_b200 sm_100a kernels.  All launches go to the current CUDA stream.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "fed_round_small.h"
+#include "kernels.h"
+
+namespace {
+
+using torch::Tensor;
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+#define CHECK_CUDA_F32(x) TORCH_CHECK((x).is_cuda() && (x).scalar_type() == torch::kFloat32, #x " must be a CUDA float32 tensor")
+#define CHECK_CUDA_I32(x) TORCH_CHECK((x).is_cuda() && (x).scalar_type() == torch::kInt32, #x " must be a CUDA int32 tensor")
+#define CHECK_OK(code, what) TORCH_CHECK((code) == 0, what, " failed with code ", (code))
+
+template <typename T>
+T* opt_ptr(const c10::optional<Tensor>& t) { return (t.has_value() && t->defined()) ? t->data_ptr<T>() : nullptr; }
+
+// ---------------------------------------------------------------------------------- fused small round
+// `cfg` carries the scalar fields; tensors are passed explicitly.  Returns (cluster, threads, smem_bytes).
+std::vector<int64_t> fed_round_small(
+    int64_t kind, int64_t din, int64_t hid, int64_t dout, Tensor X, Tensor Y, Tensor nsamp, Tensor W, Tensor theta, int64_t theta_stride,
+    c10::optional<Tensor> opt_m, c10::optional<Tensor> opt_v, c10::optional<Tensor> opt_vmax, Tensor opt_step,
+    c10::optional<Tensor> train_index, c10::optional<Tensor> train_count, c10::optional<Tensor> feat_mask,
+    c10::optional<Tensor> eval_train_model, c10::optional<Tensor> eval_test_model, c10::optional<Tensor> ens_w,
+    c10::optional<Tensor> client_out, c10::optional<Tensor> lr_dev, Tensor metrics, c10::optional<Tensor> timers,
+    std::vector<double> fcfg, std::vector<int64_t> icfg, std::vector<int64_t> peer_inbox, std::vector<int64_t> peer_flags,
+    c10::optional<Tensor> error_flag) {
+    CHECK_CUDA_F32(X); CHECK_CUDA_I32(Y); CHECK_CUDA_I32(nsamp); CHECK_CUDA_F32(W); CHECK_CUDA_F32(theta); CHECK_CUDA_I32(opt_step);
+    CHECK_CUDA_F32(metrics);
+    TORCH_CHECK(X.is_contiguous() && Y.is_contiguous() && nsamp.is_contiguous() && W.is_contiguous() && metrics.is_contiguous(),
+                "fed_round_small: tensors must be contiguous");
+    c10::cuda::CUDAGuard guard(X.device());
+    fdb::RoundParams p{};
+    p.X = X.data_ptr<float>(); p.Y = Y.data_ptr<int>(); p.nsamp = nsamp.data_ptr<int>();
+    p.W = W.data_ptr<float>();
+    p.train_index = opt_ptr<int>(train_index); p.train_count = opt_ptr<int>(train_count);
+    p.feat_mask = opt_ptr<float>(feat_mask);
+    p.eval_train_model = opt_ptr<int>(eval_train_model); p.eval_test_model = opt_ptr<int>(eval_test_model);
+    p.ens_w = opt_ptr<float>(ens_w);
+    p.theta = theta.data_ptr<float>();
+    p.opt_m = opt_ptr<float>(opt_m); p.opt_v = opt_ptr<float>(opt_v); p.opt_vmax = opt_ptr<float>(opt_vmax);
+    p.opt_step = opt_step.data_ptr<int>();
+    p.client_out = opt_ptr<float>(client_out);
+    p.lr_ptr = opt_ptr<float>(lr_dev);
+    p.metrics = metrics.data_ptr<float>();
+    p.timers = (timers.has_value() && timers->defined()) ? reinterpret_cast<long long*>(timers->data_ptr<int64_t>()) : nullptr;
+    // fcfg: lr, wd, beta1, beta2, eps
+    p.lr = (float)fcfg[0]; p.wd = (float)fcfg[1]; p.beta1 = (float)fcfg[2]; p.beta2 = (float)fcfg[3]; p.eps = (float)fcfg[4];
+    // icfg: T1, C, S, M, Lmax, batch, epochs, t_cur, rounds, round0, seed, use_adam, sample_mode, n_mode, recluster, ens_mode,
+    //       skip_aggregate, world, rank, flag_base, cluster, spin_timeout_ms
+    p.T1 = (int)icfg[0]; p.C = (int)icfg[1]; p.S = (int)icfg[2]; p.M = (int)icfg[3]; p.Lmax = (int)icfg[4];
+    p.theta_stride = (int)theta_stride;
+    p.batch_size = (int)icfg[5]; p.epochs = (int)icfg[6]; p.t_cur = (int)icfg[7]; p.rounds = (int)icfg[8]; p.round0 = (int)icfg[9];
+    p.seed = (unsigned)icfg[10]; p.use_adam = (int)icfg[11]; p.sample_mode = (int)icfg[12]; p.n_mode = (int)icfg[13];
+    p.recluster_hard = (int)icfg[14]; p.ens_mode = (int)icfg[15]; p.skip_aggregate = (int)icfg[16];
+    p.world = (int)icfg[17]; p.rank = (int)icfg[18]; p.flag_base = (unsigned)icfg[19];
+    const int cluster = (int)icfg[20];
+    p.spin_timeout_ns = (long long)icfg[21] * 1000000LL;
+    TORCH_CHECK(p.world >= 1 && p.world <= fdb::kMaxPeers, "world must be in [1, 8]");
+    if (p.world > 1) {
+        TORCH_CHECK((int)peer_inbox.size() == p.world && (int)peer_flags.size() == p.world, "need one inbox/flag pointer per rank");
+        for (int g = 0; g < p.world; ++g) {
+            p.inbox[g] = reinterpret_cast<float*>(peer_inbox[g]);
+            p.flags[g] = reinterpret_cast<unsigned*>(peer_flags[g]);
+        }
+        TORCH_CHECK(!p.recluster_hard, "per-round IFCA re-clustering is single-GPU only in this build");
+    }
+    p.error_flag = opt_ptr<int>(error_flag);
+    if (p.use_adam) TORCH_CHECK(p.opt_m && p.opt_v && p.opt_vmax, "adam needs optimizer state tensors");
+    fdb::SmallLaunchInfo info{};
+    const int rc = fdb::fed_round_small_launch((int)kind, (int)din, (int)hid, (int)dout, p, cluster, cur_stream(), &info);
+    TORCH_CHECK(rc != -1, "fed_round_small: MLP shape (", kind, ",", din, ",", hid, ",", dout, ") is not instantiated");
+    TORCH_CHECK(rc != -2, "fed_round_small: shared-memory footprint exceeds 227 KB for this (clients, models) size");
+    CHECK_OK(rc, "fed_round_small launch");
+    return {info.cluster, info.threads, info.smem_bytes};
+}
+
+bool fed_round_small_supported(int64_t kind, int64_t din, int64_t hid, int64_t dout) {
+    return fdb::fed_round_small_supported((int)kind, (int)din, (int)hid, (int)dout) != 0;
+}
+
+std::vector<Tensor> mlp_eval_matrix(Tensor theta, Tensor X, Tensor Y, Tensor nsamp, int64_t kind, int64_t din, int64_t hid, int64_t dout) {
+    CHECK_CUDA_F32(theta); CHECK_CUDA_F32(X); CHECK_CUDA_I32(Y); CHECK_CUDA_I32(nsamp);
+    c10::cuda::CUDAGuard guard(X.device());
+    const int M = (int)theta.size(0), C = (int)X.size(0), S = (int)X.size(1);
+    auto correct = torch::zeros({M, C}, theta.options());
+    auto loss = torch::zeros({M, C}, theta.options());
+    auto sq = torch::zeros({M, C}, theta.options());
+    const int rc = fdb::mlp_eval_matrix_launch((int)kind, (int)din, (int)hid, (int)dout, theta.data_ptr<float>(), (int)theta.stride(0), M,
+                                               X.data_ptr<float>(), Y.data_ptr<int>(), nsamp.data_ptr<int>(), C, S,
+                                               correct.data_ptr<float>(), loss.data_ptr<float>(), sq.data_ptr<float>(), cur_stream());
+    CHECK_OK(rc, "mlp_eval_matrix");
+    return {correct, loss, sq};
+}
+
+// ---------------------------------------------------------------------------------- arena streaming ops
+Tensor cluster_aggregate(Tensor theta, Tensor cp, Tensor n) {
+    CHECK_CUDA_F32(theta); CHECK_CUDA_F32(cp); CHECK_CUDA_F32(n);
+    c10::cuda::CUDAGuard guard(theta.device());
+    const int C = (int)cp.size(0), M = (int)cp.size(1), P = (int)cp.size(2);
+    TORCH_CHECK(theta.size(0) == M && theta.size(1) == P && theta.stride(1) == 1, "theta must be [M, P] with unit inner stride");
+    auto tot = torch::zeros({M}, theta.options());
+    CHECK_OK(fdb::cluster_aggregate_launch(theta.data_ptr<float>(), (int)theta.stride(0), cp.data_ptr<float>(), n.data_ptr<float>(), C, M, P,
+                                           tot.data_ptr<float>(), 0, 0.f, 0.f, 0.9f, 0.999f, 1e-8f, 1, nullptr, nullptr, cur_stream()),
+             "cluster_aggregate");
+    return tot;
+}
+
+Tensor cluster_aggregate_opt(Tensor theta, Tensor cp, Tensor n, int64_t opt_kind, double lr, double momentum, double b1, double b2, double eps,
+                             int64_t step, c10::optional<Tensor> s0, c10::optional<Tensor> s1) {
+    CHECK_CUDA_F32(theta); CHECK_CUDA_F32(cp); CHECK_CUDA_F32(n);
+    c10::cuda::CUDAGuard guard(theta.device());
+    const int C = (int)cp.size(0), M = (int)cp.size(1), P = (int)cp.size(2);
+    auto tot = torch::zeros({M}, theta.options());
+    CHECK_OK(fdb::cluster_aggregate_launch(theta.data_ptr<float>(), (int)theta.stride(0), cp.data_ptr<float>(), n.data_ptr<float>(), C, M, P,
+                                           tot.data_ptr<float>(), (int)opt_kind, (float)lr, (float)momentum, (float)b1, (float)b2, (float)eps,
+                                           (int)step, opt_ptr<float>(s0), opt_ptr<float>(s1), cur_stream()),
+             "cluster_aggregate_opt");
+    return tot;
+}
+
+Tensor weighted_average(Tensor rows, Tensor w) {
+    CHECK_CUDA_F32(rows); CHECK_CUDA_F32(w);
+    c10::cuda::CUDAGuard guard(rows.device());
+    auto out = torch::empty({rows.size(1)}, rows.options());
+    CHECK_OK(fdb::weighted_average_launch(rows.data_ptr<float>(), w.data_ptr<float>(), (int)rows.size(0), rows.size(1), out.data_ptr<float>(),
+                                          cur_stream()), "weighted_average");
+    return out;
+}
+
+void merge_axpby(Tensor theta, int64_t base, int64_t second, double w1, double w2) {
+    CHECK_CUDA_F32(theta);
+    c10::cuda::CUDAGuard guard(theta.device());
+    CHECK_OK(fdb::merge_axpby_launch(theta.data_ptr<float>() + base * theta.stride(0), theta.data_ptr<float>() + second * theta.stride(0),
+                                     (float)w1, (float)w2, theta.size(1), cur_stream()), "merge_axpby");
+}
+
+double mean_sq_diff(Tensor a, Tensor b) {
+    CHECK_CUDA_F32(a); CHECK_CUDA_F32(b);
+    c10::cuda::CUDAGuard guard(a.device());
+    auto out = torch::zeros({1}, a.options().dtype(torch::kFloat64));
+    CHECK_OK(fdb::sq_diff_sum_launch(a.data_ptr<float>(), b.data_ptr<float>(), a.numel(), out.data_ptr<double>(), cur_stream()), "mean_sq_diff");
+    return out.item<double>() / (double)a.numel();
+}
+
+Tensor gossip_mix(Tensor X, Tensor Wm) {
+    CHECK_CUDA_F32(X); CHECK_CUDA_F32(Wm);
+    c10::cuda::CUDAGuard guard(X.device());
+    auto out = torch::empty_like(X);
+    CHECK_OK(fdb::gossip_mix_launch(X.data_ptr<float>(), Wm.data_ptr<float>(), (int)X.size(0), X.size(1), out.data_ptr<float>(), cur_stream()),
+             "gossip_mix");
+    return out;
+}
+
+Tensor robust_clip(Tensor rows, Tensor g, double bound, c10::optional<Tensor> mask) {
+    CHECK_CUDA_F32(rows); CHECK_CUDA_F32(g);
+    c10::cuda::CUDAGuard guard(rows.device());
+    const int R = (int)rows.size(0);
+    auto scratch = torch::zeros({R}, rows.options());
+    auto nrm = torch::zeros({R}, rows.options());
+    CHECK_OK(fdb::robust_clip_launch(rows.data_ptr<float>(), g.data_ptr<float>(), opt_ptr<unsigned char>(mask), R, rows.size(1), (float)bound,
+                                     scratch.data_ptr<float>(), nrm.data_ptr<float>(), cur_stream()), "robust_clip");
+    return nrm;
+}
+
+// ---------------------------------------------------------------------------------- evaluation reductions
+void eval_logits(Tensor logits, Tensor target, Tensor acc) {
+    CHECK_CUDA_F32(logits); CHECK_CUDA_I32(target); CHECK_CUDA_F32(acc);
+    c10::cuda::CUDAGuard guard(logits.device());
+    CHECK_OK(fdb::eval_logits_launch(logits.data_ptr<float>(), target.data_ptr<int>(), (int)logits.size(0), (int)logits.size(1),
+                                     acc.data_ptr<float>(), cur_stream()), "eval_logits");
+}
+Tensor aue_sqerr(Tensor logits, Tensor target) {
+    CHECK_CUDA_F32(logits); CHECK_CUDA_I32(target);
+    c10::cuda::CUDAGuard guard(logits.device());
+    auto out = torch::zeros({}, logits.options());
+    CHECK_OK(fdb::aue_sqerr_launch(logits.data_ptr<float>(), target.data_ptr<int>(), (int)logits.size(0), (int)logits.size(1),
+                                   out.data_ptr<float>(), cur_stream()), "aue_sqerr");
+    return out;
+}
+Tensor ensemble_vote(Tensor preds, Tensor w, int64_t classes) {
+    CHECK_CUDA_I32(preds); CHECK_CUDA_F32(w);
+    c10::cuda::CUDAGuard guard(preds.device());
+    auto out = torch::empty({preds.size(1)}, preds.options());
+    CHECK_OK(fdb::ensemble_vote_launch(preds.data_ptr<int>(), w.data_ptr<float>(), (int)preds.size(0), (int)preds.size(1), (int)classes,
+                                       out.data_ptr<int>(), cur_stream()), "ensemble_vote");
+    return out.to(torch::kInt64);
+}
+Tensor confusion_matrix(Tensor pred, Tensor target, int64_t classes) {
+    CHECK_CUDA_I32(pred); CHECK_CUDA_I32(target);
+    c10::cuda::CUDAGuard guard(pred.device());
+    auto out = torch::zeros({classes, classes}, pred.options());
+    CHECK_OK(fdb::confusion_matrix_launch(pred.data_ptr<int>(), target.data_ptr<int>(), (int)pred.numel(), (int)classes, out.data_ptr<int>(),
+                                          cur_stream()), "confusion_matrix");
+    return out;
+}
+
+// ---------------------------------------------------------------------------------- optimizers
+void adam_amsgrad_rows(Tensor p, Tensor g, Tensor m, Tensor v, Tensor vmax, Tensor steps, double lr, double wd, double b1, double b2, double eps,
+                       c10::optional<Tensor> row_mask) {
+    CHECK_CUDA_F32(p); CHECK_CUDA_F32(g); CHECK_CUDA_F32(m); CHECK_CUDA_F32(v); CHECK_CUDA_F32(vmax); CHECK_CUDA_I32(steps);
+    c10::cuda::CUDAGuard guard(p.device());
+    TORCH_CHECK(p.is_contiguous() && m.is_contiguous() && v.is_contiguous() && vmax.is_contiguous(), "arena rows must be contiguous");
+    const int R = (int)steps.numel();
+    const long long P = p.numel() / R;
+    CHECK_OK(fdb::adam_amsgrad_rows_launch(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
+                                           vmax.data_ptr<float>(), steps.data_ptr<int>(), opt_ptr<unsigned char>(row_mask), R, P, (float)lr,
+                                           (float)wd, (float)b1, (float)b2, (float)eps, cur_stream()), "adam_amsgrad_rows");
+}
+void sgd_rows(Tensor p, Tensor g, double lr, double wd) {
+    CHECK_CUDA_F32(p); CHECK_CUDA_F32(g);
+    c10::cuda::CUDAGuard guard(p.device());
+    CHECK_OK(fdb::sgd_rows_launch(p.data_ptr<float>(), g.data_ptr<float>(), p.numel(), (float)lr, (float)wd, cur_stream()), "sgd_rows");
+}
+
+// ---------------------------------------------------------------------------------- clustering geometry / MPC / misc
+std::vector<Tensor> gram_cosine(Tensor U, double eps) {
+    CHECK_CUDA_F32(U);
+    c10::cuda::CUDAGuard guard(U.device());
+    const int n = (int)U.size(0);
+    auto G = torch::zeros({n, n}, U.options().dtype(torch::kFloat64));
+    const int rc = fdb::gram_launch(U.data_ptr<float>(), n, U.size(1), G.data_ptr<double>(), cur_stream());
+    if (rc == -5) G = torch::matmul(U.to(torch::kFloat64), U.to(torch::kFloat64).t());  // > 22 rows: library GEMM (cold path)
+    else CHECK_OK(rc, "gram");
+    auto nrm = torch::sqrt(torch::diagonal(G));
+    auto S = G / (nrm.unsqueeze(1) * nrm.unsqueeze(0) + eps);
+    return {S, nrm};
+}
+
+Tensor modp_matmul(Tensor A, Tensor B, int64_t p) {
+    TORCH_CHECK(A.is_cuda() && A.scalar_type() == torch::kInt64 && B.scalar_type() == torch::kInt64, "modp_matmul needs CUDA int64");
+    c10::cuda::CUDAGuard guard(A.device());
+    auto C = torch::empty({A.size(0), B.size(1)}, A.options());
+    CHECK_OK(fdb::modp_matmul_launch(reinterpret_cast<const long long*>(A.data_ptr<int64_t>()), reinterpret_cast<const long long*>(B.data_ptr<int64_t>()),
+                                     reinterpret_cast<long long*>(C.data_ptr<int64_t>()), (int)A.size(0), (int)A.size(1), (int)B.size(1), p,
+                                     cur_stream()), "modp_matmul");
+    return C;
+}
+
+std::vector<Tensor> kd_kl_fwd_bwd(Tensor s, Tensor t, double T) {
+    CHECK_CUDA_F32(s); CHECK_CUDA_F32(t);
+    c10::cuda::CUDAGuard guard(s.device());
+    auto loss = torch::zeros({}, s.options());
+    auto grad = torch::empty_like(s);
+    CHECK_OK(fdb::kd_kl_launch(s.data_ptr<float>(), t.data_ptr<float>(), (int)s.size(0), (int)s.size(1), (float)T, loss.data_ptr<float>(),
+                               grad.data_ptr<float>(), cur_stream()), "kd_kl");
+    return {loss, grad};
+}
+
+std::vector<Tensor> vfl_bce_grad(Tensor parts, Tensor y) {
+    CHECK_CUDA_F32(parts); CHECK_CUDA_F32(y);
+    c10::cuda::CUDAGuard guard(parts.device());
+    const int K = (int)parts.size(0), B = (int)parts.size(1);
+    auto loss = torch::zeros({}, parts.options());
+    auto grad = torch::empty({B, 1}, parts.options());
+    CHECK_OK(fdb::vfl_bce_launch(parts.data_ptr<float>(), y.data_ptr<float>(), K, B, loss.data_ptr<float>(), grad.data_ptr<float>(), cur_stream()),
+             "vfl_bce");
+    return {loss, grad};
+}
+
+Tensor group_norm_fwd(Tensor x, int64_t groups, c10::optional<Tensor> w, c10::optional<Tensor> b, double eps) {
+    CHECK_CUDA_F32(x);
+    c10::cuda::CUDAGuard guard(x.device());
+    auto y = torch::empty_like(x);
+    const int N = (int)x.size(0), C = (int)x.size(1);
+    const int HW = (int)(x.numel() / ((int64_t)N * C));
+    CHECK_OK(fdb::group_norm_fwd_launch(x.data_ptr<float>(), y.data_ptr<float>(), opt_ptr<float>(w), opt_ptr<float>(b), N, C, HW, (int)groups,
+                                        (float)eps, cur_stream()), "group_norm_fwd");
+    return y;
+}
+
+Tensor gemm_tn_bias_act(Tensor A, Tensor B, c10::optional<Tensor> bias, bool relu, bool out_fp32) {
+    TORCH_CHECK(A.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm_tn needs CUDA bf16 operands");
+    TORCH_CHECK(A.is_contiguous() && B.is_contiguous() && A.size(1) == B.size(1), "gemm_tn: A [M,K], B [N,K] contiguous");
+    c10::cuda::CUDAGuard guard(A.device());
+    const int M = (int)A.size(0), K = (int)A.size(1), N = (int)B.size(0);
+    auto D = torch::empty({M, N}, A.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+    const float* bp = nullptr;
+    Tensor bias_f;
+    if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
+    const int rc = fdb::gemm_tn_launch(A.data_ptr(), B.data_ptr(), D.data_ptr(), bp, M, N, K, relu ? 1 : 0, out_fp32 ? 1 : 0, cur_stream());
+    CHECK_OK(rc, "gemm_tn (tcgen05)");
+    return D;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    m.def("fed_round_small", &fed_round_small);
+    m.def("fed_round_small_supported", &fed_round_small_supported);
+    m.def("mlp_eval_matrix", &mlp_eval_matrix);
+    m.def("cluster_aggregate", &cluster_aggregate);
+    m.def("cluster_aggregate_opt", &cluster_aggregate_opt);
+    m.def("weighted_average", &weighted_average);
+    m.def("merge_axpby", &merge_axpby);
+    m.def("mean_sq_diff", &mean_sq_diff);
+    m.def("gossip_mix", &gossip_mix);
+    m.def("robust_clip", &robust_clip);
+    m.def("eval_logits", &eval_logits);
+    m.def("aue_sqerr", &aue_sqerr);
+    m.def("ensemble_vote", &ensemble_vote);
+    m.def("confusion_matrix", &confusion_matrix);
+    m.def("adam_amsgrad_rows", &adam_amsgrad_rows);
+    m.def("sgd_rows", &sgd_rows);
+    m.def("gram_cosine", &gram_cosine);
+    m.def("modp_matmul", &modp_matmul);
+    m.def("kd_kl_fwd_bwd", &kd_kl_fwd_bwd);
+    m.def("vfl_bce_grad", &vfl_bce_grad);
+    m.def("group_norm_fwd", &group_norm_fwd);
+    m.def("gemm_tn_bias_act", &gemm_tn_bias_act);
+}

@@ -1,0 +1,38 @@
+// Host-callable launchers of the feddrift_b200 sm_100a kernels (raw pointers; bindings.cpp wraps them).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace fdb {
+// aggregate.cu
+int cluster_aggregate_launch(float* theta, int theta_stride, const float* cp, const float* n, int C, int M, int P, float* tot_out,
+                             int opt_kind, float lr, float momentum, float b1, float b2, float eps, int step, float* s0, float* s1,
+                             cudaStream_t stream);
+int weighted_average_launch(const float* rows, const float* w, int n, long long P, float* out, cudaStream_t stream);
+int merge_axpby_launch(float* base_row, const float* second_row, float w1, float w2, long long P, cudaStream_t stream);
+int sq_diff_sum_launch(const float* a, const float* b, long long P, double* out, cudaStream_t stream);
+int gossip_mix_launch(const float* X, const float* Wm, int n, long long P, float* out, cudaStream_t stream);
+int robust_clip_launch(float* rows, const float* g, const unsigned char* mask, int R, long long P, float bound, float* scratch_nrm2,
+                       float* nrm_out, cudaStream_t stream);
+// eval.cu
+int eval_logits_launch(const float* logits, const int* target, int B, int K, float* acc3, cudaStream_t stream);
+int aue_sqerr_launch(const float* logits, const int* target, int B, int K, float* out1, cudaStream_t stream);
+int ensemble_vote_launch(const int* preds, const float* w, int Kmodels, int B, int classes, int* out, cudaStream_t stream);
+int confusion_matrix_launch(const int* pred, const int* target, int B, int classes, int* out, cudaStream_t stream);
+// optim.cu
+int adam_amsgrad_rows_launch(float* p, const float* g, float* m, float* v, float* vmax, int* steps, const unsigned char* row_mask, int R,
+                             long long P, float lr, float wd, float b1, float b2, float eps, cudaStream_t stream);
+int sgd_rows_launch(float* p, const float* g, long long n, float lr, float wd, cudaStream_t stream);
+// cluster_ops.cu
+int gram_launch(const float* U, int n, long long P, double* G, cudaStream_t stream);
+// mpc.cu
+int modp_matmul_launch(const long long* A, const long long* B, long long* C, int M, int K, int N, long long p, cudaStream_t stream);
+// misc.cu
+int kd_kl_launch(const float* s, const float* t, int B, int K, float T, float* loss1, float* grad_s, cudaStream_t stream);
+int vfl_bce_launch(const float* parts, const float* y, int K, int B, float* loss1, float* grad, cudaStream_t stream);
+int group_norm_fwd_launch(const float* x, float* y, const float* w, const float* b, int N, int C, int HW, int G, float eps,
+                          cudaStream_t stream);
+// gemm_tc.cu : D[M,N] (fp32 or bf16) = act(A[M,K] · B[N,K]^T + bias[N]); A,B bf16 row-major (K contiguous)
+int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
+                   cudaStream_t stream);
+}  // namespace fdb

@@ -1,0 +1,99 @@
+// K14 (FedGKT distillation loss), K15 (vertical-FL logit sum + BCE gradient), K16 (GroupNorm forward).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fdb {
+
+// loss = T² · mean_b Σ_k p_t (log(p_t + 1e-7) - log_softmax(s/T));   grad_s = T · (softmax(s/T) · Σp_t - p_t) / B
+// (reference: fedgkt/utils.py:75-94 KL_Loss — three eager softmax/log kernels + a reduction per batch).
+__global__ void __launch_bounds__(256) kd_kl_kernel(const float* __restrict__ s, const float* __restrict__ t, int B, int K, float T,
+                                                    float* __restrict__ loss1, float* __restrict__ grad_s) {
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float lacc = 0.f;
+    const float invT = 1.f / T;
+    for (int row = blockIdx.x * wpb + wib; row < B; row += gridDim.x * wpb) {
+        const float* zs = s + (size_t)row * K;
+        const float* zt = t + (size_t)row * K;
+        float ms = -INFINITY, mt = -INFINITY;
+        for (int k = lane; k < K; k += 32) { ms = fmaxf(ms, zs[k] * invT); mt = fmaxf(mt, zt[k] * invT); }
+        ms = warp_max(ms); mt = warp_max(mt);
+        float ss = 0.f, st = 0.f;
+        for (int k = lane; k < K; k += 32) { ss += expf(zs[k] * invT - ms); st += expf(zt[k] * invT - mt); }
+        ss = warp_sum(ss); st = warp_sum(st);
+        const float lss = logf(ss);
+        float l = 0.f, sum_pt = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float pt = expf(zt[k] * invT - mt) / st;
+            const float ls = zs[k] * invT - ms - lss;
+            l += pt * (logf(pt + 1e-7f) - ls);
+            sum_pt += pt;
+        }
+        l = warp_sum(l); sum_pt = warp_sum(sum_pt);
+        if (grad_s)
+            for (int k = lane; k < K; k += 32) {
+                const float pt = expf(zt[k] * invT - mt) / st;
+                const float ps = expf(zs[k] * invT - ms) / ss;
+                grad_s[(size_t)row * K + k] = T * (ps * sum_pt - pt) / (float)B;
+            }
+        if (lane == 0) lacc += l;
+    }
+    lacc = block_sum(lacc, red);
+    if (threadIdx.x == 0) atomicAdd(loss1, lacc * T * T / (float)B);
+}
+int kd_kl_launch(const float* s, const float* t, int B, int K, float T, float* loss1, float* grad_s, cudaStream_t stream) {
+    cudaMemsetAsync(loss1, 0, sizeof(float), stream);
+    kd_kl_kernel<<<max(1, min((B + 7) / 8, 148 * 8)), 256, 0, stream>>>(s, t, B, K, T, loss1, grad_s);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// z_b = Σ_k parts[k, b]; loss = mean BCE-with-logits; grad_b = (σ(z_b) - y_b) / B   (guest_trainer.py:85-104)
+__global__ void __launch_bounds__(256) vfl_bce_kernel(const float* __restrict__ parts, const float* __restrict__ y, int Kp, int B,
+                                                      float* __restrict__ loss1, float* __restrict__ grad) {
+    __shared__ float red[32];
+    float lacc = 0.f;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        float z = 0.f;
+        for (int k = 0; k < Kp; ++k) z += parts[(size_t)k * B + b];
+        const float yy = y[b];
+        lacc += fmaxf(z, 0.f) - z * yy + log1pf(expf(-fabsf(z)));
+        grad[b] = (1.f / (1.f + expf(-z)) - yy) / (float)B;
+    }
+    lacc = block_sum(lacc, red);
+    if (threadIdx.x == 0) atomicAdd(loss1, lacc / (float)B);
+}
+int vfl_bce_launch(const float* parts, const float* y, int K, int B, float* loss1, float* grad, cudaStream_t stream) {
+    cudaMemsetAsync(loss1, 0, sizeof(float), stream);
+    vfl_bce_kernel<<<max(1, min((B + 255) / 256, 148 * 4)), 256, 0, stream>>>(parts, y, K, B, loss1, grad);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// GroupNorm forward, NCHW: one CTA per (n, group); two passes over the group's contiguous C/G·HW slab
+// (mean/var with fp32 Welford-free two-moment sum, then normalise + affine).  The reference reshapes into
+// F.batch_norm (model/cv/group_normalization.py:35-40) — 4 eager kernels + 2 reshapes.
+__global__ void __launch_bounds__(256) group_norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
+                                                             const float* __restrict__ b, int C, int HW, int G, float eps) {
+    __shared__ float red[32];
+    const int n = blockIdx.x / G, g = blockIdx.x % G;
+    const int cpg = C / G;
+    const size_t base = ((size_t)n * C + (size_t)g * cpg) * HW;
+    const int len = cpg * HW;
+    float s = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) { const float v = x[base + i]; s += v; s2 = fmaf(v, v, s2); }
+    s = block_sum(s, red); s2 = block_sum(s2, red);
+    const float mean = s / (float)len;
+    const float var = fmaxf(s2 / (float)len - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        const int c = g * cpg + i / HW;
+        const float gamma = w ? w[c] : 1.f, beta = b ? b[c] : 0.f;
+        y[base + i] = (x[base + i] - mean) * rstd * gamma + beta;
+    }
+}
+int group_norm_fwd_launch(const float* x, float* y, const float* w, const float* b, int N, int C, int HW, int G, float eps,
+                          cudaStream_t stream) {
+    group_norm_fwd_kernel<<<N * G, 256, 0, stream>>>(x, y, w, b, C, HW, G, eps);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace fdb

@@ -38,7 +38,7 @@ def build(verbose: bool = False):
     os.makedirs(BUILD_DIR, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
     mod = load(name=EXT_NAME, sources=sources(), extra_cuda_cflags=flags, extra_cflags=["-O3", "-std=c++17"],
-               extra_ldflags=["-lcuda"], build_directory=BUILD_DIR, verbose=verbose, with_cuda=True)
+               build_directory=BUILD_DIR, verbose=verbose, with_cuda=True)
     global _mod, _tried
     _mod, _tried = mod, True
     return mod

@@ -1,0 +1,94 @@
+"""Python side of the fused persistent round kernel (``csrc/fed_round_small.cu``): packs the state dict
+into the launch arguments, keeps the metrics on device, and (multi-GPU) wires the symmetric inbox/flag
+buffers.  One call == one kernel launch == ``rounds`` complete FL rounds."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _ext
+
+KIND_ID = {"lr": 0, "fnn": 1}
+MODE_ID = {"pool": 0, "time": 1, "index": 2}
+LAUNCH_COUNT = {"fed_round_small": 0}
+
+
+def supported(kind: str, din: int, hid: int, dout: int) -> bool:
+    ext = _ext.load()
+    return ext is not None and bool(ext.fed_round_small_supported(KIND_ID[kind], din, hid, dout))
+
+
+def _i32(t: Optional[torch.Tensor], dev) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.to(device=dev, dtype=torch.int32).contiguous()
+
+
+def _f32(t: Optional[torch.Tensor], dev) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.to(device=dev, dtype=torch.float32).contiguous()
+
+
+def prepare(st: Dict) -> Dict:
+    """Build (once per time step) the device views the kernel reads: fp32 X, int32 Y / nsamp / index tables."""
+    cache = st.setdefault("_native", {})
+    if not cache:
+        theta = st["theta"]
+        dev = theta.device
+        X = st["X"]
+        T1, C, S = X.shape[0], X.shape[1], X.shape[2]
+        cache["X"] = X.reshape(T1, C, S, -1).to(torch.float32).contiguous()
+        cache["Y"] = _i32(st["Y"], dev)
+        cache["nsamp"] = _i32(st["nsamp"], dev)
+        cache["train_index"] = _i32(st.get("train_index"), dev)
+        cache["train_count"] = _i32(st.get("train_count"), dev)
+        cache["feat_mask"] = _f32(st.get("feat_mask"), dev)
+        cache["eval_train_model"] = _i32(st.get("eval_train_model"), dev)
+        cache["eval_test_model"] = _i32(st.get("eval_test_model"), dev)
+        cache["counts"] = torch.stack(
+            [cache["nsamp"][st["t_cur"]],
+             cache["nsamp"][st["t_cur"] + 1] if st["t_cur"] + 1 < T1 else torch.zeros_like(cache["nsamp"][0])],
+            dim=1).float()
+    return cache
+
+
+def run_native(st: Dict, rounds: int, metrics_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    ext = _ext.load(required=True)
+    theta = st["theta"]
+    dev = theta.device
+    X, W = st["X"], st["W"]
+    T1, C, S = X.shape[0], X.shape[1], X.shape[2]
+    M = theta.shape[0]
+    cache = prepare(st)
+    if not (W.is_cuda and W.dtype == torch.float32 and W.is_contiguous()):
+        st["W"] = W = W.to(device=dev, dtype=torch.float32).contiguous()
+    ens_w = _f32(st.get("ens_w"), dev)
+    use_adam = st.get("optimizer", "adam") != "sgd"
+    if metrics_out is None:
+        metrics_out = torch.zeros(rounds, C, 4, dtype=torch.float32, device=dev)
+    lr = st["lr"]
+    lr_dev = lr if isinstance(lr, torch.Tensor) else None
+    Lmax = int(cache["train_index"].shape[2]) if cache["train_index"] is not None else 0
+    mg = st.get("multi_gpu")  # dict(world, rank, inbox_ptrs, flag_ptrs, flag_base, error_flag)
+    world = int(mg["world"]) if mg else 1
+    icfg = [T1, C, S, M, Lmax, int(st["batch_size"]), int(st["epochs"]), int(st["t_cur"]), int(rounds), int(st["round0"]),
+            int(st["seed"]) & 0xFFFFFFFF, int(use_adam), MODE_ID[st.get("sample_mode", "pool")],
+            1 if st.get("n_mode", "batches") == "samples" else 0, int(bool(st.get("recluster_hard", False))),
+            int(st.get("ens_mode", 0) or 0), int(bool(st.get("skip_aggregate", False))), world,
+            int(mg["rank"]) if mg else 0, int(mg["flag_base"]) if mg else 0, int(st.get("cluster", 0)),
+            int(st.get("spin_timeout_ms", 2000))]
+    fcfg = [float(lr) if lr_dev is None else 0.0, float(st["wd"]), 0.9, 0.999, 1e-8]
+    info = ext.fed_round_small(
+        KIND_ID[st["kind"]], int(st["din"]), int(st["hid"]), int(st["dout"]), cache["X"], cache["Y"], cache["nsamp"], W, theta,
+        int(st.get("theta_stride", theta.stride(0))), st.get("opt_m"), st.get("opt_v"), st.get("opt_vmax"), st["opt_step"],
+        cache["train_index"], cache["train_count"], cache["feat_mask"], cache["eval_train_model"], cache["eval_test_model"],
+        ens_w, st.get("client_out"), lr_dev, metrics_out, st.get("timers"), fcfg, icfg,
+        list(mg["inbox_ptrs"]) if mg else [], list(mg["flag_ptrs"]) if mg else [], mg.get("error_flag") if mg else None)
+    if mg:
+        mg["flag_base"] = int(mg["flag_base"]) + rounds
+    LAUNCH_COUNT["fed_round_small"] += 1
+    st["round0"] = int(st["round0"]) + rounds
+    st["_launch_info"] = info
+    return {"metrics": metrics_out, "counts": cache["counts"]}

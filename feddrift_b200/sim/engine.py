@@ -86,6 +86,7 @@ class DriftSim:
         self.global_round = 0
         self.history: List[Dict] = []
         self._small: Optional[Dict] = None
+        self._last_counts = None
         self.clients = ClientArena(self.C, self.M, self.bank.P, self.device,
                                    adam=(args.client_optimizer != "sgd"))
         self.timings = {"cluster_s": 0.0, "rounds_s": 0.0}
@@ -117,6 +118,7 @@ class DriftSim:
         self.clients.reset_optimizer()
         self.algo.begin_step(t)
         self._small = None
+        self._counts_host = None
         self.timings["cluster_s"] += time.perf_counter() - t0
 
     def end_time_step(self) -> None:
@@ -178,6 +180,86 @@ class DriftSim:
             self.algo.after_block(self.t, self.round_in_step)
         self.timings["rounds_s"] += time.perf_counter() - t0
         return last
+
+    # ------------------------------------------------------------------ device-only / end-to-end single rounds
+    def run_rounds_device(self, n: int) -> torch.Tensor:
+        """Launch ``n`` fused rounds and leave the per-round metrics ON DEVICE (no host sync, no logging).
+        Returns the device metrics view ``[n, C, 4]``."""
+        st = self._small_state()
+        st["round0"] = self.round_in_step
+        if self.device.type == "cuda":
+            from ..ops import small_round
+            buf = getattr(self, "_metrics_buf", None)
+            if buf is None or buf.shape[0] < n:
+                buf = self._metrics_buf = torch.zeros(max(n, 64), self.C, 4, dtype=torch.float32, device=self.device)
+            out = small_round.run_native(st, n, buf[:n])
+        else:
+            out = ops.fed_round_small(st, n)
+        self.round_in_step += n
+        self.global_round += n
+        self._last_counts = out["counts"]
+        return out["metrics"]
+
+    def run_round_device(self) -> torch.Tensor:
+        return self.run_rounds_device(1)
+
+    def make_host_round_inputs(self) -> Dict[str, torch.Tensor]:
+        """Pinned host copies of what one round consumes: the clients' time-t training data and time-(t+1)
+        test data (features + labels) — in a deployment these arrive from the data plane every round."""
+        t = self.t
+        hi = min(t + 2, self.data_host.steps)
+        pin = self.device.type == "cuda"
+        X = self.data_host.X[t:hi].reshape(hi - t, self.C, self.data_host.X.shape[2], -1).float().contiguous()
+        Y = self.data_host.Y[t:hi].to(torch.int32).contiguous()
+        out = {"X": X.pin_memory() if pin else X, "Y": Y.pin_memory() if pin else Y}
+        self._host_metrics = torch.zeros(self.C, 4, dtype=torch.float32)
+        if pin:
+            self._host_metrics = self._host_metrics.pin_memory()
+        return out
+
+    def host_round_bytes(self):
+        hi = min(self.t + 2, self.data_host.steps)
+        n = (hi - self.t) * self.C * self.data_host.X.shape[2]
+        return int(n * (self.data_host.feature_num * 4 + 4)), int(self.C * 4 * 4)
+
+    def run_round(self, host_inputs: Optional[Dict[str, torch.Tensor]] = None, log: bool = False) -> Dict:
+        """ONE end-to-end FL round through the public API: (optional) host→device copy of the round's inputs
+        from pinned memory, the fused round kernel, device→host copy of the per-client metrics, host reduction.
+        Synchronises (the caller gets real numbers back)."""
+        st = self._small_state()
+        t = self.t
+        if host_inputs is not None:
+            if self.device.type == "cuda":
+                from ..ops import small_round
+                cache = small_round.prepare(st)
+                hi = t + host_inputs["X"].shape[0]
+                cache["X"][t:hi].copy_(host_inputs["X"], non_blocking=True)
+                cache["Y"][t:hi].copy_(host_inputs["Y"], non_blocking=True)
+            else:
+                hi = t + host_inputs["X"].shape[0]
+                st["X"][t:hi].copy_(host_inputs["X"].reshape(st["X"][t:hi].shape))
+                st["Y"][t:hi].copy_(host_inputs["Y"])
+        met = self.run_rounds_device(1)
+        hm = getattr(self, "_host_metrics", None)
+        if hm is None:
+            hm = self._host_metrics = torch.zeros(self.C, 4, dtype=torch.float32)
+        hm.copy_(met[0], non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        m = hm.numpy()
+        if getattr(self, "_counts_host", None) is None:
+            self._counts_host = self._last_counts.cpu()
+        cnt = self._counts_host
+        c = cnt.numpy()
+        ntr, nte = max(float(c[:, 0].sum()), 1.0), max(float(c[:, 1].sum()), 1.0)
+        res = {"round": self.round_in_step - 1, "iteration": t, "train_acc": float(m[:, 0].sum()) / ntr,
+               "train_loss": float(m[:, 1].sum()) / ntr, "test_acc": float(m[:, 2].sum()) / nte,
+               "test_loss": float(m[:, 3].sum()) / nte}
+        if log:
+            for k_, key in (("train_acc", "Train/Acc"), ("train_loss", "Train/Loss"), ("test_acc", "Test/Acc"),
+                            ("test_loss", "Test/Loss")):
+                self.sink.log({key: res[k_], "round": res["round"]})
+        return res
 
     def _flush_metrics(self, out: Dict[str, torch.Tensor], r0: int, n: int) -> Dict:
         """One D2H copy per block; emits the reference's wandb keys for every tested round."""

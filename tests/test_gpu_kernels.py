@@ -1,0 +1,135 @@
+"""GPU numerics of the streaming / reduction / GEMM kernels vs plain PyTorch fp32 references."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from feddrift_b200 import ops
+from feddrift_b200.ops import reference as ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(10, 4, 38), (32, 3, 4096), (7, 2, 100003)])
+def test_cluster_aggregate(shape):
+    C, M, P = shape
+    cp = torch.randn(C, M, P)
+    n = torch.randint(0, 5, (C, M)).float()
+    n[:, 0] = 0  # an unused model must stay untouched
+    theta = torch.randn(M, P)
+    th_ref = theta.clone()
+    ref.cluster_aggregate_(th_ref, cp, n)
+    th = theta.cuda()
+    ops.cluster_aggregate_(th, cp.cuda(), n.cuda())
+    assert torch.allclose(th.cpu(), th_ref, rtol=1e-5, atol=1e-5)
+
+
+def test_weighted_average_and_merge_and_gossip():
+    rows, w = torch.randn(9, 5000), torch.rand(9)
+    assert torch.allclose(ops.weighted_average(rows.cuda(), w.cuda()).cpu(), ref.weighted_average(rows, w), atol=1e-5)
+    th = torch.randn(4, 777)
+    a = th.clone()
+    ref.merge_axpby_(a, 0, 2, 0.3, 0.7)
+    b = th.cuda()
+    ops.merge_axpby_(b, 0, 2, 0.3, 0.7)
+    assert torch.allclose(b.cpu(), a, atol=1e-6)
+    X, Wm = torch.randn(8, 3000), torch.rand(8, 8)
+    Wm = Wm / Wm.sum(1, keepdim=True)
+    assert torch.allclose(ops.gossip_mix(X.cuda(), Wm.cuda()).cpu(), Wm @ X, atol=1e-5)
+
+
+def test_robust_clip_and_ada_stats():
+    rows, g = torch.randn(6, 10000) * 3, torch.randn(10000)
+    a = rows.clone()
+    n_ref = ref.robust_clip_(a, g, 5.0)
+    b = rows.cuda()
+    n_gpu = ops.robust_clip_(b, g.cuda(), 5.0)
+    assert torch.allclose(b.cpu(), a, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(n_gpu.cpu(), n_ref, rtol=1e-4)
+    x, y = torch.randn(12345), torch.randn(12345)
+    assert abs(ops.ada_stats(x.cuda(), y.cuda()) - ref.ada_stats(x, y)) < 1e-5
+
+
+def test_adam_amsgrad_rows_matches_torch_optim():
+    R, P = 5, 1000
+    p0 = torch.randn(R, P)
+    ps = [torch.nn.Parameter(p0[r].clone()) for r in range(R)]
+    opts = [torch.optim.Adam([q], lr=0.01, weight_decay=1e-3, amsgrad=True) for q in ps]
+    p = p0.cuda()
+    m, v, vm = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    steps = torch.zeros(R, dtype=torch.int32, device="cuda")
+    for it in range(4):
+        g = torch.randn(R, P)
+        for r in range(R):
+            ps[r].grad = g[r].clone()
+            opts[r].step()
+        ops.adam_amsgrad_rows_(p, g.cuda(), m, v, vm, steps, 0.01, 1e-3)
+    want = torch.stack([q.detach() for q in ps])
+    assert torch.allclose(p.cpu(), want, rtol=1e-4, atol=1e-6)
+    assert int(steps[0]) == 4
+
+
+def test_eval_reductions():
+    logits, y = torch.randn(777, 90), torch.randint(0, 90, (777,))
+    acc = ops.eval_logits(logits.cuda(), y.cuda()).cpu()
+    r = ref.eval_logits(logits, y)
+    assert acc[0] == r[0] and abs(acc[1] - r[1]) < 1e-2 * 777 * 1e-2 + 1e-1 and acc[2] == 777
+    assert abs(float(ops.aue_sqerr(logits.cuda(), y.cuda())) - float(ref.aue_sqerr(logits, y))) < 1e-2
+    preds, w = torch.randint(0, 5, (4, 300)), torch.rand(4)
+    assert torch.equal(ops.ensemble_vote(preds.cuda(), w.cuda(), 5).cpu(), ref.ensemble_vote(preds, w, 5))
+    pr, tg = torch.randint(0, 10, (5000,)), torch.randint(0, 10, (5000,))
+    assert torch.equal(ops.confusion_matrix(pr.cuda(), tg.cuda(), 10).cpu(), ref.confusion_matrix(pr, tg, 10))
+
+
+def test_gram_cosine_and_modp_and_misc():
+    U = torch.randn(7, 50000)
+    S, nrm = ops.gram_cosine(U.cuda())
+    S2, nrm2 = ref.gram_cosine(U)
+    assert torch.allclose(S.cpu(), S2, atol=1e-5) and torch.allclose(nrm.cpu(), nrm2, rtol=1e-5)
+    p = 2 ** 31 - 1
+    A, B = torch.randint(0, p, (17, 33)), torch.randint(0, p, (33, 9))
+    want = torch.tensor([[sum(int(A[i, k]) * int(B[k, j]) for k in range(33)) % p for j in range(9)] for i in range(17)])
+    assert torch.equal(ops.modp_matmul(A.cuda(), B.cuda(), p).cpu(), want)
+    s, t = torch.randn(64, 10, requires_grad=True), torch.randn(64, 10)
+    l_ref = ref.kd_kl_loss(s, t, 3.0)
+    l_ref.backward()
+    sg = s.detach().cuda().requires_grad_(True)
+    l_gpu = ops.kd_kl_loss(sg, t.cuda(), 3.0)
+    l_gpu.backward()
+    assert abs(float(l_gpu) - float(l_ref)) < 1e-4 and torch.allclose(sg.grad.cpu(), s.grad, atol=1e-5)
+    parts, y = torch.randn(3, 128, 1), torch.randint(0, 2, (128, 1)).float()
+    l1, g1 = ref.vfl_bce_grad(parts, y)
+    l2, g2 = ops.vfl_bce_grad(parts.cuda(), y.cuda())
+    assert abs(float(l1) - float(l2)) < 1e-5 and torch.allclose(g2.cpu(), g1, atol=1e-6)
+    x, w, b = torch.randn(4, 32, 8, 8), torch.randn(32), torch.randn(32)
+    with torch.no_grad():
+        assert torch.allclose(ops.group_norm(x.cuda(), 4, w.cuda(), b.cuda()).cpu(), F.group_norm(x, 4, w, b), atol=1e-4)
+
+
+@pytest.mark.parametrize("mnk", [(128, 128, 64), (500, 1568, 784), (64, 10, 1568), (333, 128, 9216), (256, 512, 3136)])
+def test_tcgen05_gemm(mnk):
+    from feddrift_b200.ops import _ext
+    M, N, K = mnk
+    A = (torch.randn(M, K) * 0.5).bfloat16().cuda()
+    B = (torch.randn(N, K) * 0.5).bfloat16().cuda()
+    bias = torch.randn(N).cuda()
+    D = _ext.load().gemm_tn_bias_act(A, B, bias, True, True)
+    want = torch.relu(A.float() @ B.float().t() + bias)
+    err = (D - want).abs().max().item()
+    assert err < 2e-2 * max(1.0, want.abs().max().item()), err
+
+
+def test_tclinear_forward_backward():
+    from feddrift_b200.ops.linear import TcLinear
+    torch.manual_seed(0)
+    lin = TcLinear(784, 1568, activation="relu").cuda()
+    x = torch.randn(100, 784, device="cuda", requires_grad=True)
+    y = lin(x)
+    y.square().mean().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    yr = torch.relu(F.linear(xr, lin.weight.detach(), lin.bias.detach()))
+    wr = lin.weight.detach().clone().requires_grad_(True)
+    yr2 = torch.relu(F.linear(xr, wr, lin.bias.detach()))
+    yr2.square().mean().backward()
+    assert torch.allclose(y, yr, rtol=3e-2, atol=3e-2)
+    assert torch.allclose(x.grad, xr.grad, rtol=5e-2, atol=2e-3)
+    assert torch.allclose(lin.weight.grad, wr.grad, rtol=5e-2, atol=2e-3)

@@ -1,0 +1,41 @@
+"""One MPI-rank worth of the UNMODIFIED reference (``fedml_experiments/distributed/fedavg_cont_ens/main_fedavg.py``)
+executed with ``runpy`` under the shims.  Rank 0 gets a timing probe: ``test_on_all_clients`` is the last thing the
+server does in a round (``FedAvgEnsServerManager.py:46-47``), so wrapping it (instrumentation only — the reference
+code itself is untouched) yields an end-of-round timestamp after a ``torch.cuda.synchronize``."""
+import json
+import os
+import runpy
+import sys
+import time
+
+
+def main():
+    ref_root = os.environ["FDB_REF_ROOT"]
+    exp_dir = os.path.join(ref_root, "fedml_experiments", "distributed", "fedavg_cont_ens")
+    os.chdir(exp_dir)
+    rank = int(os.environ.get("RANK", "0"))
+    out_path = os.environ.get("FDB_REF_TIMING", "")
+    if rank == 0 and out_path:
+        import torch
+        from fedml_api.distributed.fedavg_ens import FedAvgEnsAggregatorSoftCluster as mod
+        cls = mod.FedAvgEnsAggregatorSoftCluster
+        orig = cls.test_on_all_clients
+        stamps = []
+
+        def timed(self, round_idx):
+            r = orig(self, round_idx)
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            stamps.append(time.perf_counter())
+            with open(out_path, "w") as fh:
+                json.dump({"round_end": stamps}, fh)
+            return r
+
+        cls.test_on_all_clients = timed
+    script = os.environ.get("FDB_REF_SCRIPT", "main_fedavg.py")
+    sys.argv = [script] + sys.argv[1:]
+    runpy.run_path(os.path.join(exp_dir, script), run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+"""Reference arm of bench.py: run the unmodified FedDrift reference (installed in ``baseline/_ref``) on the headline
+config through its own stock path — ``prepare_data.py`` then ``main_fedavg.py`` once per time step with
+``WORKER_NUM + 1`` ranks (what ``run_fedavg_distributed_pytorch.sh:55-84`` does with mpirun) — and report FL
+rounds/sec of the timed time step.  MPI is provided by ``baseline/shims/mpi4py`` (torch.distributed/gloo p2p).
+"""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+import socket
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+SHIMS = os.path.join(HERE, "shims")
+EXP = os.path.join(REF, "fedml_experiments", "distributed", "fedavg_cont_ens")
+CLIENTS = 10
+BENCH_TIME_STEP = 5
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _env(extra=None):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([SHIMS, REF, env.get("PYTHONPATH", "")])
+    env.update({"FDB_REF_SHIMS": "1", "FDB_REF_ROOT": REF, "WANDB_MODE": "disabled", "WANDB_SILENT": "true",
+                "MASTER_ADDR": "127.0.0.1", "OMP_NUM_THREADS": "1"})
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_PORT", "TORCHELASTIC_RUN_ID", "GROUP_RANK", "LOCAL_WORLD_SIZE",
+              "ROLE_RANK", "ROLE_WORLD_SIZE", "TORCHELASTIC_RESTART_COUNT", "TORCHELASTIC_MAX_RESTARTS"):
+        env.pop(k, None)
+    if extra:
+        env.update(extra)
+    return env
+
+
+def _common_flags(gpus: int, rounds: int, it: int, total_iter: int):
+    return ["--gpu_server_num", "1", "--gpu_num_per_server", str(max(gpus, 1)), "--model", "fnn", "--dataset", "sea",
+            "--data_dir", "./../../../data/", "--noise_prob", "0", "--client_num_in_total", str(CLIENTS),
+            "--client_num_per_round", str(CLIENTS), "--comm_round", str(rounds), "--epochs", "5", "--batch_size", "500",
+            "--lr", "0.01", "--ci", "0", "--total_train_iteration", str(total_iter), "--curr_train_iteration", str(it),
+            "--concept_num", "4", "--reset_models", "0", "--drift_together", "0", "--report_client", "1",
+            "--retrain_data", "win-1", "--concept_drift_algo", "softcluster", "--concept_drift_algo_arg", "H_A_C_1_10_0",
+            "--time_stretch", "1", "--dummy_arg", "0", "--change_points", "A"]
+
+
+def _run_time_step(gpus: int, rounds: int, it: int, total_iter: int, timing_path: str, timeout_s: float):
+    """Spawn WORKER_NUM+1 ranks (rank 0 = server).  The job ends when the server calls MPI Abort."""
+    port = _free_port()
+    world = CLIENTS + 1
+    procs = []
+    if os.path.exists(timing_path):
+        os.remove(timing_path)
+    for rank in range(world):
+        env = _env({"RANK": str(rank), "WORLD_SIZE": str(world), "MASTER_PORT": str(port),
+                    "FDB_REF_TIMING": timing_path if rank == 0 else ""})
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "ref_rank.py")] +
+                                      _common_flags(gpus, rounds, it, total_iter), env=env, cwd=EXP,
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.PIPE if rank == 0 else subprocess.DEVNULL))
+    t0 = time.time()
+    err = b""
+    try:
+        _, err = procs[0].communicate(timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        pass
+    finally:
+        for p in procs:  # exact PIDs we started; never pattern kills
+            if p.poll() is None:
+                p.kill()
+        for p in procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:
+                pass
+    stamps = []
+    if os.path.exists(timing_path):
+        with open(timing_path) as fh:
+            stamps = json.load(fh)["round_end"]
+    return stamps, time.time() - t0, err.decode(errors="replace")[-2000:] if err else ""
+
+
+def main(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:  # under torchrun only rank 0 drives the reference job (it spawns its own 11 ranks)
+        return
+    if not os.path.isdir(os.path.join(REF, "fedml_api")):
+        from baseline import install_reference
+        if install_reference.main() != 0 or not os.path.isdir(os.path.join(REF, "fedml_api")):
+            print(json.dumps({"impl": "reference", "unavailable": "reference not installed in baseline/_ref "
+                              "(pip install of /root/reference fails: no setup.py/pyproject.toml; see DESIGN.md)"}))
+            return
+    K, W = int(args.steps), max(int(args.warmup), 1)
+    budget_s = float(os.environ.get("FDB_REF_MAX_SECONDS", "1500"))
+    per_round_est = 0.3 * CLIENTS + 1.0  # ≥ 0.3 s sleep per ingested upload (com_manager.py:71-79)
+    K_eff = K
+    if (W + K) * per_round_est > budget_s:
+        K_eff = max(3, int(budget_s / per_round_est) - W)
+    total_iter = 10
+    # stale state from a previous run must not leak in
+    for f in ("model_params.pt", "sc_state.pkl", "output.log"):
+        p = os.path.join(EXP, f)
+        if os.path.exists(p):
+            os.remove(p)
+    # 1) stock data preparation
+    prep = subprocess.run([sys.executable, os.path.join(HERE, "ref_rank.py"), "--dataset", "sea", "--data_dir",
+                           "./../../../data/", "--sample_num", "100", "--noise_prob", "0", "--partition_method", "homo",
+                           "--client_num_in_total", str(CLIENTS), "--client_num_per_round", str(CLIENTS), "--batch_size",
+                           "500", "--train_iteration", str(total_iter), "--drift_together", "0", "--time_stretch", "1",
+                           "--change_points", "A"], env=_env({"FDB_REF_SCRIPT": "prepare_data.py", "RANK": "0",
+                                                              "WORLD_SIZE": "1"}), cwd=EXP, capture_output=True, text=True)
+    if prep.returncode != 0:
+        print(json.dumps({"impl": "reference", "unavailable": "prepare_data.py failed: " + prep.stderr[-300:].replace("\n", " ")}))
+        return
+    timing = os.path.join(HERE, "_ref_timing.json")
+    # 2) untimed: time steps 0..4 with one round each so that step 5 sees real cluster state
+    for it in range(BENCH_TIME_STEP):
+        stamps, wall, err = _run_time_step(args.gpus, 1, it, total_iter, timing, 300)
+        if not stamps:
+            print(json.dumps({"impl": "reference", "unavailable": f"time step {it} produced no round: {err[-300:]}".replace("\n", " ")}))
+            return
+    # 3) timed time step: W warm-up rounds then K timed rounds
+    stamps, wall, err = _run_time_step(args.gpus, W + K_eff, BENCH_TIME_STEP, total_iter, timing,
+                                       (W + K_eff) * per_round_est * 2 + 120)
+    if len(stamps) < W + 2:
+        print(json.dumps({"impl": "reference", "unavailable": f"timed step finished {len(stamps)} rounds: {err[-300:]}".replace("\n", " ")}))
+        return
+    done = min(len(stamps) - W, K_eff)
+    elapsed = stamps[W + done - 1] - stamps[W - 1]
+    value = done / elapsed
+    out = {"metric": "fl_rounds_per_sec", "value": value, "unit": "rounds/s", "n_gpus": int(args.gpus), "steps": done,
+           "warmup": W, "ms_per_step": 1e3 * elapsed / done, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "config": {"model": "FeedForwardNN(3,6,2) SEA-4", "clients": CLIENTS, "local_steps": 5, "model_slots": 4,
+                      "algo": "softcluster H_A_C_1_10_0 (FedDrift), change points A", "time_step": BENCH_TIME_STEP,
+                      "parallelism": f"{CLIENTS}+1 ranks round-robin on {args.gpus} GPU(s) (init_training_device)",
+                      "transport": "mpi4py shim over torch.distributed gloo p2p (pickled CPU state_dicts)",
+                      "timing": "server wall clock at end of test_on_all_clients after cuda synchronize",
+                      "requested_steps": K},
+           "e2e": {"value": value, "unit": "rounds/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None},
+           "gpu_launches": None, "impl": "reference"}
+    print(json.dumps(out))

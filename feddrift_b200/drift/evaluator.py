@@ -64,7 +64,7 @@ class Evaluator:
                                           s["kind"], s["in"], s["hidden"], s["out"])
             ns = self.data.nsamp[t].clamp(min=1).to(corr.device).float()
             acc = (corr / ns).double().cpu().numpy()
-            acc[:, (self.data.nsamp[t] == 0).numpy()] = 0.0
+            acc[:, (self.data.nsamp[t] == 0).cpu().numpy()] = 0.0
             return acc
         out = np.zeros((len(model_ids), C))
         for r, m in enumerate(model_ids):

@@ -108,7 +108,7 @@ class DriftSurfState:
         bank.theta[scratch_row].copy_(snap.to(bank.device))
         acc = ev.acc_matrix([scratch_row], t)[0]
         bank.theta[scratch_row].copy_(saved)
-        ns = ev.data.nsamp[t].double().numpy()
+        ns = ev.data.nsamp[t].double().cpu().numpy()
         return float((acc * ns).sum() / max(ns.sum(), 1.0))
 
     def _append(self, key: str, it: int) -> None:

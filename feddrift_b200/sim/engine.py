@@ -87,6 +87,7 @@ class DriftSim:
         self.history: List[Dict] = []
         self._small: Optional[Dict] = None
         self._last_counts = None
+        self.multi = None
         self.clients = ClientArena(self.C, self.M, self.bank.P, self.device,
                                    adam=(args.client_optimizer != "sgd"))
         self.timings = {"cluster_s": 0.0, "rounds_s": 0.0}
@@ -151,6 +152,8 @@ class DriftSim:
                     self._small[k] = plan[k]
             if self._small["optimizer"] == "sgd":
                 self._small["wd"] = 0.0
+            if getattr(self, "multi", None) is not None:
+                self._small["multi_gpu"] = self.multi
             if self.bank.stride != self.bank.P:
                 self._small["theta_stride"] = self.bank.stride
         return self._small
@@ -240,6 +243,9 @@ class DriftSim:
                 st["X"][t:hi].copy_(host_inputs["X"].reshape(st["X"][t:hi].shape))
                 st["Y"][t:hi].copy_(host_inputs["Y"])
         met = self.run_rounds_device(1)
+        if getattr(self, "multi", None) is not None:
+            import torch.distributed as dist
+            dist.all_reduce(met)
         hm = getattr(self, "_host_metrics", None)
         if hm is None:
             hm = self._host_metrics = torch.zeros(self.C, 4, dtype=torch.float32)
@@ -263,6 +269,11 @@ class DriftSim:
 
     def _flush_metrics(self, out: Dict[str, torch.Tensor], r0: int, n: int) -> Dict:
         """One D2H copy per block; emits the reference's wandb keys for every tested round."""
+        if getattr(self, "multi", None) is not None:  # cold path: every rank only evaluated its own clients
+            import torch.distributed as dist
+            out = dict(out)
+            out["metrics"] = out["metrics"].clone()
+            dist.all_reduce(out["metrics"])
         met = out["metrics"].detach().to("cpu", torch.float64).numpy()  # [n, C, 4]
         cnt = out["counts"].detach().to("cpu", torch.float64).numpy()   # [C, 2]
         a = self.args

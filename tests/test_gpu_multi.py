@@ -1,0 +1,43 @@
+"""Multi-GPU: the fused round kernel with NVLink peer-inbox aggregation must reproduce the single-GPU result."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+WORKER = r'''
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["FDB_ROOT"])
+from feddrift_b200.sim import DriftSim, make_args
+from feddrift_b200.parallel.symm import attach_multi_gpu, check_error
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+args = make_args(comm_round=6, total_train_iteration=3)
+sim = DriftSim(args, device=f"cuda:{rank}")
+attach_multi_gpu(sim, world, rank)
+out = sim.run()
+check_error(sim)
+ref = DriftSim(make_args(comm_round=6, total_train_iteration=3), device=f"cuda:{rank}")
+oref = ref.run()
+err = (sim.bank.theta - ref.bank.theta).abs().max().item()
+ok = err < 1e-4 and abs(out["history"][-1]["train_acc"] - oref["history"][-1]["train_acc"]) < 0.02
+print(json.dumps({"rank": rank, "err": err, "ok": bool(ok), "acc": out["history"][-1]["train_acc"]}))
+dist.destroy_process_group()
+sys.exit(0 if ok else 3)
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_gpu_matches_single_gpu(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FDB_ROOT=root)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]

@@ -57,11 +57,11 @@ class World:
                 if not self.order:
                     break
                 dst = self.order.popleft()
+            msg = _STOP
             try:
-                msg = self.mailboxes[dst].get_nowait()
+                while msg is _STOP:  # stale stop sentinels of a finished manager must not shift the FIFO
+                    msg = self.mailboxes[dst].get_nowait()
             except queue.Empty:
-                continue
-            if msg is _STOP:
                 continue
             cm = self.managers.get(dst)
             if cm is None or not cm.is_running:
@@ -88,6 +88,16 @@ class InProcCommunicationManager(BaseCommunicationManager):
         self.rank = rank
         self.is_running = True
         world.managers[rank] = self
+        box, keep = world.mailboxes[rank], []
+        while True:  # a new manager on this rank starts with a mailbox free of old stop sentinels
+            try:
+                item = box.get_nowait()
+            except queue.Empty:
+                break
+            if item is not _STOP:
+                keep.append(item)
+        for item in keep:
+            box.put(item)
 
     def send_message(self, msg: Message) -> None:
         self.world.post(msg)

@@ -549,7 +549,7 @@ class ClusterFLAlgo(DriftAlgo):
         for i in g2:
             self.assign[members[i]] = 1
         self.sim.bank.copy(1, 0)
-        self.sim._small = None  # re-plan with the new assignment
+        self.sim.invalidate_plan()  # re-plan with the new assignment
         return True
 
 

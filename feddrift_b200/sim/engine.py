@@ -86,6 +86,7 @@ class DriftSim:
         self.global_round = 0
         self.history: List[Dict] = []
         self._small: Optional[Dict] = None
+        self._plan: Optional[Dict] = None
         self._last_counts = None
         self.multi = None
         self.clients = ClientArena(self.C, self.M, self.bank.P, self.device,
@@ -119,6 +120,7 @@ class DriftSim:
         self.clients.reset_optimizer()
         self.algo.begin_step(t)
         self._small = None
+        self._plan = None
         self._counts_host = None
         self.timings["cluster_s"] += time.perf_counter() - t0
 
@@ -129,10 +131,20 @@ class DriftSim:
             ckpt.save(self, os.path.join(cdir, f"step_{self.t:04d}.fdck"))
 
     # ------------------------------------------------------------------ rounds
+    def current_plan(self) -> Dict:
+        """The algorithm's training plan for the current time step (built once; sample lists are randomised)."""
+        if self._plan is None:
+            self._plan = self.algo.plan(self.t)
+        return self._plan
+
+    def invalidate_plan(self) -> None:
+        self._plan = None
+        self._small = None
+
     def _small_state(self) -> Dict:
         """Device-side argument block of the fused round kernel for the current time step."""
         if self._small is None:
-            a, s, plan = self.args, self.spec, self.algo.plan(self.t)
+            a, s, plan = self.args, self.spec, self.current_plan()
             X = self.data.X.reshape(self.data.steps, self.C, self.data.X.shape[2], -1)
             self._small = dict(
                 kind=s["kind"], din=s["in"], hid=s["hidden"], dout=s["out"],

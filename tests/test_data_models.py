@@ -1,0 +1,84 @@
+import numpy as np
+import torch
+
+from feddrift_b200.data import changepoints as cp
+from feddrift_b200.data.drift import (DriftData, generate_drift_data, load_all_data, load_partition_data,
+                                      select_iterations)
+from feddrift_b200.models import create_model, reinitialize
+from feddrift_b200.models.utils import flat_size, flatten_state_dict, unflatten_to_state_dict, flat_spec
+from feddrift_b200.parallel.arena import ModelBank
+
+
+def test_changepoint_tables_and_random():
+    A = cp.named("A")
+    assert A.shape == (11, 10) and A.max() == 1 and A[0].sum() == 0
+    assert cp.named("B").max() == 3
+    assert cp.load("A", 10, 25).shape == (11, 25)          # tiled clients
+    assert cp.load("A", 20, 10).shape[0] >= 21              # stationary tail
+    r = cp.load("rand", 10, 10, rng=np.random.RandomState(0))
+    assert set(np.unique(r)) <= {0, 1} and (np.diff(r, axis=0) >= 0).all()
+
+
+def test_generators_follow_concepts():
+    d = generate_drift_data("sea", 4, 10, 200, 0.0, 1, "A", sea_label_noise=0.0)
+    assert d.X.shape == (5, 10, 200, 3) and d.class_num == 2
+    x, y = d.X[4, 1], d.Y[4, 1]   # A.cp: client 1 is on concept 1 (θ=9) at step 4
+    assert torch.equal(y, (x[:, 1] + x[:, 2] > 9.0).long())
+    for name in ("sine", "circle"):
+        dd = generate_drift_data(name, 3, 4, 50, 0.1, 1, "rand")
+        assert dd.X.shape == (4, 4, 50, 2) and 0 < dd.Y.float().mean() < 1
+    m = generate_drift_data("MNIST", 2, 3, 40, 0.0, 1, "B")
+    assert m.X.shape == (3, 3, 40, 784) and m.class_num == 10
+
+
+def test_retrain_selectors_and_fedml_tuple(tmp_path):
+    assert select_iterations("all", 3) == [0, 1, 2, 3]
+    assert select_iterations("win-2", 3) == [2, 3]
+    assert select_iterations("weight-linear", 2) == [0, 1, 1, 2, 2, 2]
+    assert select_iterations("weight-exp", 2) == [0, 1, 1, 2, 2, 2, 2]
+    assert select_iterations("sel-0,2", 5) == [0, 2]
+    assert select_iterations("clientsel-[[0],[1,2]]", 5, 1) == [1, 2]
+    d = generate_drift_data("sea", 3, 4, 30, 0.0, 1, "rand")
+    tup = load_partition_data(d, 16, 1, "win-2", rng=np.random.RandomState(0))
+    assert tup[0] == 4 and tup[1] == 4 * 60 and tup[2] == 4 * 30 and len(tup[6][0]) == 4 and tup[8] == 2
+    allb = load_all_data(d, 16, 2)
+    assert len(allb) == 4 and len(allb[0]) == 3 and allb[0][0][0][0].shape == (16, 3)
+    d.to_csv_dir(str(tmp_path))
+    back = DriftData.from_csv_dir(str(tmp_path), "sea", 4, 4, 2)
+    assert torch.allclose(back.X, d.X, atol=1e-5) and torch.equal(back.Y, d.Y)
+
+
+def test_models_param_counts_and_reinit_identity():
+    assert sum(p.numel() for p in create_model("fnn", 2, 3).parameters()) == 38
+    assert sum(p.numel() for p in create_model("lr", 10, 784).parameters()) == 7850
+    assert sum(p.numel() for p in create_model("fnn", 10, 784).parameters()) == 1246570
+    assert sum(p.numel() for p in create_model("cnn", 10).parameters()) == 1199882
+    assert sum(p.numel() for p in create_model("cnn_fedavg", 10).parameters()) == 1663370
+    assert sum(p.numel() for p in create_model("rnn", 90).parameters()) == 822570
+    a, b = create_model("fnn", 2, 3), create_model("fnn", 2, 3)
+    assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))  # reseeded → identical
+    with torch.no_grad():
+        a.fc1.weight.add_(1)
+    reinitialize(a)
+    assert torch.equal(a.fc1.weight, b.fc1.weight)
+    x = torch.randn(5, 784)
+    assert create_model("cnn", 10)(x).sum(1).allclose(torch.ones(5), atol=1e-5)  # softmax output (quirk)
+    assert (create_model("lr", 2, 3)(torch.randn(4, 3)) >= 0).all()               # sigmoid output (quirk)
+
+
+def test_model_bank_views_and_flat_roundtrip():
+    tmpl = create_model("fnn", 2, 3)
+    bank = ModelBank(tmpl, 3)
+    assert bank.P == 38 and bank.stride % 32 == 0
+    sd = bank.state_dict(1)
+    sd["fc1.bias"].add_(1.0)                      # views alias the arena row
+    assert torch.allclose(bank.theta[1][18:24], bank.init_row[18:24] + 1)
+    mod = bank.module(1)
+    x = torch.randn(7, 3)
+    assert torch.allclose(mod(x), bank.forward(1, x), atol=1e-6)
+    bank.copy(2, 1)
+    bank.reinit(1)
+    assert torch.equal(bank.theta[1], bank.init_row) and not torch.equal(bank.theta[2], bank.init_row)
+    flat = flatten_state_dict(tmpl.state_dict())
+    back = unflatten_to_state_dict(flat, flat_spec(tmpl))
+    assert all(torch.equal(back[k], v) for k, v in tmpl.state_dict().items()) and flat_size(tmpl) == 38

@@ -85,20 +85,29 @@ def unpack_payload(header: bytes, flat: torch.Tensor) -> Dict[str, Any]:
     return _restore(skeleton, bag)
 
 
-class DistCommunicationManager(BaseCommunicationManager):
-    def __init__(self, rank: int, size: int, group=None, device: str = "cpu"):
-        super().__init__()
-        if not dist.is_initialized():
-            raise RuntimeError("torch.distributed must be initialised (FedML_init does it)")
-        self.rank, self.size, self.group = rank, size, group
-        self.device = torch.device(device)
+class _Endpoint:
+    """ONE send thread + ONE receive thread per process and process group.  Managers come and go (a new
+    Server/ClientManager pair per time step) but the blocking any-source ``dist.recv`` must have a single owner,
+    otherwise a stale receiver of a finished manager would swallow the next time step's messages."""
+
+    _instances: Dict[int, "_Endpoint"] = {}
+
+    def __init__(self, rank: int, size: int, group, device):
+        self.rank, self.size, self.group, self.device = rank, size, group, device
         self.q_send: "queue.Queue" = queue.Queue()
         self.q_recv: "queue.Queue" = queue.Queue()
-        self.is_running = True
-        self._send_thread = threading.Thread(target=self._send_loop, daemon=True, name=f"send{rank}")
-        self._recv_thread = threading.Thread(target=self._recv_loop, daemon=True, name=f"recv{rank}")
-        self._send_thread.start()
-        self._recv_thread.start()
+        self.threads = [threading.Thread(target=self._send_loop, daemon=True, name=f"fdb-send{rank}"),
+                        threading.Thread(target=self._recv_loop, daemon=True, name=f"fdb-recv{rank}")]
+        for t in self.threads:
+            t.start()
+
+    @classmethod
+    def get(cls, rank, size, group, device) -> "_Endpoint":
+        key = id(group) if group is not None else 0
+        ep = cls._instances.get(key)
+        if ep is None:
+            ep = cls._instances[key] = _Endpoint(rank, size, group, device)
+        return ep
 
     # wire: [hdr_len, data_len] int64 -> header bytes -> data bytes
     def _send_one(self, dst: int, header: bytes, flat: torch.Tensor) -> None:
@@ -115,8 +124,9 @@ class DistCommunicationManager(BaseCommunicationManager):
             try:
                 if item is None:
                     return
-                dst, header, flat = item
-                self._send_one(dst, header, flat)
+                self._send_one(*item)
+            except Exception:  # group torn down
+                return
             finally:
                 self.q_send.task_done()
 
@@ -126,6 +136,8 @@ class DistCommunicationManager(BaseCommunicationManager):
             try:
                 src = dist.recv(lens, group=self.group, tag=_TAG_HDR)
                 hlen, dlen = int(lens[0]), int(lens[1])
+                if hlen == 0:  # shutdown frame
+                    return
                 hdr = torch.empty(hlen, dtype=torch.uint8, device=self.device)
                 dist.recv(hdr, src=src, group=self.group, tag=_TAG_META)
                 flat = torch.empty(dlen, dtype=torch.uint8, device=self.device)
@@ -133,27 +145,57 @@ class DistCommunicationManager(BaseCommunicationManager):
                     dist.recv(flat, src=src, group=self.group, tag=_TAG_DATA)
             except Exception:  # process group torn down while blocked
                 return
-            params = unpack_payload(hdr.cpu().numpy().tobytes(), flat.cpu())
-            self.q_recv.put(Message().init(params))
+            self.q_recv.put(Message().init(unpack_payload(hdr.cpu().numpy().tobytes(), flat.cpu())))
+
+    def shutdown(self) -> None:
+        """Orderly teardown: everybody drains, then each rank wakes its right neighbour's receiver with an empty
+        frame, so no thread is left blocked inside gloo at interpreter exit."""
+        self.q_send.join()
+        dist.barrier(group=self.group)
+        if self.size > 1:
+            nxt = (self.rank + 1) % self.size
+            dist.send(torch.zeros(2, dtype=torch.int64, device=self.device), nxt, group=self.group, tag=_TAG_HDR)
+        self.q_send.put(None)
+        for t in self.threads:
+            t.join(10)
+
+
+class DistCommunicationManager(BaseCommunicationManager):
+    def __init__(self, rank: int, size: int, group=None, device: str = "cpu"):
+        super().__init__()
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (FedML_init does it)")
+        self.rank, self.size, self.group = rank, size, group
+        self.device = torch.device(device)
+        self.ep = _Endpoint.get(rank, size, group, self.device)
+        self.is_running = True
 
     def send_message(self, msg: Message) -> None:
         header, flat = pack_payload(msg.to_string())
-        self.q_send.put((int(msg.get_receiver_id()), header, flat))
+        self.ep.q_send.put((int(msg.get_receiver_id()), header, flat))
 
     def handle_receive_message(self) -> None:
         while self.is_running:
-            msg = self.q_recv.get()
+            msg = self.ep.q_recv.get()
             if msg is None:
                 break
             self.notify(msg)
 
     def stop_receive_message(self) -> None:
-        """Cooperative stop: drain our outgoing queue, then unblock the dispatch loop.
-        The receive thread is a daemon blocked in ``dist.recv``; it dies with the group."""
+        """Cooperative stop: drain our outgoing queue, then unblock OUR dispatch loop (the endpoint lives on)."""
         self.flush()
         self.is_running = False
-        self.q_recv.put(None)
+        self.ep.q_recv.put(None)
 
     def flush(self) -> None:
         """Block until every queued outgoing message has been handed to the transport."""
-        self.q_send.join()
+        self.ep.q_send.join()
+
+
+def shutdown_transport(destroy_group: bool = True) -> None:
+    """Tear down every endpoint of this process (call once at the very end of a distributed run)."""
+    for ep in list(_Endpoint._instances.values()):
+        ep.shutdown()
+    _Endpoint._instances.clear()
+    if destroy_group and dist.is_initialized():
+        dist.destroy_process_group()

@@ -127,6 +127,14 @@ def FedML_init(backend: str = "GLOO", world_size: Optional[int] = None):
                  "cuda" if backend == "NCCL" else "cpu"), dist.get_rank(), dist.get_world_size()
 
 
+def FedML_finalize() -> None:
+    """Orderly end of a distributed run (the reference ends with ``MPI.COMM_WORLD.Abort()``)."""
+    import torch.distributed as dist
+    if dist.is_initialized():
+        from ..core.comm.dist import shutdown_transport
+        shutdown_transport()
+
+
 # ====================================================================================== data loaders
 def _with(args, **kw):
     a = copy.copy(args)

@@ -94,7 +94,17 @@ def run_facade(args, sink):
         def loader(a):
             tup = load_partition_data(data, a.batch_size, a.curr_train_iteration, a.retrain_data)
             return list(tup[1:]) + [data.feature_num]
-        datasets = FedML_FedAvgEns_data_loader(args, loader, device, comm, process_id)
+        bank = ev = None
+        if t > 0 and args.concept_drift_algo in ("mmacc", "driftsurf"):
+            # these algorithms score last step's models on the new data BEFORE choosing training sets
+            from ..drift.evaluator import Evaluator
+            from ..parallel.arena import ModelBank
+            prev_params = args.state_store.get("model_params") or {}
+            bank = ModelBank(create_model(args.model, data.class_num, data.feature_num), len(prev_params) + 1, device)
+            for m, p in prev_params.items():
+                bank.load_state_dict(m, p)
+            ev = Evaluator(bank, data.to(device), args.batch_size)
+        datasets = FedML_FedAvgEns_data_loader(args, loader, device, comm, process_id, bank=bank, evaluator=ev)
         all_data = load_all_data(data, args.batch_size, t)
         class_num, feat = datasets[0][-2], datasets[0][-1]
         models = [create_model(args.model, class_num, feat) for _ in datasets]
@@ -111,6 +121,9 @@ def run_facade(args, sink):
                                              class_num, args)
         if process_id == 0:
             history.append({"iteration": t, "train_acc": sink.last("Train/Acc"), "test_acc": sink.last("Test/Acc")})
+    if args.backend in ("GLOO", "NCCL"):
+        from ..drift.fedavg_ens import FedML_finalize
+        FedML_finalize()
     return {"history": history, "summary": dict(sink.run.summary)}
 
 

@@ -47,7 +47,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -112,11 +112,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- kernel-level (device-timed) number: one fused launch per round, L2 flushed between rounds
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.5)  # nvidia-smi start-up (outside every timed region)
     for _ in range(Wm):
         sim.run_round_device()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     l0 = small_round.LAUNCH_COUNT["fed_round_small"]
     barrier()

@@ -59,6 +59,8 @@ std::vector<int64_t> fed_round_small(
     p.world = (int)icfg[17]; p.rank = (int)icfg[18]; p.flag_base = (unsigned)icfg[19];
     const int cluster = (int)icfg[20];
     p.spin_timeout_ns = (long long)icfg[21] * 1000000LL;
+    p.warps_per_pair = icfg.size() > 22 ? (int)icfg[22] : 1;
+    TORCH_CHECK(p.t_cur < 64, "fed_round_small supports t_cur < 64 time steps");
     TORCH_CHECK(p.world >= 1 && p.world <= fdb::kMaxPeers, "world must be in [1, 8]");
     if (p.world > 1) {
         TORCH_CHECK((int)peer_inbox.size() == p.world && (int)peer_flags.size() == p.world, "need one inbox/flag pointer per rank");

@@ -40,8 +40,10 @@ struct SmallCfg {
     static constexpr int kCols = (P + 31) / 32;  // parameters owned per lane
 };
 
+constexpr int kTmax = 64;  // the fused kernel supports t_cur < kTmax time steps (host falls back otherwise)
+
 struct SmemLayout {
-    int theta, part, slot, slot_model, gbuf, thl, ncm, tot, active, pairs, misc, total;
+    int theta, part, slot, slot_model, gbuf, thl, wsum, ptab_nb, ptab_w, ncm, tot, active, pairs, misc, total;
 };
 
 template <class Net>
@@ -57,6 +59,9 @@ __host__ __device__ inline SmemLayout make_layout(int M, int C, int pairs_per_ct
     L.slot_model = take(pairs_per_cta);
     L.gbuf = take(Cfg::kWarps * P * 33);
     L.thl = take(Cfg::kWarps * P);
+    L.wsum = take(Cfg::kWarps * P);
+    L.ptab_nb = take(Cfg::kWarps * kTmax);
+    L.ptab_w = take(Cfg::kWarps * kTmax);
     L.ncm = take(C * M);
     L.tot = take(M);
     L.active = take(M);
@@ -64,6 +69,12 @@ __host__ __device__ inline SmemLayout make_layout(int M, int C, int pairs_per_ct
     L.misc = take(8);
     L.total = o;
     return L;
+}
+
+// barrier among the WPP warps of a pair group (named barrier 1 + group id; id 0 is __syncthreads)
+FDB_DEVICE void group_barrier(int wpp, int gidx) {
+    if (wpp == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + gidx), "r"(wpp * 32) : "memory");
 }
 
 // sample coordinates of element i of the current mini-batch
@@ -92,14 +103,30 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
     float* part_s = smem + L.part;
     float* slot_s = smem + L.slot;
     int* slot_model = reinterpret_cast<int*>(smem + L.slot_model);
+    const int WPP = (p.warps_per_pair == 4 || p.warps_per_pair == 2) ? p.warps_per_pair : 1;
+    const int NG = NW / WPP;                    // pair groups per CTA
+    const int gidx = warp / WPP, sub = warp % WPP;
     float* gbuf = smem + L.gbuf + warp * (P * 33);
-    float* thl = smem + L.thl + warp * P;
+    float* thl = smem + L.thl + gidx * P;                    // group-local model
+    float* wsum = smem + L.wsum + gidx * (WPP * P);          // per-warp column sums of the group
+    int* ptab_nb = reinterpret_cast<int*>(smem + L.ptab_nb) + gidx * kTmax;
+    float* ptab_w = smem + L.ptab_w + gidx * kTmax;
     float* ncm_s = smem + L.ncm;
     float* tot_s = smem + L.tot;
     int* active_s = reinterpret_cast<int*>(smem + L.active);
     int* pairs_s = reinterpret_cast<int*>(smem + L.pairs);
     int* misc_s = reinterpret_cast<int*>(smem + L.misc);  // [0] = npairs
 
+    // ---- cold-start: pull the working set (samples of steps ≤ t+1, labels) into L2 with one wave of prefetches ----
+    {
+        const int steps = min(t + 2, p.T1);
+        const size_t xb = (size_t)steps * C * S * IN * sizeof(float), yb = (size_t)steps * C * S * sizeof(int);
+        const size_t gthreads = (size_t)G * blockDim.x, gt = (size_t)crank * blockDim.x + tid;
+        for (size_t off = gt * 128; off < xb; off += gthreads * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.X) + off));
+        for (size_t off = gt * 128; off < yb; off += gthreads * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.Y) + off));
+    }
     // ---- load the cluster models once (broadcast == this smem fill; afterwards θ never leaves the SM) ----
     for (int e = tid; e < MP; e += blockDim.x) theta_s[e] = p.theta[(e / P) * p.theta_stride + (e % P)];
     const float lr = p.lr_ptr ? *p.lr_ptr : p.lr;
@@ -171,86 +198,89 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
         }
         const int npairs = misc_s[0];
 
-        // ------------------------------------------------------------------ local training: one warp per pair
-        for (int i = crank + G * warp; i < npairs; i += G * NW) {
+        // ------------------------------------------------------------------ local training: WPP warps per pair
+        // A *group* of WPP warps (1, 2 or 4) owns one (client, model) pair: the mini-batch is strided over the
+        // group's lanes; every warp transposes its lanes' partial gradients through padded smem so lane l holds the
+        // column sums of parameters l, l+32, …; the group's leader warp adds the WPP partial columns, applies the
+        // optimizer for the columns it owns and publishes the new local model; two named barriers per step.
+        if (gidx < NG) {
+        for (int i = crank + G * gidx; i < npairs; i += G * NG) {
             const int k = pairs_s[i];
             const int c = k / M, m = k % M;
             const int li = i / G;
             float th[P];
 #pragma unroll
             for (int q = 0; q < P; ++q) th[q] = theta_s[m * P + q];
-#pragma unroll
-            for (int q = 0; q < COLS; ++q)  // thl = the warp's local model; lane l owns entries l, l+32, …
-                if (lane + 32 * q < P) thl[lane + 32 * q] = theta_s[m * P + lane + 32 * q];
-            __syncwarp();
-            // optimizer state of the parameters this lane owns
             float om[COLS], ov[COLS], ovm[COLS];
-            int ostep = p.opt_step[c * M + m];
+            int ostep = 0;
             const size_t obase = (size_t)(c * M + m) * P;
-            if (p.use_adam) {
+            double b1pow = 1.0, b2pow = 1.0;
+            if (sub == 0) {
 #pragma unroll
-                for (int q = 0; q < COLS; ++q) {
-                    const int pp = lane + 32 * q;
-                    om[q] = pp < P ? p.opt_m[obase + pp] : 0.f;
-                    ov[q] = pp < P ? p.opt_v[obase + pp] : 0.f;
-                    ovm[q] = pp < P ? p.opt_vmax[obase + pp] : 0.f;
+                for (int q = 0; q < COLS; ++q)  // thl = the group's local model; leader lane l owns entries l, l+32, …
+                    if (lane + 32 * q < P) thl[lane + 32 * q] = theta_s[m * P + lane + 32 * q];
+                if (p.use_adam) {
+                    ostep = p.opt_step[c * M + m];
+#pragma unroll
+                    for (int q = 0; q < COLS; ++q) {
+                        const int pp = lane + 32 * q;
+                        om[q] = pp < P ? p.opt_m[obase + pp] : 0.f;
+                        ov[q] = pp < P ? p.opt_v[obase + pp] : 0.f;
+                        ovm[q] = pp < P ? p.opt_vmax[obase + pp] : 0.f;
+                    }
+                    if (ostep > 0) { b1pow = pow((double)b1, (double)ostep); b2pow = pow((double)b2, (double)ostep); }
+                }
+                // per-pair batch-pool table (t_cur < kTmax is enforced on the host)
+                for (int tt = lane; tt <= t; tt += 32) {
+                    const int nb = (p.nsamp[tt * C + c] + B - 1) / B;
+                    const float w = (p.sample_mode == 2) ? 0.f : p.W[(tt * M + m) * C + c];
+                    ptab_nb[tt] = (p.sample_mode == 0) ? ((w * (float)nb > 0.f) ? nb : 0) : nb;
+                    ptab_w[tt] = w;
                 }
             }
             float fm[IN];
 #pragma unroll
             for (int q = 0; q < IN; ++q) fm[q] = p.feat_mask ? p.feat_mask[m * IN + q] : 1.f;
-
-            // pool geometry (uniform across lanes)
+            group_barrier(WPP, gidx);
             int npool = 0; float wtot = 0.f;
-            if (p.sample_mode == 0) {
-                for (int tt = 0; tt <= t; ++tt) {
-                    const int nb = (p.nsamp[tt * C + c] + B - 1) / B;
-                    if (p.W[(tt * M + m) * C + c] * (float)nb > 0.f) npool += nb;
-                }
-            } else if (p.sample_mode == 1) {
-                for (int tt = 0; tt <= t; ++tt) wtot += p.W[(tt * M + m) * C + c];
-            }
+            if (p.sample_mode == 0) { for (int tt = 0; tt <= t; ++tt) npool += ptab_nb[tt]; }
+            else if (p.sample_mode == 1) { for (int tt = 0; tt <= t; ++tt) wtot += ptab_w[tt]; }
             const int cnt = (p.sample_mode == 2) ? p.train_count[m * C + c] : 0;
             const int* list = (p.sample_mode == 2) ? p.train_index + (size_t)(m * C + c) * p.Lmax : nullptr;
 
             for (int step = 0; step < p.epochs; ++step) {
                 const unsigned h1 = batch_hash(p.seed, rnd, (unsigned)c, (unsigned)m, (unsigned)step);
-                BatchSel bs;
-                bs.mode = p.sample_mode; bs.list = list; bs.tb = 0; bs.lo = 0; bs.n = 0;
+                int sel_tb = 0, sel_lo = 0, sel_n = 0;
                 if (p.sample_mode == 0) {
                     int j = (int)hash_choice(h1, (unsigned)npool);
                     for (int tt = 0; tt <= t; ++tt) {
-                        const int ns = p.nsamp[tt * C + c];
-                        const int nb = (ns + B - 1) / B;
-                        if (p.W[(tt * M + m) * C + c] * (float)nb > 0.f) {
-                            if (j < nb) { bs.tb = tt; bs.lo = j * B; bs.n = min(B, ns - j * B); break; }
-                            j -= nb;
-                        }
+                        const int nb = ptab_nb[tt];
+                        if (j < nb) { sel_tb = tt; sel_lo = j * B; sel_n = min(B, p.nsamp[tt * C + c] - j * B); break; }
+                        j -= nb;
                     }
                 } else if (p.sample_mode == 1) {
                     const unsigned h2 = mix32(h1 ^ 0x68E31DA4u);
                     const float u = __uint2float_rn(h1 >> 8) * 5.9604644775390625e-8f * wtot;
                     float cum = 0.f; int tt_sel = 0;
-                    for (int tt = 0; tt <= t; ++tt) { cum += p.W[(tt * M + m) * C + c]; if (cum <= u) tt_sel = tt + 1; }
+                    for (int tt = 0; tt <= t; ++tt) { cum += ptab_w[tt]; if (cum <= u) tt_sel = tt + 1; }
                     tt_sel = min(tt_sel, t);
-                    while (tt_sel > 0 && p.nsamp[tt_sel * C + c] == 0) --tt_sel;
+                    while (tt_sel > 0 && ptab_nb[tt_sel] == 0) --tt_sel;
                     const int ns = p.nsamp[tt_sel * C + c];
-                    const int nb = max((ns + B - 1) / B, 1);
-                    const int b = (int)hash_choice(h2, (unsigned)nb);
-                    bs.tb = tt_sel; bs.lo = b * B; bs.n = max(min(B, ns - b * B), 0);
+                    const int b = (int)hash_choice(h2, (unsigned)max(ptab_nb[tt_sel], 1));
+                    sel_tb = tt_sel; sel_lo = b * B; sel_n = max(min(B, ns - b * B), 0);
                 } else {
                     const int nbm = (cnt + B - 1) / B;
                     const int b = (int)hash_choice(h1, (unsigned)nbm);
-                    bs.lo = b * B; bs.n = min(B, cnt - b * B);
+                    sel_lo = b * B; sel_n = min(B, cnt - b * B);
                 }
                 float g[P];
 #pragma unroll
                 for (int q = 0; q < P; ++q) g[q] = 0.f;
-                const float scale = 1.0f / (float)max(bs.n, 1);
-                for (int sidx = lane; sidx < bs.n; sidx += 32) {
-                    int tb = bs.tb, s = bs.lo + sidx;
-                    if (bs.mode == 2) { const int qid = bs.list[bs.lo + sidx]; tb = qid / S; s = qid - tb * S; }
-                    const size_t row = (size_t)(tb * C + c) * S + s;
+                const float scale = 1.0f / (float)max(sel_n, 1);
+                for (int sidx = sub * 32 + lane; sidx < sel_n; sidx += 32 * WPP) {
+                    int tb = sel_tb, sx = sel_lo + sidx;
+                    if (p.sample_mode == 2) { const int qid = list[sel_lo + sidx]; tb = qid / S; sx = qid - tb * S; }
+                    const size_t row = (size_t)(tb * C + c) * S + sx;
                     float x[IN];
 #pragma unroll
                     for (int q = 0; q < IN; ++q) x[q] = p.X[row * IN + q] * fm[q];
@@ -261,64 +291,79 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                     Net::softmax_ce(z, y, pr, am);
                     Net::backward_accum(th, x, z, h, pr, y, scale, g);
                 }
-                // transpose-reduce: lane l ends up with Σ_lanes g[p] for p = l + 32q
+                // transpose-reduce inside the warp: lane l ends up with Σ_lanes g[p] for p = l + 32q
 #pragma unroll
                 for (int q = 0; q < P; ++q) gbuf[q * 33 + lane] = g[q];
                 __syncwarp();
-                if (p.use_adam) ++ostep;
-                double bc1 = 1.0, bc2s = 1.0;
-                if (p.use_adam) {
-                    bc1 = 1.0 - pow((double)b1, (double)ostep);
-                    bc2s = sqrt(1.0 - pow((double)b2, (double)ostep));
+                float gcol[COLS];
+#pragma unroll
+                for (int q = 0; q < COLS; ++q) {
+                    const int pp = lane + 32 * q;
+                    float gs = 0.f;
+                    if (pp < P) {
+#pragma unroll 8
+                        for (int j = 0; j < 32; ++j) gs += gbuf[pp * 33 + j];
+                        if (WPP > 1) wsum[sub * P + pp] = gs;
+                    }
+                    gcol[q] = gs;
                 }
-                const float step_size = (float)((double)lr / bc1);
-                const float bc2_sqrt = (float)bc2s;
+                if (WPP > 1) group_barrier(WPP, gidx);
+                if (sub == 0) {
+                    float step_size = lr, bc2_sqrt = 1.f;
+                    if (p.use_adam) {  // bias corrections from running fp64 powers; the divisions/sqrt run in fp32
+                        ++ostep;
+                        b1pow *= (double)b1;
+                        b2pow *= (double)b2;
+                        step_size = lr / (float)(1.0 - b1pow);
+                        bc2_sqrt = sqrtf((float)(1.0 - b2pow));
+                    }
+#pragma unroll
+                    for (int q = 0; q < COLS; ++q) {
+                        const int pp = lane + 32 * q;
+                        if (pp < P) {
+                            float gs = gcol[q];
+                            for (int w2 = 1; w2 < WPP; ++w2) gs += wsum[w2 * P + pp];
+                            float w = thl[pp];
+                            if (p.use_adam) {
+                                gs = fmaf(p.wd, w, gs);
+                                om[q] = fmaf(gs - om[q], 1.0f - b1, om[q]);
+                                ov[q] = fmaf((1.0f - b2) * gs, gs, ov[q] * b2);
+                                ovm[q] = fmaxf(ovm[q], ov[q]);
+                                const float denom = sqrtf(ovm[q]) / bc2_sqrt + p.eps;
+                                w = w - step_size * (om[q] / denom);
+                            } else {
+                                w = w - lr * gs;
+                            }
+                            thl[pp] = w;
+                        }
+                    }
+                }
+                group_barrier(WPP, gidx);
+#pragma unroll
+                for (int q = 0; q < P; ++q) th[q] = thl[q];
+            }
+            if (sub == 0) {  // persist optimizer state, publish the weighted local model
+                if (p.use_adam) {
+#pragma unroll
+                    for (int q = 0; q < COLS; ++q) {
+                        const int pp = lane + 32 * q;
+                        if (pp < P) { p.opt_m[obase + pp] = om[q]; p.opt_v[obase + pp] = ov[q]; p.opt_vmax[obase + pp] = ovm[q]; }
+                    }
+                    if (lane == 0) p.opt_step[c * M + m] = ostep;
+                }
+                const float wgt = ncm_s[k] / tot_s[m];
 #pragma unroll
                 for (int q = 0; q < COLS; ++q) {
                     const int pp = lane + 32 * q;
                     if (pp < P) {
-                        float gs = 0.f;
-#pragma unroll 8
-                        for (int j = 0; j < 32; ++j) gs += gbuf[pp * 33 + j];
-                        float w = thl[pp];
-                        if (p.use_adam) {
-                            gs = fmaf(p.wd, w, gs);
-                            om[q] = fmaf(gs - om[q], 1.0f - b1, om[q]);
-                            ov[q] = fmaf((1.0f - b2) * gs, gs, ov[q] * b2);
-                            ovm[q] = fmaxf(ovm[q], ov[q]);
-                            const float denom = sqrtf(ovm[q]) / bc2_sqrt + p.eps;
-                            w = w - step_size * (om[q] / denom);
-                        } else {
-                            w = w - lr * gs;
-                        }
-                        thl[pp] = w;
+                        slot_s[li * P + pp] = thl[pp] * wgt;
+                        if (p.client_out && r == p.rounds - 1) p.client_out[obase + pp] = thl[pp];
                     }
                 }
-                __syncwarp();
-#pragma unroll
-                for (int q = 0; q < P; ++q) th[q] = thl[q];
-                __syncwarp();
+                if (lane == 0) slot_model[li] = m;
             }
-            // persist optimizer state, publish the weighted local model
-            if (p.use_adam) {
-#pragma unroll
-                for (int q = 0; q < COLS; ++q) {
-                    const int pp = lane + 32 * q;
-                    if (pp < P) { p.opt_m[obase + pp] = om[q]; p.opt_v[obase + pp] = ov[q]; p.opt_vmax[obase + pp] = ovm[q]; }
-                }
-                if (lane == 0) p.opt_step[c * M + m] = ostep;
-            }
-            const float wgt = ncm_s[k] / tot_s[m];
-#pragma unroll
-            for (int q = 0; q < COLS; ++q) {
-                const int pp = lane + 32 * q;
-                if (pp < P) {
-                    slot_s[li * P + pp] = thl[pp] * wgt;
-                    if (p.client_out && r == p.rounds - 1) p.client_out[obase + pp] = thl[pp];
-                }
-            }
-            if (lane == 0) slot_model[li] = m;
-            __syncwarp();
+            group_barrier(WPP, gidx);  // thl / ptab are rewritten by the next pair
+        }
         }
         __syncthreads();
         if (p.timers && crank == 0 && blockIdx.x == 0 && tid == 0) p.timers[r * 4 + 0] = globaltimer_ns();
@@ -411,73 +456,66 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
             if (G > 1) cluster.sync(); else __syncthreads();
         }
 
-        // ------------------------------------------------------------------ evaluation: one warp per client
-        for (int c = crank * NW + warp; c < C; c += G * NW) {
+        // ------------------------------------------------------------------ evaluation: one warp per (client, split)
+        for (int it = crank * NW + warp; it < 2 * C; it += G * NW) {
+            const int c = it >> 1, which = it & 1;
             if (p.world > 1 && (c % p.world) != p.rank) continue;
+            const int tt = t + which;
+            if (tt >= p.T1) continue;
             int pick = 0; float bw = p.W[(t * M + 0) * C + c];
             for (int m = 1; m < M; ++m) { const float w = p.W[(t * M + m) * C + c]; if (w > bw) { bw = w; pick = m; } }
-            int mtr = pick, mte = pick;
-            if (p.eval_train_model && p.eval_train_model[c] >= 0) mtr = p.eval_train_model[c];
-            if (p.eval_test_model && p.eval_test_model[c] >= 0) mte = p.eval_test_model[c];
-            float res[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int which = 0; which < 2; ++which) {
-                const int tt = t + which;
-                if (tt >= p.T1) break;
-                const int ns = p.nsamp[tt * C + c];
-                float corr = 0.f, loss = 0.f;
-                if (which == 1 && p.ens_mode != 0) {
-                    for (int s = lane; s < ns; s += 32) {
-                        const size_t row = (size_t)(tt * C + c) * S + s;
-                        float x[IN];
+            int msel = pick;
+            const int* ovr = which ? p.eval_test_model : p.eval_train_model;
+            if (ovr && ovr[c] >= 0) msel = ovr[c];
+            const int ns = p.nsamp[tt * C + c];
+            float corr = 0.f, loss = 0.f;
+            if (which == 1 && p.ens_mode != 0) {
+                for (int sx = lane; sx < ns; sx += 32) {
+                    const size_t row = (size_t)(tt * C + c) * S + sx;
+                    float x[IN];
 #pragma unroll
-                        for (int q = 0; q < IN; ++q) x[q] = p.X[row * IN + q];
-                        float tally[OUT];
+                    for (int q = 0; q < IN; ++q) x[q] = p.X[row * IN + q];
+                    float tally[OUT];
 #pragma unroll
-                        for (int o = 0; o < OUT; ++o) tally[o] = 0.f;
-                        for (int m = 0; m < M; ++m) {
-                            const float w = p.ens_w[c * M + m];
-                            if (!(w > 0.f)) continue;
-                            float th[P];
+                    for (int o = 0; o < OUT; ++o) tally[o] = 0.f;
+                    for (int m = 0; m < M; ++m) {
+                        const float w = p.ens_w[c * M + m];
+                        if (!(w > 0.f)) continue;
+                        float th[P];
 #pragma unroll
-                            for (int q = 0; q < P; ++q) th[q] = theta_s[m * P + q];
-                            float z[OUT], h[HID > 0 ? HID : 1], pr[OUT];
-                            int am;
-                            Net::forward(th, x, z, h);
-                            Net::softmax_ce(z, 0, pr, am);
-#pragma unroll
-                            for (int o = 0; o < OUT; ++o) tally[o] += (p.ens_mode == 1) ? ((o == am) ? w : 0.f) : w * pr[o];
-                        }
-                        int am = 0; float mx = tally[0];
-#pragma unroll
-                        for (int o = 1; o < OUT; ++o) if (tally[o] > mx) { mx = tally[o]; am = o; }
-                        corr += (am == p.Y[row]) ? 1.f : 0.f;
-                    }
-                } else {
-                    const int m = which ? mte : mtr;
-                    float th[P];
-#pragma unroll
-                    for (int q = 0; q < P; ++q) th[q] = theta_s[m * P + q];
-                    for (int s = lane; s < ns; s += 32) {
-                        const size_t row = (size_t)(tt * C + c) * S + s;
-                        float x[IN];
-#pragma unroll
-                        for (int q = 0; q < IN; ++q) x[q] = p.X[row * IN + q];
-                        const int y = p.Y[row];
+                        for (int q = 0; q < P; ++q) th[q] = theta_s[m * P + q];
                         float z[OUT], h[HID > 0 ? HID : 1], pr[OUT];
                         int am;
                         Net::forward(th, x, z, h);
-                        loss += Net::softmax_ce(z, y, pr, am);
-                        corr += (am == y) ? 1.f : 0.f;
+                        Net::softmax_ce(z, 0, pr, am);
+#pragma unroll
+                        for (int o = 0; o < OUT; ++o) tally[o] += (p.ens_mode == 1) ? ((o == am) ? w : 0.f) : w * pr[o];
                     }
+                    int am = 0; float mx = tally[0];
+#pragma unroll
+                    for (int o = 1; o < OUT; ++o) if (tally[o] > mx) { mx = tally[o]; am = o; }
+                    corr += (am == p.Y[row]) ? 1.f : 0.f;
                 }
-                res[which * 2 + 0] = warp_sum(corr);
-                res[which * 2 + 1] = warp_sum(loss);
+            } else {
+                float th[P];
+#pragma unroll
+                for (int q = 0; q < P; ++q) th[q] = theta_s[msel * P + q];
+                for (int sx = lane; sx < ns; sx += 32) {
+                    const size_t row = (size_t)(tt * C + c) * S + sx;
+                    float x[IN];
+#pragma unroll
+                    for (int q = 0; q < IN; ++q) x[q] = p.X[row * IN + q];
+                    const int y = p.Y[row];
+                    float z[OUT], h[HID > 0 ? HID : 1], pr[OUT];
+                    int am;
+                    Net::forward(th, x, z, h);
+                    loss += Net::softmax_ce(z, y, pr, am);
+                    corr += (am == y) ? 1.f : 0.f;
+                }
             }
-            if (lane == 0) {
-                float4 v = make_float4(res[0], res[1], res[2], res[3]);
-                *reinterpret_cast<float4*>(p.metrics + ((size_t)r * C + c) * 4) = v;
-            }
+            corr = warp_sum(corr); loss = warp_sum(loss);
+            if (lane == 0)
+                *reinterpret_cast<float2*>(p.metrics + ((size_t)r * C + c) * 4 + which * 2) = make_float2(corr, loss);
         }
         if (p.timers && crank == 0 && blockIdx.x == 0 && tid == 0) p.timers[r * 4 + 2] = globaltimer_ns();
         // (no barrier needed here: θ_s is next written after the __syncthreads that follows local training)
@@ -534,10 +572,13 @@ static int launch_round(const RoundParams& p, int cluster, cudaStream_t stream, 
     using Cfg = SmallCfg<Net>;
     const int CM = p.C * p.M;
     int G = cluster;
-    if (G <= 0) {  // auto: enough warps for every candidate pair, portable cluster sizes only
+    const int wpp = (p.warps_per_pair == 4 || p.warps_per_pair == 2) ? p.warps_per_pair : 1;
+    const int groups_per_cta = Cfg::kWarps / wpp;
+    if (G <= 0) {  // auto: enough warp groups for every candidate pair, portable cluster sizes only
         G = 1;
-        while (G < 8 && G * Cfg::kWarps < CM) G *= 2;
+        while (G < 8 && G * groups_per_cta < CM) G *= 2;
     }
+    if (G > 8) G = 8;
     const int pairs_per_cta = (CM + G - 1) / G;
     const SmemLayout L = make_layout<Net>(p.M, p.C, pairs_per_cta);
     const int smem = L.total * (int)sizeof(float);

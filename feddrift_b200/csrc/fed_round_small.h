@@ -41,6 +41,7 @@ struct RoundParams {
     int recluster_hard; // IFCA: argmax re-clustering after every aggregation
     int ens_mode;       // 0 none, 1 weighted hard vote, 2 weighted soft vote (test metric)
     int skip_aggregate; // 1 = train + export only (CFL inspects raw updates)
+    int warps_per_pair; // 1, 2 or 4 warps cooperate on one (client, model) pair
     // multi-GPU (clients sharded c % world == rank); world == 1 → everything local
     int world, rank;
     float* inbox[kMaxPeers];     // inbox[g]: this rank's view of peer g's symmetric inbox  [2, world, M*(P)+M]

@@ -6,6 +6,12 @@
 
 namespace fdb {
 
+// fast-math intrinsics (ex2.approx / lg2.approx based; ≤ 2 ulp) — the softmax/CE of a 2-class MLP is not
+// precision critical and this removes ~150 instructions of range reduction per sample from the critical path
+FDB_DEVICE float fexp(float x) { return __expf(x); }
+FDB_DEVICE float flog(float x) { return __logf(x); }
+FDB_DEVICE float fdiv(float a, float b) { return __fdividef(a, b); }
+
 template <int KIND, int IN, int HID, int OUT>
 struct Mlp {
     static constexpr int kKind = KIND, kIn = IN, kHid = HID, kOut = OUT;
@@ -21,7 +27,7 @@ struct Mlp {
                 float a = th[LB + o];
 #pragma unroll
                 for (int i = 0; i < IN; ++i) a = fmaf(th[LW + o * IN + i], x[i], a);
-                z[o] = 1.0f / (1.0f + expf(-a));
+                z[o] = fdiv(1.0f, 1.0f + fexp(-a));
             }
         } else {
 #pragma unroll
@@ -50,12 +56,12 @@ struct Mlp {
             if (z[o] > mx) { mx = z[o]; amax = o; }
         float s = 0.f;
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) { p[o] = expf(z[o] - mx); s += p[o]; }
-        const float inv = 1.0f / s;
+        for (int o = 0; o < OUT; ++o) { p[o] = fexp(z[o] - mx); s += p[o]; }
+        const float inv = fdiv(1.0f, s);
         float zy = z[0];
 #pragma unroll
         for (int o = 0; o < OUT; ++o) { p[o] *= inv; if (o == y) zy = z[o]; }
-        return logf(s) + mx - zy;
+        return flog(s) + mx - zy;
     }
 
     // accumulate d(mean CE)/dθ for one sample into g (scale = 1/batch)

@@ -47,6 +47,28 @@ def prepare(st: Dict) -> Dict:
         cache["feat_mask"] = _f32(st.get("feat_mask"), dev)
         cache["eval_train_model"] = _i32(st.get("eval_train_model"), dev)
         cache["eval_test_model"] = _i32(st.get("eval_test_model"), dev)
+        # launch shape hints: warps per pair from the mini-batch size, cluster size from the active pair count
+        B, t = int(st["batch_size"]), int(st["t_cur"])
+        bmax = min(B, int(cache["nsamp"].max()))
+        cache["wpp"] = 4 if bmax > 64 else (2 if bmax > 32 else 1)
+        P = theta.shape[1]
+        nwarps = 16 if P <= 24 else (12 if P <= 40 else 8)
+        groups = max(1, nwarps // cache["wpp"])
+        if st.get("recluster_hard"):
+            npairs = C * theta.shape[0]
+        elif st.get("sample_mode", "pool") == "index":
+            npairs = int((cache["train_count"] > 0).sum())
+        else:
+            Wc = st["W"][: t + 1].detach().float().cpu()
+            active = (Wc[t] != 0).any(dim=1)
+            npairs = int(((Wc.sum(0) > 0) & active[:, None]).sum())
+        mg = st.get("multi_gpu")
+        if mg:
+            npairs = -(-npairs // int(mg["world"]))
+        G = 1
+        while G < 8 and G * groups < npairs:
+            G *= 2
+        cache["cluster"] = G
         cache["counts"] = torch.stack(
             [cache["nsamp"][st["t_cur"]],
              cache["nsamp"][st["t_cur"] + 1] if st["t_cur"] + 1 < T1 else torch.zeros_like(cache["nsamp"][0])],
@@ -77,8 +99,8 @@ def run_native(st: Dict, rounds: int, metrics_out: Optional[torch.Tensor] = None
             int(st["seed"]) & 0xFFFFFFFF, int(use_adam), MODE_ID[st.get("sample_mode", "pool")],
             1 if st.get("n_mode", "batches") == "samples" else 0, int(bool(st.get("recluster_hard", False))),
             int(st.get("ens_mode", 0) or 0), int(bool(st.get("skip_aggregate", False))), world,
-            int(mg["rank"]) if mg else 0, int(mg["flag_base"]) if mg else 0, int(st.get("cluster", 0)),
-            int(st.get("spin_timeout_ms", 2000))]
+            int(mg["rank"]) if mg else 0, int(mg["flag_base"]) if mg else 0, int(st.get("cluster", 0) or cache["cluster"]),
+            int(st.get("spin_timeout_ms", 2000)), int(st.get("warps_per_pair", 0) or cache["wpp"])]
     fcfg = [float(lr) if lr_dev is None else 0.0, float(st["wd"]), 0.9, 0.999, 1e-8]
     info = ext.fed_round_small(
         KIND_ID[st["kind"]], int(st["din"]), int(st["hid"]), int(st["dout"]), cache["X"], cache["Y"], cache["nsamp"], W, theta,

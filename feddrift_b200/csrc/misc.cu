@@ -24,15 +24,15 @@ __global__ void __launch_bounds__(256) kd_kl_kernel(const float* __restrict__ s,
         const float lss = logf(ss);
         float l = 0.f, sum_pt = 0.f;
         for (int k = lane; k < K; k += 32) {
-            const float pt = expf(zt[k] * invT - mt) / st;
+            const float pt = expf(zt[k] * invT - mt) / st + 1e-7f;   // the reference adds 1e-7 to the teacher probs
             const float ls = zs[k] * invT - ms - lss;
-            l += pt * (logf(pt + 1e-7f) - ls);
+            l += pt * (logf(pt) - ls);
             sum_pt += pt;
         }
         l = warp_sum(l); sum_pt = warp_sum(sum_pt);
         if (grad_s)
             for (int k = lane; k < K; k += 32) {
-                const float pt = expf(zt[k] * invT - mt) / st;
+                const float pt = expf(zt[k] * invT - mt) / st + 1e-7f;
                 const float ps = expf(zs[k] * invT - ms) / ss;
                 grad_s[(size_t)row * K + k] = T * (ps * sum_pt - pt) / (float)B;
             }

@@ -416,21 +416,23 @@ def gram_cosine(U: torch.Tensor, eps: float = 1e-12):
 
 # --------------------------------------------------------------------------- K13..K16
 def modp_matmul(A: torch.Tensor, B: torch.Tensor, p: int) -> torch.Tensor:
-    """(A @ B) mod p for int64 operands already reduced mod p (python-int exact fallback via float128-free split)."""
+    """(A @ B) mod p, exact for any p < 2**63 (python-int arithmetic when products could overflow int64)."""
     A, B = A.to(torch.int64) % p, B.to(torch.int64) % p
-    out = torch.zeros(A.shape[0], B.shape[1], dtype=torch.int64)
-    # chunk the K dimension so partial sums stay < 2^63 (p < 2^31 -> products < 2^62)
-    for k in range(A.shape[1]):
-        out = (out + (A[:, k:k + 1] * B[k:k + 1, :]) % p) % p
-    return out
+    if p < (1 << 31):
+        out = torch.zeros(A.shape[0], B.shape[1], dtype=torch.int64)
+        for k in range(A.shape[1]):  # products < 2^62: reduce per term
+            out = (out + (A[:, k:k + 1] * B[k:k + 1, :]) % p) % p
+        return out
+    An, Bn = A.numpy().astype(object), B.numpy().astype(object)
+    return torch.from_numpy((An.dot(Bn) % p).astype(np.int64))
 
 
 def kd_kl_loss(student_logits, teacher_logits, temperature: float = 1.0):
     """FedGKT distillation loss: T² · KL(softmax(t/T) ‖ softmax(s/T)), batch-mean (K14)."""
     T = temperature
     ls = F.log_softmax(student_logits / T, dim=1)
-    pt = F.softmax(teacher_logits / T, dim=1)
-    return (T * T) * (pt * (torch.log(pt + 1e-7) - ls)).sum(1).mean()
+    pt = F.softmax(teacher_logits / T, dim=1) + 1e-7
+    return (T * T) * (pt * (torch.log(pt) - ls)).sum(1).mean()
 
 
 def vfl_bce_grad(logit_parts: torch.Tensor, y: torch.Tensor):

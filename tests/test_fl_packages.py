@@ -122,3 +122,104 @@ def test_framework_templates():
     comm, _, size = FedML_init("INPROC", 6)
     mgrs = FedML_Decentralized_Demo_distributed(0, size, comm, a)
     assert all(m.completed == [0, 1, 2] for m in mgrs)
+
+
+def _img_loaders(n_clients=2, n=24, classes=4, bs=8, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_clients):
+        y = torch.randint(0, classes, (n,), generator=g)
+        x = torch.randn(n, 3, 16, 16, generator=g) + y[:, None, None, None].float()
+        tr = [(x[i:i + bs], y[i:i + bs]) for i in range(0, n, bs)]
+        out.append((tr, tr[:1]))
+    return out
+
+
+def test_splitnn_round_robin():
+    from feddrift_b200.fl.split import SplitNN_distributed, split_model
+    set_sink(MetricsSink())
+    net = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(3 * 16 * 16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4))
+    bottom, top = split_model(net, 2)
+    loaders = _img_loaders()
+    res = SplitNN_distributed([copy.deepcopy(bottom) for _ in loaders], top, loaders, "cpu", epochs=3, lr=0.05)
+    assert len(res) == 6 and res[-1]["acc"] >= res[0]["acc"] and all(np.isfinite(r["loss"]) for r in res)
+
+
+def test_fedgkt_two_stage_training():
+    from feddrift_b200.fl.split import FedML_FedGKT_distributed
+    from feddrift_b200.models.resnet import resnet8_56, resnet56_server, ResNet, Bottleneck
+    sink = set_sink(MetricsSink())
+    a = SimpleNamespace(comm_round=2, epochs_client=1, epochs_server=1, lr=0.01, wd=1e-4, optimizer="SGD", temperature=3.0,
+                        alpha=1.0, whether_training_on_client=1, whether_distill_on_the_server=1)
+    loaders = _img_loaders()
+    server_model = ResNet(Bottleneck, [1, 1, 1], 4, stem="features")
+    srv, hist = FedML_FedGKT_distributed([resnet8_56(4) for _ in loaders], server_model, loaders, "cpu", a)
+    assert len(hist) == 2 and "best" in srv.checkpoints and len(sink.series("Test/AccTop1")) == 2
+    assert set(srv.get_global_logits(0).keys()) == {0, 1, 2}
+
+
+def test_vertical_fl_distributed_and_standalone():
+    from feddrift_b200.fl.split import (FedML_VFL_distributed, VFLGuestModel, VFLGuestTrainer, VFLHostModel, VFLHostTrainer,
+                                        VerticalMultiplePartyLogisticRegressionFederatedLearning)
+    from feddrift_b200.models.vfl import LocalModel, VFLClassifier, VFLFeatureExtractor
+    set_sink(MetricsSink())
+    rng = np.random.RandomState(0)
+    n = 256
+    Xa, Xb = rng.randn(n, 5).astype(np.float32), rng.randn(n, 4).astype(np.float32)
+    y = ((Xa[:, 0] + Xb[:, 1]) > 0).astype(np.float32)
+    a = SimpleNamespace(lr=0.05, batch_size=64, frequency_of_the_test=1)
+    guest = VFLGuestTrainer(2, "cpu", Xa, y, Xa, y, VFLFeatureExtractor(5, 8), VFLClassifier(8, 1), a)
+    host = VFLHostTrainer(1, "cpu", Xb, Xb, VFLFeatureExtractor(4, 8), VFLClassifier(8, 1, bias=False), a)
+    hist = FedML_VFL_distributed(guest, [host], comm_round=6)
+    assert hist[-1]["test_acc"] > 0.8 and hist[-1]["test_auc"] > 0.85
+    fl = VerticalMultiplePartyLogisticRegressionFederatedLearning(VFLGuestModel(LocalModel(5, 6, 0.05), learning_rate=0.05))
+    fl.add_party(id="B", party_model=VFLHostModel(LocalModel(4, 6, 0.05), learning_rate=0.05))
+    losses = [fl.fit(Xa[i:i + 64], y[i:i + 64], {"B": Xb[i:i + 64]}, s) for s in range(8) for i in range(0, n, 64)]
+    assert np.mean(losses[-4:]) < np.mean(losses[:4])
+    pred = fl.predict(Xa, {"B": Xb})
+    assert ((pred.flatten() > 0.5) == (y > 0.5)).mean() > 0.7
+
+
+def test_fednas_search_round():
+    from feddrift_b200.fl.fednas import FedML_FedNAS_distributed
+    from feddrift_b200.models.darts import Genotype, Network, NetworkCIFAR, Network_GumbelSoftmax
+    set_sink(MetricsSink())
+    a = SimpleNamespace(comm_round=1, epochs=1, learning_rate=0.025, momentum=0.9, weight_decay=3e-4, grad_clip=5.0,
+                        arch_learning_rate=3e-3, arch_weight_decay=1e-3, lambda_train_regularizer=1.0, lambda_valid_regularizer=1.0)
+    loaders = _img_loaders(n=16)
+    net = Network(4, 4, 3)
+    assert net.alphas_normal.shape == (14, 8)
+    a0 = net.alphas_normal.detach().clone()
+    agg, hist = FedML_FedNAS_distributed(net, loaders, loaders[0][0], "cpu", a)
+    g = hist[0][1]
+    assert isinstance(g, Genotype) and len(g.normal) == 8 and not torch.equal(agg.model.alphas_normal.detach(), a0)
+    ev = NetworkCIFAR(4, 4, 3, False, g)
+    logits, aux = ev(torch.randn(2, 3, 16, 16))
+    assert logits.shape == (2, 4) and aux is None
+    gd = Network_GumbelSoftmax(4, 4, 3)
+    assert gd(torch.randn(2, 3, 16, 16)).shape == (2, 4)
+
+
+def test_turboaggregate_primitives_and_secure_average():
+    from feddrift_b200.fl import turboaggregate as ta
+    p, rng = 2 ** 31 - 1, np.random.RandomState(0)
+    X = rng.randint(0, p, size=(4, 6))
+    sh = ta.BGW_encoding(X, 7, 2, p, rng)
+    idx = [1, 4, 6]
+    assert (ta.BGW_decoding(sh[idx].reshape(3, -1), idx, p).reshape(4, 6) == X % p).all()
+    assert ta.modular_inv(3, 7) == 5 and ta.divmod(6, 3, 7) == 2 and ta.PI([2, 3, 4], 5) == 4
+    U = ta.gen_Lagrange_coeffs([1, 2], [3, 4, 5], p)
+    assert U.shape == (2, 3) and (U.sum(1) % p == 1).all()          # Lagrange basis sums to one
+    N, K, T = 8, 2, 1
+    enc = ta.LCC_encoding(X, N, K, T, p, rng)
+    assert enc.shape == (N, 2, 6)
+    pts_a, pts_b = np.array([1, 2, 3]), np.array([10, 11, 12, 13])
+    Y = rng.randint(0, p, size=(3, 5))
+    enc2 = ta.LCC_encoding_with_points(Y, pts_a, pts_b, p)
+    assert (ta.LCC_decoding_with_points(enc2[:3], pts_b[:3], pts_a, p) == Y).all()
+    assert (ta.Gen_Additive_SS(5, 4, p, rng).sum(0) % p == 0).all()
+    assert ta.my_key_agreement(12, ta.my_pk_gen(34, p, 5), p, 5) == ta.my_key_agreement(34, ta.my_pk_gen(12, p, 5), p, 5)
+    agg = ta.TurboAggregator(6, 2)
+    Ux, w = torch.randn(6, 40), torch.rand(6) + 0.1
+    out = agg.aggregate(Ux, w, dropped=[0, 5])
+    assert (out - (Ux * (w / w.sum())[:, None]).sum(0)).abs().max() < 1e-3

@@ -27,7 +27,7 @@ std::vector<int64_t> fed_round_small(
     c10::optional<Tensor> eval_train_model, c10::optional<Tensor> eval_test_model, c10::optional<Tensor> ens_w,
     c10::optional<Tensor> client_out, c10::optional<Tensor> lr_dev, Tensor metrics, c10::optional<Tensor> timers,
     std::vector<double> fcfg, std::vector<int64_t> icfg, std::vector<int64_t> peer_inbox, std::vector<int64_t> peer_flags,
-    c10::optional<Tensor> error_flag) {
+    c10::optional<Tensor> error_flag, c10::optional<Tensor> counters, std::vector<int64_t> peer_metrics) {
     CHECK_CUDA_F32(X); CHECK_CUDA_I32(Y); CHECK_CUDA_I32(nsamp); CHECK_CUDA_F32(W); CHECK_CUDA_F32(theta); CHECK_CUDA_I32(opt_step);
     CHECK_CUDA_F32(metrics);
     TORCH_CHECK(X.is_contiguous() && Y.is_contiguous() && nsamp.is_contiguous() && W.is_contiguous() && metrics.is_contiguous(),
@@ -71,6 +71,10 @@ std::vector<int64_t> fed_round_small(
         TORCH_CHECK(!p.recluster_hard, "per-round IFCA re-clustering is single-GPU only in this build");
     }
     p.error_flag = opt_ptr<int>(error_flag);
+    p.counters = opt_ptr<int>(counters);
+    for (int g = 0; g < fdb::kMaxPeers; ++g) p.metrics_peer[g] = nullptr;
+    if (p.world > 1 && (int)peer_metrics.size() == p.world)
+        for (int g = 0; g < p.world; ++g) p.metrics_peer[g] = reinterpret_cast<float*>(peer_metrics[g]);
     if (p.use_adam) TORCH_CHECK(p.opt_m && p.opt_v && p.opt_vmax, "adam needs optimizer state tensors");
     fdb::SmallLaunchInfo info{};
     const int rc = fdb::fed_round_small_launch((int)kind, (int)din, (int)hid, (int)dout, p, cluster, cur_stream(), &info);

@@ -130,12 +130,15 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
     // ---- load the cluster models once (broadcast == this smem fill; afterwards θ never leaves the SM) ----
     for (int e = tid; e < MP; e += blockDim.x) theta_s[e] = p.theta[(e / P) * p.theta_stride + (e % P)];
     const float lr = p.lr_ptr ? *p.lr_ptr : p.lr;
+    // graph-replay friendly: the round number (RNG stream) and the cross-GPU epoch come from device counters
+    const int round0 = p.counters ? p.counters[0] : p.round0;
+    const unsigned flag_base = p.counters ? (unsigned)p.counters[1] : p.flag_base;
     const float b1 = p.beta1, b2 = p.beta2;
     bool need_prep = true;
     __syncthreads();
 
     for (int r = 0; r < p.rounds; ++r) {
-        const unsigned rnd = (unsigned)(p.round0 + r);
+        const unsigned rnd = (unsigned)(round0 + r);
         const int buf = r & 1;
 
         // ------------------------------------------------------------------ prep: pair list from W
@@ -390,8 +393,8 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                 }
             } else {
                 // ---- cross-GPU: push the cluster partial to every peer inbox, publish epoch, sum in rank order
-                const unsigned epoch = p.flag_base + (unsigned)r + 1u;
-                const int xbuf = (int)((p.flag_base + (unsigned)r) & 1u);
+                const unsigned epoch = flag_base + (unsigned)r + 1u;
+                const int xbuf = (int)((flag_base + (unsigned)r) & 1u);
                 if (crank == 0) {
                     for (int e = tid; e < MP; e += blockDim.x) {
                         float v = 0.f;
@@ -514,13 +517,39 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                 }
             }
             corr = warp_sum(corr); loss = warp_sum(loss);
-            if (lane == 0)
-                *reinterpret_cast<float2*>(p.metrics + ((size_t)r * C + c) * 4 + which * 2) = make_float2(corr, loss);
+            if (lane == 0) {
+                const size_t moff = ((size_t)r * C + c) * 4 + which * 2;
+                if (p.world > 1 && p.metrics_peer[0]) {  // the owner writes this client's row into EVERY rank's buffer
+                    for (int gq = 0; gq < p.world; ++gq) {
+                        st_relaxed_sys_f32(p.metrics_peer[gq] + moff, corr);
+                        st_relaxed_sys_f32(p.metrics_peer[gq] + moff + 1, loss);
+                    }
+                } else {
+                    *reinterpret_cast<float2*>(p.metrics + moff) = make_float2(corr, loss);
+                }
+            }
         }
         if (p.timers && crank == 0 && blockIdx.x == 0 && tid == 0) p.timers[r * 4 + 2] = globaltimer_ns();
         // (no barrier needed here: θ_s is next written after the __syncthreads that follows local training)
     }
 
+    // ---- multi-GPU: make every rank's metric rows visible everywhere before the host (or the next graph node) reads
+    if (p.world > 1 && p.metrics_peer[0]) {
+        __threadfence_system();
+        if (G > 1) cluster.sync(); else __syncthreads();
+        if (crank == 0) {
+            const unsigned done = flag_base + (unsigned)p.rounds;
+            if (tid < p.world) st_release_sys(p.flags[tid] + 2 * p.world + p.rank, done);
+            if (tid < p.world) {
+                const unsigned* f = p.flags[p.rank] + 2 * p.world + tid;
+                const long long t0 = globaltimer_ns();
+                while ((int)(ld_acquire_sys(f) - done) < 0) {
+                    if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 2); break; }
+                }
+            }
+        }
+    }
+    if (p.counters && crank == 0 && tid == 0) { p.counters[0] = round0 + p.rounds; p.counters[1] = (int)(flag_base + (unsigned)p.rounds); }
     // ---- write the models back (all CTAs hold identical copies; cluster rank 0 stores) ----
     __syncthreads();
     if (crank == 0)

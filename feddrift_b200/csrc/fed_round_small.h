@@ -30,6 +30,7 @@ struct RoundParams {
     // outputs
     float* metrics;      // [rounds, C, 4]
     long long* timers;   // optional [rounds, 4] globaltimer ns stamps of CTA 0 (train end, agg end, eval end, -)
+    int* counters;       // optional device counters {round_in_step, global_epoch}: read at start, advanced at exit
     // scalars
     float lr, wd, beta1, beta2, eps;
     int T1, C, S, M, Lmax, theta_stride;
@@ -45,7 +46,8 @@ struct RoundParams {
     // multi-GPU (clients sharded c % world == rank); world == 1 → everything local
     int world, rank;
     float* inbox[kMaxPeers];     // inbox[g]: this rank's view of peer g's symmetric inbox  [2, world, M*(P)+M]
-    unsigned* flags[kMaxPeers];  // flags[g]:  peer g's flag words [2? , world]
+    unsigned* flags[kMaxPeers];  // flags[g]:  peer g's flag words [3, world] (2 aggregation parities + metrics epoch)
+    float* metrics_peer[kMaxPeers];  // every rank's (symmetric) metrics buffer, or nullptrs
     unsigned flag_base;          // monotonically increasing epoch base (per launch)
     long long spin_timeout_ns;   // bail out instead of hanging the GPU if a peer never arrives
     int* error_flag;             // set to nonzero on timeout

@@ -34,6 +34,13 @@ class Evaluator:
         if n == 0:
             return 0.0, 0.0, 0.0
         dev = self.bank.device
+        s = self.bank.mlp
+        if s is not None and mask is None:  # small MLP: the K4 kernel on a single pooled "client"
+            xs = x.reshape(1, n, -1).to(dev).float()
+            corr, loss = ops.mlp_eval_matrix(self.bank.theta[m:m + 1], xs, y.reshape(1, n).to(dev),
+                                             torch.tensor([n], dtype=torch.int32, device=dev), s["kind"], s["in"], s["hidden"],
+                                             s["out"])
+            return float(corr[0, 0]), float(n), float(loss[0, 0])
         acc = torch.zeros(3, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for i in range(0, n, self.eval_batch):

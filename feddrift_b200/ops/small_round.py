@@ -88,8 +88,12 @@ def run_native(st: Dict, rounds: int, metrics_out: Optional[torch.Tensor] = None
         st["W"] = W = W.to(device=dev, dtype=torch.float32).contiguous()
     ens_w = _f32(st.get("ens_w"), dev)
     use_adam = st.get("optimizer", "adam") != "sgd"
+    mg0 = st.get("multi_gpu")
     if metrics_out is None:
-        metrics_out = torch.zeros(rounds, C, 4, dtype=torch.float32, device=dev)
+        if mg0 and mg0.get("metrics_buf") is not None:
+            metrics_out = mg0["metrics_buf"][: rounds * C * 4].view(rounds, C, 4)
+        else:
+            metrics_out = torch.zeros(rounds, C, 4, dtype=torch.float32, device=dev)
     lr = st["lr"]
     lr_dev = lr if isinstance(lr, torch.Tensor) else None
     Lmax = int(cache["train_index"].shape[2]) if cache["train_index"] is not None else 0
@@ -102,14 +106,22 @@ def run_native(st: Dict, rounds: int, metrics_out: Optional[torch.Tensor] = None
             int(mg["rank"]) if mg else 0, int(mg["flag_base"]) if mg else 0, int(st.get("cluster", 0) or cache["cluster"]),
             int(st.get("spin_timeout_ms", 2000)), int(st.get("warps_per_pair", 0) or cache["wpp"])]
     fcfg = [float(lr) if lr_dev is None else 0.0, float(st["wd"]), 0.9, 0.999, 1e-8]
+    peer_metrics = []
+    if mg and mg.get("metrics_ptrs") is not None:
+        # the caller's metrics_out must be (a view at offset 0 of) this rank's symmetric metrics buffer
+        assert metrics_out.data_ptr() == mg["metrics_buf"].data_ptr(), "multi-GPU metrics must live in the symmetric buffer"
+        peer_metrics = list(mg["metrics_ptrs"])
     info = ext.fed_round_small(
         KIND_ID[st["kind"]], int(st["din"]), int(st["hid"]), int(st["dout"]), cache["X"], cache["Y"], cache["nsamp"], W, theta,
         int(st.get("theta_stride", theta.stride(0))), st.get("opt_m"), st.get("opt_v"), st.get("opt_vmax"), st["opt_step"],
         cache["train_index"], cache["train_count"], cache["feat_mask"], cache["eval_train_model"], cache["eval_test_model"],
         ens_w, st.get("client_out"), lr_dev, metrics_out, st.get("timers"), fcfg, icfg,
-        list(mg["inbox_ptrs"]) if mg else [], list(mg["flag_ptrs"]) if mg else [], mg.get("error_flag") if mg else None)
+        list(mg["inbox_ptrs"]) if mg else [], list(mg["flag_ptrs"]) if mg else [], mg.get("error_flag") if mg else None,
+        st.get("counters"), peer_metrics)
     if mg:
         mg["flag_base"] = int(mg["flag_base"]) + rounds
+    if st.get("counters") is not None:
+        st["_counter_rounds"] = st.get("_counter_rounds", 0) + rounds
     LAUNCH_COUNT["fed_round_small"] += 1
     st["round0"] = int(st["round0"]) + rounds
     st["_launch_info"] = info

@@ -28,12 +28,18 @@ def attach_multi_gpu(sim, world: int, rank: int) -> None:
     MP = sim.M * sim.bank.P
     inbox_floats = 2 * world * MP
     inbox_floats = (inbox_floats + 31) // 32 * 32  # keep the flag words on their own 128-byte line
-    flag_words = 2 * world
-    r = _rendezvous(inbox_floats + max(flag_words, 32), sim.device)
+    flag_words = 3 * world
+    flag_floats = max((flag_words + 31) // 32 * 32, 32)
+    max_rounds = int(getattr(sim.args, "max_rounds_per_launch", 0) or max(sim.args.comm_round, 256))
+    metric_floats = max_rounds * sim.C * 4
+    r = _rendezvous(inbox_floats + flag_floats + metric_floats, sim.device)
     base = r["ptrs"]
+    moff = inbox_floats + flag_floats
     sim.multi = {
         "world": world, "rank": rank, "flag_base": 0,
         "inbox_ptrs": base, "flag_ptrs": [p + 4 * inbox_floats for p in base],
+        "metrics_ptrs": [p + 4 * moff for p in base], "metrics_buf": r["buf"][moff:moff + metric_floats],
+        "metrics_rounds": max_rounds,
         "error_flag": torch.zeros(1, dtype=torch.int32, device=sim.device),
         "_keepalive": r,
     }

@@ -166,6 +166,10 @@ class DriftSim:
                 self._small["wd"] = 0.0
             if getattr(self, "multi", None) is not None:
                 self._small["multi_gpu"] = self.multi
+            if self.device.type == "cuda":  # device-resident round / epoch counters (CUDA-graph replay friendly)
+                self._small["counters"] = torch.tensor(
+                    [self.round_in_step, int(self.multi["flag_base"]) if self.multi else 0], dtype=torch.int32, device=self.device)
+            self._graph = None
             if self.bank.stride != self.bank.P:
                 self._small["theta_stride"] = self.bank.stride
         return self._small
@@ -179,6 +183,8 @@ class DriftSim:
             rpl = int(getattr(self.args, "rounds_per_launch", 0) or 0)
             if rpl > 0:
                 block = min(block, rpl)
+            if self.multi is not None:
+                block = min(block, int(self.multi["metrics_rounds"]))
             if self.spec is not None and self.algo.fused_ok():
                 st = self._small_state()
                 st["round0"] = self.round_in_step
@@ -204,10 +210,14 @@ class DriftSim:
         st["round0"] = self.round_in_step
         if self.device.type == "cuda":
             from ..ops import small_round
-            buf = getattr(self, "_metrics_buf", None)
-            if buf is None or buf.shape[0] < n:
-                buf = self._metrics_buf = torch.zeros(max(n, 64), self.C, 4, dtype=torch.float32, device=self.device)
-            out = small_round.run_native(st, n, buf[:n])
+            if self.multi is not None:
+                assert n <= int(self.multi["metrics_rounds"]), "block larger than the symmetric metrics buffer"
+                out = small_round.run_native(st, n, None)  # rows of every rank land in the symmetric buffer
+            else:
+                buf = getattr(self, "_metrics_buf", None)
+                if buf is None or buf.shape[0] < n:
+                    buf = self._metrics_buf = torch.zeros(max(n, 64), self.C, 4, dtype=torch.float32, device=self.device)
+                out = small_round.run_native(st, n, buf[:n])
         else:
             out = ops.fed_round_small(st, n)
         self.round_in_step += n
@@ -237,12 +247,54 @@ class DriftSim:
         n = (hi - self.t) * self.C * self.data_host.X.shape[2]
         return int(n * (self.data_host.feature_num * 4 + 4)), int(self.C * 4 * 4)
 
-    def run_round(self, host_inputs: Optional[Dict[str, torch.Tensor]] = None, log: bool = False) -> Dict:
+    def _build_round_graph(self, host_inputs: Dict[str, torch.Tensor]):
+        """Capture [H2D inputs → fused round kernel → D2H metrics] into ONE CUDA graph (replayed once per round)."""
+        from ..ops import small_round
+        st = self._small_state()
+        cache = small_round.prepare(st)
+        t = self.t
+        hi = t + host_inputs["X"].shape[0]
+        hm = self._host_metrics
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up outside capture (allocations, attribute sets)
+            self.run_rounds_device(1)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cache["X"][t:hi].copy_(host_inputs["X"], non_blocking=True)
+            cache["Y"][t:hi].copy_(host_inputs["Y"], non_blocking=True)
+            met = self.run_rounds_device(1)
+            hm.copy_(met[0], non_blocking=True)
+        self.round_in_step -= 1   # the capture itself executed nothing
+        self.global_round -= 1
+        small_round.LAUNCH_COUNT["fed_round_small"] -= 1
+        if self.multi is not None:
+            self.multi["flag_base"] = int(self.multi["flag_base"]) - 1
+        return g
+
+    def run_round(self, host_inputs: Optional[Dict[str, torch.Tensor]] = None, log: bool = False,
+                  use_graph: bool = False) -> Dict:
         """ONE end-to-end FL round through the public API: (optional) host→device copy of the round's inputs
         from pinned memory, the fused round kernel, device→host copy of the per-client metrics, host reduction.
         Synchronises (the caller gets real numbers back)."""
         st = self._small_state()
         t = self.t
+        if use_graph and host_inputs is not None and self.device.type == "cuda":
+            from ..ops import small_round
+            if getattr(self, "_host_metrics", None) is None or not self._host_metrics.is_pinned():
+                self._host_metrics = torch.zeros(self.C, 4, dtype=torch.float32).pin_memory()
+            if getattr(self, "_graph", None) is None or self._graph[1] is not host_inputs:
+                self._graph = (self._build_round_graph(host_inputs), host_inputs)
+            self._graph[0].replay()
+            self.round_in_step += 1
+            self.global_round += 1
+            small_round.LAUNCH_COUNT["fed_round_small"] += 1
+            if self.multi is not None:
+                self.multi["flag_base"] = int(self.multi["flag_base"]) + 1
+            torch.cuda.current_stream().synchronize()
+            return self._round_result(self._host_metrics.numpy(), log)
         if host_inputs is not None:
             if self.device.type == "cuda":
                 from ..ops import small_round
@@ -254,21 +306,20 @@ class DriftSim:
                 hi = t + host_inputs["X"].shape[0]
                 st["X"][t:hi].copy_(host_inputs["X"].reshape(st["X"][t:hi].shape))
                 st["Y"][t:hi].copy_(host_inputs["Y"])
-        met = self.run_rounds_device(1)
-        if getattr(self, "multi", None) is not None:
-            import torch.distributed as dist
-            dist.all_reduce(met)
+        met = self.run_rounds_device(1)   # multi-GPU: every rank already holds all clients' rows (peer stores)
         hm = getattr(self, "_host_metrics", None)
         if hm is None:
             hm = self._host_metrics = torch.zeros(self.C, 4, dtype=torch.float32)
         hm.copy_(met[0], non_blocking=True)
         if self.device.type == "cuda":
             torch.cuda.current_stream().synchronize()
-        m = hm.numpy()
+        return self._round_result(hm.numpy(), log)
+
+    def _round_result(self, m, log: bool) -> Dict:
+        t = self.t
         if getattr(self, "_counts_host", None) is None:
             self._counts_host = self._last_counts.cpu()
-        cnt = self._counts_host
-        c = cnt.numpy()
+        c = self._counts_host.numpy()
         ntr, nte = max(float(c[:, 0].sum()), 1.0), max(float(c[:, 1].sum()), 1.0)
         res = {"round": self.round_in_step - 1, "iteration": t, "train_acc": float(m[:, 0].sum()) / ntr,
                "train_loss": float(m[:, 1].sum()) / ntr, "test_acc": float(m[:, 2].sum()) / nte,
@@ -281,11 +332,6 @@ class DriftSim:
 
     def _flush_metrics(self, out: Dict[str, torch.Tensor], r0: int, n: int) -> Dict:
         """One D2H copy per block; emits the reference's wandb keys for every tested round."""
-        if getattr(self, "multi", None) is not None:  # cold path: every rank only evaluated its own clients
-            import torch.distributed as dist
-            out = dict(out)
-            out["metrics"] = out["metrics"].clone()
-            dist.all_reduce(out["metrics"])
         met = out["metrics"].detach().to("cpu", torch.float64).numpy()  # [n, C, 4]
         cnt = out["counts"].detach().to("cpu", torch.float64).numpy()   # [C, 2]
         a = self.args

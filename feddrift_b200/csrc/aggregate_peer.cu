@@ -1,0 +1,183 @@
+// fedavg_reduce_apply_peer — the multi-GPU per-cluster FedAvg aggregation + broadcast as ONE kernel per rank, with the
+// collective done by the kernel itself over NVLink peer memory (no NCCL):
+//
+//   phase 0  every rank reduces its local clients' weights  Σ_c n[c,m]  and pushes the M totals to all peers
+//   phase 1  local weighted partial sums   part_g[m,:] = Σ_{c on g} n[c,m]·θ_c[m,:]        (HBM-bound, like K1)
+//   barrier  grid-wide (cooperative launch) + cross-GPU epoch flags (st.release.sys / ld.acquire.sys)
+//   phase 2  reduce-scatter + apply + all-gather fused: rank g owns the slice [g·P/W, (g+1)·P/W) of every cluster
+//            model; it pulls that slice of every peer's partial with 128-bit peer loads (W independent loads in
+//            flight per thread), divides by the global weight total and pushes the finished slice into EVERY rank's
+//            θ buffer with peer stores — the broadcast of the new cluster models is the epilogue of the reduction
+//   barrier  cross-GPU epoch flag so θ is complete everywhere when the kernel retires
+//
+// Wire bytes per rank: (W-1)/W·M·P·4 in + the same out — the reduce-scatter/all-gather minimum; the reference moves
+// N pickled state_dicts of ALL M models to and from rank 0 every round.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace fdb {
+
+struct PeerAggParams {
+    const float* cp;      // [C_local, M, P] local client rows
+    const float* n;       // [C_local, M] local weights
+    float* part[8];       // part[r]: rank r's symmetric partial buffer [M, P] (part[rank] is local)
+    float* theta[8];      // theta[r]: rank r's symmetric model buffer  [M, theta_stride]
+    float* tot_inbox[8];  // tot_inbox[r]: rank r's [world, M] weight-total inbox
+    unsigned* flags[8];   // flags[r]: rank r's [3, world] epoch words
+    unsigned* grid_sync;  // local monotonically increasing grid-barrier counter
+    unsigned epoch;       // this launch's epoch (monotonic across launches)
+    unsigned grid_base;   // grid_sync value expected before this launch
+    int C, M, P, theta_stride, world, rank;
+    long long spin_timeout_ns;
+    int* error_flag;
+};
+
+FDB_DEVICE void grid_barrier(unsigned* counter, unsigned target, long long timeout_ns, int* err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const long long t0 = globaltimer_ns();
+        while ((int)(*reinterpret_cast<volatile unsigned*>(counter) - target) < 0) {
+            if (globaltimer_ns() - t0 > timeout_ns) { if (err) atomicExch(err, 3); break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+FDB_DEVICE void peer_barrier(const PeerAggParams& p, int slot, unsigned epoch) {
+    // every rank publishes `epoch` into word [slot, rank] of all peers, then waits for all of its own words
+    if (blockIdx.x == 0) {
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + slot * p.world + p.rank, epoch);
+    }
+    if ((int)threadIdx.x < p.world) {
+        const unsigned* f = p.flags[p.rank] + slot * p.world + threadIdx.x;
+        const long long t0 = globaltimer_ns();
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+            if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 4); break; }
+        }
+    }
+    __syncthreads();
+}
+
+FDB_DEVICE float4 ld_peer_f4(const float* ptr) {
+    float4 v;
+    asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr) : "memory");
+    return v;
+}
+FDB_DEVICE void st_peer_f4(float* ptr, float4 v) {
+    asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __grid_constant__ PeerAggParams p) {
+    extern __shared__ float wsm[];  // [C] local weights of the current model, then [M] totals
+    __shared__ float red[32];
+    const int C = p.C, M = p.M, P = p.P, W = p.world;
+    const int P4 = P >> 2;  // host guarantees P % 4 == 0 (rows are padded)
+    float* tot_s = wsm + C;
+
+    // ---- phase 0: local weight totals → every peer's inbox
+    if (blockIdx.x == 0) {
+        for (int m = 0; m < M; ++m) {
+            float part = 0.f;
+            for (int c = threadIdx.x; c < C; c += blockDim.x) part += p.n[c * M + m];
+            const float tot = block_sum(part, red);
+            if (threadIdx.x == 0)
+                for (int r = 0; r < W; ++r) st_relaxed_sys_f32(p.tot_inbox[r] + p.rank * M + m, tot);
+        }
+    }
+    // ---- phase 1: un-normalised local partial sums (same streaming pattern as cluster_aggregate_kernel)
+    float* mine = p.part[p.rank];
+    for (int m = 0; m < M; ++m) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) wsm[c] = p.n[c * M + m];
+        __syncthreads();
+        const float* base = p.cp + (size_t)m * P;
+        const size_t cstride = (size_t)M * P;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int c = 0;
+            for (; c + 4 <= C; c += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(base + (size_t)(c + u) * cstride) + i);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float w = wsm[c + u];
+                    acc.x = fmaf(v[u].x, w, acc.x); acc.y = fmaf(v[u].y, w, acc.y);
+                    acc.z = fmaf(v[u].z, w, acc.z); acc.w = fmaf(v[u].w, w, acc.w);
+                }
+            }
+            for (; c < C; ++c) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(base + (size_t)c * cstride) + i);
+                const float w = wsm[c];
+                acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+            }
+            reinterpret_cast<float4*>(mine + (size_t)m * P)[i] = acc;
+        }
+    }
+    // ---- everyone's partials + totals are in place
+    grid_barrier(p.grid_sync, p.grid_base + gridDim.x, p.spin_timeout_ns, p.error_flag);
+    peer_barrier(p, 0, p.epoch);
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < W; ++r) t += ld_relaxed_sys_f32(p.tot_inbox[p.rank] + r * M + m);
+        tot_s[m] = t;
+    }
+    __syncthreads();
+
+    // ---- phase 2: my slice of every model: pull from all peers, normalise, push to all peers
+    const int per = (P4 + W - 1) / W, lo = p.rank * per, hi = min(P4, lo + per);
+    for (int m = 0; m < M; ++m) {
+        const float tot = tot_s[m];
+        if (!(tot > 0.f)) continue;  // unused cluster: leave θ untouched everywhere
+        const float inv = 1.0f / tot;
+        for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < W) v[r] = ld_peer_f4(p.part[r] + (size_t)m * P + (size_t)i * 4);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < W) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+            acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < W) st_peer_f4(p.theta[r] + (size_t)m * p.theta_stride + (size_t)i * 4, acc);
+        }
+    }
+    // ---- θ complete on every rank before anyone leaves
+    grid_barrier(p.grid_sync, p.grid_base + 2 * gridDim.x, p.spin_timeout_ns, p.error_flag);
+    peer_barrier(p, 1, p.epoch);
+}
+
+int fedavg_reduce_apply_peer_launch(const float* cp, const float* n, int C, int M, int P, int theta_stride, int world, int rank,
+                                    const long long* part_ptrs, const long long* theta_ptrs, const long long* tot_ptrs,
+                                    const long long* flag_ptrs, unsigned* grid_sync, unsigned epoch, unsigned grid_base, int grid,
+                                    long long timeout_ms, int* error_flag, cudaStream_t stream) {
+    if (world < 1 || world > 8 || (P & 3)) return -5;
+    PeerAggParams p{};
+    p.cp = cp; p.n = n; p.C = C; p.M = M; p.P = P; p.theta_stride = theta_stride; p.world = world; p.rank = rank;
+    for (int r = 0; r < world; ++r) {
+        p.part[r] = reinterpret_cast<float*>(part_ptrs[r]);
+        p.theta[r] = reinterpret_cast<float*>(theta_ptrs[r]);
+        p.tot_inbox[r] = reinterpret_cast<float*>(tot_ptrs[r]);
+        p.flags[r] = reinterpret_cast<unsigned*>(flag_ptrs[r]);
+    }
+    p.grid_sync = grid_sync; p.epoch = epoch; p.grid_base = grid_base;
+    p.spin_timeout_ns = timeout_ms * 1000000LL; p.error_flag = error_flag;
+    const int smem = (C + M + 8) * (int)sizeof(float);
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)fedavg_reduce_apply_peer_kernel, dim3(grid), dim3(512), args, smem, stream);
+    return e == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace fdb

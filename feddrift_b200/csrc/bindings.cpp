@@ -172,6 +172,26 @@ Tensor robust_clip(Tensor rows, Tensor g, double bound, c10::optional<Tensor> ma
     return nrm;
 }
 
+int64_t fedavg_reduce_apply_peer(Tensor cp, Tensor n, int64_t P, int64_t theta_stride, int64_t world, int64_t rank,
+                                 std::vector<int64_t> part_ptrs, std::vector<int64_t> theta_ptrs, std::vector<int64_t> tot_ptrs,
+                                 std::vector<int64_t> flag_ptrs, Tensor grid_sync, int64_t epoch, int64_t grid_base, int64_t timeout_ms,
+                                 Tensor error_flag) {
+    CHECK_CUDA_F32(cp); CHECK_CUDA_F32(n); CHECK_CUDA_I32(grid_sync); CHECK_CUDA_I32(error_flag);
+    c10::cuda::CUDAGuard guard(cp.device());
+    const int C = (int)cp.size(0), M = (int)cp.size(1);
+    TORCH_CHECK(cp.size(2) == P && cp.is_contiguous(), "cp must be contiguous [C, M, P]");
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cp.device().index());
+    std::vector<long long> a(part_ptrs.begin(), part_ptrs.end()), b(theta_ptrs.begin(), theta_ptrs.end()),
+        c(tot_ptrs.begin(), tot_ptrs.end()), d(flag_ptrs.begin(), flag_ptrs.end());
+    const int rc = fdb::fedavg_reduce_apply_peer_launch(cp.data_ptr<float>(), n.data_ptr<float>(), C, M, (int)P, (int)theta_stride, (int)world,
+                                                        (int)rank, a.data(), b.data(), c.data(), d.data(),
+                                                        reinterpret_cast<unsigned*>(grid_sync.data_ptr<int>()), (unsigned)epoch,
+                                                        (unsigned)grid_base, sms, timeout_ms, error_flag.data_ptr<int>(), cur_stream());
+    CHECK_OK(rc, "fedavg_reduce_apply_peer");
+    return sms;
+}
+
 // ---------------------------------------------------------------------------------- evaluation reductions
 void eval_logits(Tensor logits, Tensor target, Tensor acc) {
     CHECK_CUDA_F32(logits); CHECK_CUDA_I32(target); CHECK_CUDA_F32(acc);
@@ -301,6 +321,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("cluster_aggregate", &cluster_aggregate);
     m.def("cluster_aggregate_opt", &cluster_aggregate_opt);
     m.def("weighted_average", &weighted_average);
+    m.def("fedavg_reduce_apply_peer", &fedavg_reduce_apply_peer);
     m.def("merge_axpby", &merge_axpby);
     m.def("mean_sq_diff", &mean_sq_diff);
     m.def("gossip_mix", &gossip_mix);

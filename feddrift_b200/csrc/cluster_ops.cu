@@ -10,7 +10,7 @@ namespace fdb {
 
 constexpr int kChunk = 512;  // floats of each row staged per iteration
 
-__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ U, int n, long long P, double* __restrict__ G) {
+__global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ U, int n, long long P, double* __restrict__ part) {
     extern __shared__ float tile[];  // [n][kChunk + 1]
     const int pairs = n * (n + 1) / 2;
     // each thread owns a set of (i<=j) pairs; partial sums in fp32 per chunk, flushed to fp64 accumulators
@@ -46,25 +46,37 @@ __global__ void __launch_bounds__(256) gram_kernel(const float* __restrict__ U, 
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if (sub == 0) {
-            int i = 0, rem = pr;
-            while (rem >= n - i) { rem -= n - i; ++i; }
-            const int j = i + rem;
-            atomicAdd(G + (size_t)i * n + j, v);
-            if (i != j) atomicAdd(G + (size_t)j * n + i, v);
-        }
+        if (sub == 0) part[(size_t)blockIdx.x * pairs + pr] = v;   // one partial per (CTA, pair): no atomics on hot addresses
+    }
+}
+
+// second stage: fold the per-CTA partial Gram matrices (grid × pairs doubles) into the symmetric n×n result
+__global__ void gram_finish_kernel(const double* __restrict__ part, int grid, int n, double* __restrict__ G) {
+    const int pairs = n * (n + 1) / 2;
+    for (int pr = threadIdx.x; pr < pairs; pr += blockDim.x) {
+        double v = 0.0;
+        for (int b = 0; b < grid; ++b) v += part[(size_t)b * pairs + pr];
+        int i = 0, rem = pr;
+        while (rem >= n - i) { rem -= n - i; ++i; }
+        const int j = i + rem;
+        G[(size_t)i * n + j] = v;
+        G[(size_t)j * n + i] = v;
     }
 }
 
 int gram_launch(const float* U, int n, long long P, double* G, cudaStream_t stream) {
     // supports n(n+1)/2 <= 8 * 32 pairs per CTA (n <= 22); larger clusters are tiled by the caller
     if (n * (n + 1) / 2 > 8 * 32) return -5;
-    cudaMemsetAsync(G, 0, sizeof(double) * n * n, stream);
+    const int pairs = n * (n + 1) / 2;
     const int smem = n * (kChunk + 1) * (int)sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const long long chunks = (P + kChunk - 1) / kChunk;
     const int blocks = (int)max(1LL, min(chunks, 148LL * 4));
-    gram_kernel<<<blocks, 256, smem, stream>>>(U, n, P, G);
+    double* part = nullptr;
+    if (cudaMallocAsync(&part, sizeof(double) * (size_t)blocks * pairs, stream) != cudaSuccess) return -8;
+    gram_kernel<<<blocks, 256, smem, stream>>>(U, n, P, part);
+    gram_finish_kernel<<<1, 256, 0, stream>>>(part, blocks, n, G);
+    cudaFreeAsync(part, stream);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

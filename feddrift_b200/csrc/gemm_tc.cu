@@ -1,12 +1,17 @@
 // gemm_tn: D[M,N] = act(A[M,K] · B[N,K]ᵀ + bias[N])   bf16 operands, fp32 accumulation in TMEM.
 //
 // Hand-written Blackwell GEMM used by TcLinear (fnn-MNIST 784→1568→10, CNN fc 9216→128, LSTM/classifier heads):
-//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128B-swizzled 128×64 bf16 tiles) into a 4-stage smem ring,
-//     full/empty mbarrier pipeline, one elected producer thread;
-//   * tcgen05.mma.cta_group::1.kind::f16 (UMMA 128×128×16) issued by ONE thread, accumulator in TMEM
-//     (128 lanes × 128 fp32 columns), completion signalled with tcgen05.commit → mbarrier;
-//   * epilogue: 4 warps read the accumulator with tcgen05.ld.32x32b.x32, fuse bias + ReLU + (optional) bf16 cast
-//     in registers and store 128-byte row segments straight to global memory (no smem round trip, no extra pass).
+//   * PERSISTENT, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles tile = blockIdx.x + i·gridDim.x
+//     (M-fastest rasterisation so concurrently running CTAs share the same B panel in L2);
+//   * warp 0 = TMA producer (cp.async.bulk.tensor.2d, 128B-swizzled 128×64 / BN×64 bf16 boxes) into a 4-stage smem ring
+//     with full/empty mbarriers; warp 1 = single-thread tcgen05.mma issuer (UMMA 128×BN×16, BN ∈ {128, 256});
+//     warp 2 owns the TMEM allocation; warps 4-7 = epilogue;
+//   * the accumulator is DOUBLE-BUFFERED in TMEM (2 × BN fp32 columns): the epilogue of tile i (tcgen05.ld →
+//     bias + ReLU + cast in registers → 128-byte row-segment stores) overlaps the MMAs of tile i+1
+//     (tmem_full / tmem_empty mbarrier pair per buffer);
+//   * split-K (grid.z) for skinny outputs (e.g. 512×128×9216): partial tiles are accumulated with fp32 atomics into a
+//     zeroed output and bias/activation are applied by a small second kernel.
+// All waits are bounded (trap after 2 s) so a protocol bug faults the context instead of hanging the GPU.
 // The reference's equivalent is eager `nn.Linear` + separate bias/ReLU kernels in fp32 on cuBLAS
 // (fedml_api/model/fnn/fnn.py:11-15, cv/cnn.py:128-136).
 #include <cuda.h>
@@ -17,11 +22,17 @@
 
 namespace fdb {
 
-constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16, STAGES = 4;
-constexpr int kTmemCols = 128;
-constexpr int kGemmThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
-constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
-constexpr uint32_t kSmemBytes = STAGES * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int kGemmThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 epilogue
+constexpr uint32_t kStageBytesA = BM * BK * 2;
+
+template <int BN> struct GemmCfg {
+    static constexpr uint32_t kStageBytesB = BN * BK * 2;
+    static constexpr uint32_t kTmemCols = 2 * BN;  // double-buffered accumulator (256 or 512 columns)
+    static constexpr uint32_t kSmemBytes = STAGES * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+    // c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
 // ---------------------------------------------------------------- PTX wrappers
 FDB_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -30,6 +41,9 @@ FDB_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
 }
 FDB_DEVICE void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+FDB_DEVICE void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 FDB_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -67,30 +81,46 @@ FDB_DEVICE void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint
 FDB_DEVICE uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
-    d |= (uint64_t)(0) << 16;                            // leading byte offset (unused for swizzled K-major)
     d |= (uint64_t)((1024u) >> 4) << 32;                 // stride byte offset
     d |= (uint64_t)1 << 46;                              // descriptor version
     d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
     return d;
 }
-// c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+FDB_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
+template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ D,
-               const float* __restrict__ bias, int M, int N, int K, int relu, int out_fp32) {
+               const float* __restrict__ bias, int M, int N, int K, int relu, int out_fp32, int splits) {
+    using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * kStageBytesA;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (kStageBytesA + kStageBytesB));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (kStageBytesA + Cfg::kStageBytesB));
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.y, n_blk = blockIdx.x;
-    const int num_k_blocks = (K + BK - 1) / BK;
+    const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int kb_total = (K + BK - 1) / BK;
+    const int kb_per = (kb_total + splits - 1) / splits;
+    const int kb_lo = blockIdx.z * kb_per, kb_hi = min(kb_total, kb_lo + kb_per);
+    const int nkb = max(kb_hi - kb_lo, 0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -98,11 +128,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(kTmemCols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(Cfg::kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tcgen05_fence_before();
@@ -111,88 +141,113 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(empty_bar + s, ph ^ 1);
-                mbar_expect_tx(full_bar + s, kStageBytesA + kStageBytesB);
-                tma_load_2d(&map_a, full_bar + s, smem_a + s * kStageBytesA, kb * BK, m_blk * BM);
-                tma_load_2d(&map_b, full_bar + s, smem_b + s * kStageBytesB, kb * BK, n_blk * BN);
+        if (lane == 0 && nkb > 0) {  // ===== TMA producer
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+                for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(empty_bar + s, ph ^ 1);
+                    mbar_expect_tx(full_bar + s, kStageBytesA + Cfg::kStageBytesB);
+                    tma_load_2d(&map_a, full_bar + s, smem_a + s * kStageBytesA, kb * BK, m_blk * BM);
+                    tma_load_2d(&map_b, full_bar + s, smem_b + s * Cfg::kStageBytesB, kb * BK, n_blk * BN);
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer (single thread)
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(full_bar + s, ph);
+        if (lane == 0 && nkb > 0) {  // ===== MMA issuer (single thread)
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+                const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+                mbar_wait(tmem_empty + acc, aph ^ 1);   // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(smem_a + s * kStageBytesA);
-                const uint32_t b_addr = smem_u32(smem_b + s * kStageBytesB);
+                const uint32_t d_addr = tmem_base + acc * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full_bar + s, ph);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + s * kStageBytesA);
+                    const uint32_t b_addr = smem_u32(smem_b + s * Cfg::kStageBytesB);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
-                    const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
-                    umma_f16(tmem_base, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_f16(d_addr, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2),
+                                 Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+                    tcgen05_commit(empty_bar + s);  // frees the smem stage once these MMAs retire
                 }
-                tcgen05_commit(empty_bar + s);  // frees the smem stage once these MMAs retire
+                tcgen05_commit(tmem_full + acc);    // accumulator complete → epilogue
             }
-            tcgen05_commit(tmem_full_bar);      // accumulator complete → epilogue
         }
-    } else if (warp >= 4) {
-        // ===== epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) == output rows
+    } else if (warp >= 4 && nkb > 0) {
+        // ===== epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) == output rows of the tile
         const int q = warp - 4;
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-        const int row = m_blk * BM + q * 32 + lane;
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+            const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+            mbar_wait(tmem_full + acc, aph);
+            tcgen05_fence_after();
+            const int row = m_blk * BM + q * 32 + lane;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int col0 = n_blk * BN + c0;
-            if (row < M && col0 < N) {
-                if (out_fp32) {
-                    float* out = reinterpret_cast<float*>(D) + (size_t)row * N + col0;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int col0 = n_blk * BN + c0;
+                if (col0 >= N) break;   // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, v);
+                if (row < M) {
+                    if (splits > 1) {
+                        float* out = reinterpret_cast<float*>(D) + (size_t)row * N + col0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (col0 + j < N) {
-                            float x = __uint_as_float(v[j]);
-                            if (bias) x += __ldg(bias + col0 + j);
-                            if (relu) x = fmaxf(x, 0.f);
-                            out[j] = x;
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < N) atomicAdd(out + j, __uint_as_float(v[j]));
+                    } else if (out_fp32) {
+                        float* out = reinterpret_cast<float*>(D) + (size_t)row * N + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (col0 + j < N) {
+                                float x = __uint_as_float(v[j]);
+                                if (bias) x += __ldg(bias + col0 + j);
+                                if (relu) x = fmaxf(x, 0.f);
+                                out[j] = x;
+                            }
                         }
-                    }
-                } else {
-                    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(D) + (size_t)row * N + col0;
+                    } else {
+                        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(D) + (size_t)row * N + col0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (col0 + j < N) {
-                            float x = __uint_as_float(v[j]);
-                            if (bias) x += __ldg(bias + col0 + j);
-                            if (relu) x = fmaxf(x, 0.f);
-                            out[j] = __float2bfloat16(x);
+                        for (int j = 0; j < 32; ++j) {
+                            if (col0 + j < N) {
+                                float x = __uint_as_float(v[j]);
+                                if (bias) x += __ldg(bias + col0 + j);
+                                if (relu) x = fmaxf(x, 0.f);
+                                out[j] = __float2bfloat16(x);
+                            }
                         }
                     }
                 }
             }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + acc);   // 4 epilogue warps → the MMA warp may reuse the buffer
         }
-        tcgen05_fence_before();
     }
+    tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols));
+    }
+}
+
+// bias + activation (+ cast) pass for split-K outputs
+__global__ void bias_act_kernel(const float* __restrict__ acc, void* __restrict__ D, const float* __restrict__ bias, long long MN, int N,
+                                int relu, int out_fp32) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < MN; i += (long long)gridDim.x * blockDim.x) {
+        float x = acc[i];
+        if (bias) x += bias[i % N];
+        if (relu) x = fmaxf(x, 0.f);
+        if (out_fp32) reinterpret_cast<float*>(D)[i] = x;
+        else reinterpret_cast<__nv_bfloat16*>(D)[i] = __float2bfloat16(x);
     }
 }
 
@@ -226,20 +281,57 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols /*K*/
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+template <int BN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
+                       int out_fp32, int splits, int sms, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess) return -3;
+        attr_set = true;
+    }
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    dim3 grid(min(tiles, max(1, sms / splits)), 1, splits);
+    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
                    cudaStream_t stream) {
     if (K % 8 != 0 || M <= 0 || N <= 0) return -5;  // TMA global stride must be a multiple of 16 B
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -6;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int bn = (N > 128) ? 256 : 128;
     CUtensorMap ma, mb;
-    if (make_map(&ma, A, M, K, BM) != 0 || make_map(&mb, B, N, K, BN) != 0) return -7;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) return -3;
-        attr_set = true;
+    if (make_map(&ma, A, M, K, BM) != 0 || make_map(&mb, B, N, K, bn) != 0) return -7;
+    const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    const int kb_total = (K + BK - 1) / BK;
+    // split-K when the output has too few tiles to fill the machine and K is long
+    int splits = 1;
+    if (tiles * 4 <= sms && kb_total >= 16) {
+        splits = min(min(sms / tiles, kb_total / 4), 32);
+        if (splits < 2) splits = 1;
     }
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    gemm_tn_kernel<<<grid, kGemmThreads, kSmemBytes, stream>>>(ma, mb, D, bias, M, N, K, relu, out_fp32);
-    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+    if (splits > 1) {
+        float* acc = nullptr;
+        const size_t bytes = (size_t)M * N * sizeof(float);
+        if (out_fp32) acc = reinterpret_cast<float*>(D);
+        else if (cudaMallocAsync(&acc, bytes, stream) != cudaSuccess) return -8;
+        cudaMemsetAsync(acc, 0, bytes, stream);
+        int rc = (bn == 256) ? launch_gemm<256>(ma, mb, acc, nullptr, M, N, K, 0, 1, splits, sms, stream)
+                             : launch_gemm<128>(ma, mb, acc, nullptr, M, N, K, 0, 1, splits, sms, stream);
+        if (rc != 0) return rc;
+        if (bias || relu || !out_fp32) {
+            const long long MN = (long long)M * N;
+            bias_act_kernel<<<(int)min((MN + 255) / 256, 148LL * 8), 256, 0, stream>>>(acc, D, bias, MN, N, relu, out_fp32);
+        }
+        if (!out_fp32) cudaFreeAsync(acc, stream);
+        return cudaGetLastError() == cudaSuccess ? 0 : -4;
+    }
+    return (bn == 256) ? launch_gemm<256>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, stream)
+                       : launch_gemm<128>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, stream);
 }
 
 }  // namespace fdb

@@ -26,8 +26,9 @@ from . import changepoints as cp
 
 SEA_THRESHOLDS = (8.0, 9.0, 7.0, 9.0)  # fitted to the shipped concept{1..4}.csv
 DEFAULT_DELTAS = {"sea": 0.04, "sine": 0.20, "circle": 0.10, "MNIST": 0.10}
-FEATURE_SHAPE = {"sea": (3,), "sine": (2,), "circle": (2,), "MNIST": (784,), "fmow": (3, 224, 224)}
-CLASS_NUM = {"sea": 2, "sine": 2, "circle": 2, "MNIST": 10, "fmow": 62}
+FEATURE_SHAPE = {"sea": (3,), "sine": (2,), "circle": (2,), "MNIST": (784,), "fmow": (3, 224, 224), "cifar10": (3, 32, 32),
+                 "shakespeare": (80,)}
+CLASS_NUM = {"sea": 2, "sine": 2, "circle": 2, "MNIST": 10, "fmow": 62, "cifar10": 10, "shakespeare": 90}
 
 
 # ----------------------------------------------------------------------------- concept samplers
@@ -103,6 +104,25 @@ class DigitPool:
                 ya, yb = y == a, y == b
                 y[ya], y[yb] = b, a
         return x, y
+
+
+_CHAR_T = {}
+
+
+def _char_concept(rng, n, concept, seq_len=80, vocab=90):
+    """Character-LM concept: a concept is a (sparse) bigram transition table; x = 80 char ids, y = the next char."""
+    if concept not in _CHAR_T:
+        r = np.random.RandomState(1000 + concept)
+        _CHAR_T[concept] = r.dirichlet(np.full(vocab - 4, 0.05), size=vocab)
+    T = _CHAR_T[concept]
+    cdf = np.cumsum(T, axis=1)
+    out = np.zeros((n, seq_len + 1), dtype=np.int64)
+    s = rng.randint(4, vocab, size=n)
+    for i in range(seq_len + 1):
+        u = rng.rand(n)
+        s = 4 + (cdf[s] < u[:, None]).sum(1).clip(max=vocab - 5)
+        out[:, i] = s
+    return out[:, :seq_len], out[:, seq_len]
 
 
 def _image_concept(rng, n, concept, shape, classes):
@@ -205,12 +225,14 @@ def generate_drift_data(dataset: str, train_iteration: int, num_client: int, sam
     mat = cp.load(change_points, train_iteration, num_client, drift_together, stretch, rng)
     T1 = train_iteration + 1
     key = "MNIST" if dataset.lower() == "mnist" else dataset.lower()
+    if key in ("fed_shakespeare",):
+        key = "shakespeare"
     if key == "fmow":
         feat = tuple(image_shape) if image_shape else FEATURE_SHAPE["fmow"]
     else:
         feat = FEATURE_SHAPE[key]
     classes = CLASS_NUM[key]
-    X = np.zeros((T1, num_client, sample_num) + feat, dtype=np.float32)
+    X = np.zeros((T1, num_client, sample_num) + feat, dtype=np.int64 if key == "shakespeare" else np.float32)
     Y = np.zeros((T1, num_client, sample_num), dtype=np.int64)
     pool = DigitPool(data_dir) if key == "MNIST" else None
     for it in range(T1):
@@ -224,6 +246,8 @@ def generate_drift_data(dataset: str, train_iteration: int, num_client: int, sam
                 x, y = _circle(rng, sample_num, k)
             elif key == "MNIST":
                 x, y = pool.take(sample_num, k, mnist_mode)
+            elif key == "shakespeare":
+                x, y = _char_concept(rng, sample_num, k)
             else:
                 x, y = _image_concept(rng, sample_num, k, feat, classes)
             if noise_prob > 0:

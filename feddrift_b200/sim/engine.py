@@ -77,7 +77,8 @@ class DriftSim:
         from .algos import make_algo
         self.algo = algo if algo is not None else make_algo(args, self)
         self.M = self.algo.num_model_slots()
-        template = create_model(args.model, data.class_num, data.feature_num)
+        mkw = {"small_input": True} if (args.model in ("resnet", "resnet18") and data.X.shape[-1] <= 64) else {}
+        template = create_model(args.model, data.class_num, data.feature_num, **mkw)
         self.bank = ModelBank(template, self.M, self.device)
         self.spec = self.bank.mlp
         self.evaluator = Evaluator(self.bank, self.data, args.batch_size)
@@ -89,6 +90,7 @@ class DriftSim:
         self._plan: Optional[Dict] = None
         self._last_counts = None
         self.multi = None
+        self.shard_clients = False   # generic path: shard clients over torch.distributed ranks + PeerAggregator
         self.clients = ClientArena(self.C, self.M, self.bank.P, self.device,
                                    adam=(args.client_optimizer != "sgd"))
         self.timings = {"cluster_s": 0.0, "rounds_s": 0.0}

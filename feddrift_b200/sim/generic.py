@@ -54,7 +54,10 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
         Wt = st["W"][t]
         active = (st["train_count"] > 0).any(dim=1) if st["sample_mode"] == "index" else (Wt != 0).any(dim=1)
         cl.n.zero_()
+        world, rank = _world_rank(sim)
         for c in range(C):
+            if world > 1 and c % world != rank:   # clients are sharded over the ranks (one process per GPU)
+                continue
             Xc = Xc_all[:, c].reshape(T1 * S, *data.X.shape[3:])
             Yc = data.Y[:, c].reshape(T1 * S)
             for m in range(M):
@@ -76,7 +79,10 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
         if hasattr(sim.algo, "on_client_updates") and not sim.algo.split_done and rnd == sim.algo.split_round:
             sim.algo.on_client_updates(t, cl.params, cl.n)
         if not skip:
-            ops.cluster_aggregate_(bank.theta, cl.params, cl.n)
+            if world > 1:
+                _peer_aggregate(sim, world, rank)
+            else:
+                ops.cluster_aggregate_(bank.theta, cl.params, cl.n)
         if plan.get("recluster_hard"):
             acc = sim.evaluator.acc_matrix(list(range(M)), t)
             best = np.argmax(acc, axis=0)
@@ -85,8 +91,30 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
             plan["W"] = st["W"].clone()
             sim.algo.absorb_weights(t, st["W"])
         _evaluate(sim, plan, st, r, metrics, ens_mode)
+    if _world_rank(sim)[0] > 1:   # cold path: every rank evaluated only its own clients
+        import torch.distributed as dist
+        dist.all_reduce(metrics)
     counts = torch.stack([data.nsamp[t], data.nsamp[t + 1] if t + 1 < T1 else torch.zeros_like(data.nsamp[t])], 1).float()
     return {"metrics": metrics, "counts": counts}
+
+
+def _world_rank(sim):
+    import torch.distributed as dist
+    if getattr(sim, "shard_clients", False) and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def _peer_aggregate(sim, world, rank):
+    """Multi-GPU aggregation + broadcast of the cluster models in ONE kernel over NVLink peer memory
+    (``parallel/peer_aggregate.py``): this rank contributes the rows of its own clients."""
+    from ..parallel.peer_aggregate import PeerAggregator
+    pa = getattr(sim, "_peer_agg", None)
+    if pa is None:
+        pa = sim._peer_agg = PeerAggregator(sim.M, sim.bank.P, sim.device, sim.bank.theta)
+    mine = [c for c in range(sim.C) if c % world == rank]
+    theta = pa.aggregate(sim.clients.params[mine], sim.clients.n[mine])
+    sim.bank.theta.copy_(theta)
 
 
 def _cpu(x: Optional[torch.Tensor]):
@@ -159,8 +187,11 @@ def _evaluate(sim, plan, st, r, metrics, ens_mode):
     pick = st["W"][t].argmax(dim=0)
     etr, ete = plan.get("eval_train_model"), plan.get("eval_test_model")
     acc = torch.zeros(3, dtype=torch.float32, device=sim.device)
+    world, rank = _world_rank(sim)
     with torch.no_grad():
         for c in range(C):
+            if world > 1 and c % world != rank:
+                continue
             mtr = int(etr[c]) if etr is not None and int(etr[c]) >= 0 else int(pick[c])
             mte = int(ete[c]) if ete is not None and int(ete[c]) >= 0 else int(pick[c])
             n0 = int(sim.data_host.nsamp[t, c])

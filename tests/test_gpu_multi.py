@@ -85,3 +85,39 @@ def test_peer_reduce_apply_broadcast_matches_reference(tmp_path):
            "--master-port", "29519", str(script)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+GENERIC_WORKER = r'''
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["FDB_ROOT"])
+from feddrift_b200.sim import DriftSim, make_args
+from feddrift_b200.utils.metrics import MetricsSink
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+kw = dict(model="cnn", dataset="MNIST", client_num_in_total=6, client_num_per_round=6, concept_drift_algo="win-1",
+          concept_num=2, change_points="A", sample_num=16, batch_size=8, comm_round=2, total_train_iteration=2, epochs=2)
+sim = DriftSim(make_args(**kw), device=f"cuda:{rank}", sink=MetricsSink())
+sim.shard_clients = True
+out = sim.run()
+sim._peer_agg.check()
+ref = DriftSim(make_args(**kw), device=f"cuda:{rank}", sink=MetricsSink())
+oref = ref.run()
+err = (sim.bank.theta - ref.bank.theta).abs().max().item()
+ok = err < 5e-3 and abs(out["history"][-1]["train_loss"] - oref["history"][-1]["train_loss"]) < 5e-2
+print(json.dumps({"rank": rank, "err": err, "ok": bool(ok)}))
+dist.destroy_process_group()
+sys.exit(0 if ok else 3)
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_generic_executor_sharded_clients_with_peer_aggregation(tmp_path):
+    script = tmp_path / "generic_worker.py"
+    script.write_text(GENERIC_WORKER)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FDB_ROOT=root)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29521", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]

@@ -1,0 +1,55 @@
+"""BASELINE.json configs 2-5 on the device engine (synthetic data of the named shapes, random-init weights): rounds/s
+at time step 1 after a short warm-up.  Small MLPs take the fused kernel, everything else the generic executor."""
+import json
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from feddrift_b200.sim import DriftSim, make_args  # noqa: E402
+from feddrift_b200.utils.metrics import MetricsSink  # noqa: E402
+
+CONFIGS = {
+    "cfg2_sea_fnn_100clients_feddrift": dict(model="fnn", dataset="sea", client_num_in_total=100, client_num_per_round=100,
+                                             concept_drift_algo="softcluster", concept_drift_algo_arg="H_A_C_1_10_0", concept_num=4,
+                                             change_points="A", sample_num=100, batch_size=500, comm_round=40),
+    "cfg3_mnist_cnn_64clients_ifca": dict(model="cnn", dataset="MNIST", client_num_in_total=64, client_num_per_round=64,
+                                          concept_drift_algo="softclusterwin-1", concept_drift_algo_arg="hard-r", concept_num=4,
+                                          change_points="B", sample_num=64, batch_size=32, comm_round=3),
+    "cfg4_cifar_resnet18_32clients_aue": dict(model="resnet18", dataset="cifar10", client_num_in_total=32, client_num_per_round=32,
+                                              concept_drift_algo="aue", concept_drift_algo_arg="", concept_num=2, ensemble_window=2,
+                                              change_points="A", sample_num=32, batch_size=32, comm_round=2),
+    "cfg5_shakespeare_lstm_128clients_win1": dict(model="rnn", dataset="shakespeare", client_num_in_total=128, client_num_per_round=128,
+                                                  concept_drift_algo="win-1", concept_drift_algo_arg="", concept_num=2,
+                                                  change_points="A", sample_num=32, batch_size=16, comm_round=2),
+    "cfg5_shakespeare_lstm_128clients_feddrift": dict(model="rnn", dataset="shakespeare", client_num_in_total=128, client_num_per_round=128,
+                                                      concept_drift_algo="softcluster", concept_drift_algo_arg="H_A_C_1_10_0", concept_num=2,
+                                                      change_points="A", sample_num=32, batch_size=16, comm_round=2),
+}
+which = sys.argv[1:] or list(CONFIGS)
+for name in which:
+    kw = dict(CONFIGS[name])
+    kw.update(total_train_iteration=2, epochs=5, lr=0.01, report_client=0)
+    try:
+        t0 = time.perf_counter()
+        sim = DriftSim(make_args(**kw), device="cuda", sink=MetricsSink())
+        sim.run_time_step(0, rounds=1)
+        sim.begin_time_step(1)
+        sim.run_rounds(1)
+        torch.cuda.synchronize()
+        setup = time.perf_counter() - t0
+        R = kw["comm_round"]
+        t1 = time.perf_counter()
+        out = sim.run_rounds(R)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t1
+        print(json.dumps({"config": name, "rounds": R, "rounds_per_s": R / dt, "s_per_round": dt / R, "setup_s": setup,
+                          "fused_kernel": bool(sim.spec is not None and sim.algo.fused_ok()), "P": sim.bank.P,
+                          "last": {k: round(v, 4) for k, v in out.items() if isinstance(v, float)},
+                          "mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+        del sim
+        torch.cuda.empty_cache()
+    except Exception as e:  # keep going: a failing config must not hide the others
+        import traceback
+        print(json.dumps({"config": name, "error": repr(e)[:300], "trace": traceback.format_exc()[-600:]}), flush=True)

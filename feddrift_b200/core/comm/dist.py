@@ -12,7 +12,6 @@ Replaces the reference's mpi4py pickle p2p (``mpi_send_thread.py:20-29``,
 """
 from __future__ import annotations
 
-import io
 import pickle
 import queue
 import threading

@@ -14,10 +14,9 @@ CSV import/export (``client_{c}_iter_{t}.csv``) is kept for interoperability wit
 from __future__ import annotations
 
 import json
-import math
 import os
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch

@@ -20,7 +20,7 @@ import copy
 import logging
 import os
 import pickle
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import numpy as np
 import torch
@@ -31,7 +31,7 @@ from ..core.comm.inproc import World
 from ..core.managers import ClientManager, ServerManager
 from ..core.message import DeviceRef, Message
 from ..data import changepoints as cpmod
-from ..data.drift import DEFAULT_DELTAS, DriftData, load_all_data, load_partition_data
+from ..data.drift import DEFAULT_DELTAS, DriftData
 from ..models import utils as mutils
 from ..parallel.arena import ModelBank
 from ..utils.metrics import get_sink

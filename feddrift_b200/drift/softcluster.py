@@ -14,7 +14,7 @@ Algorithms: ``hard`` / ``hard-r`` (IFCA), ``softmax_α``, ``mmacc_δ`` (FedDrift
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch

@@ -15,12 +15,10 @@ Positional-argument compatibility with the reference's run script is provided by
 from __future__ import annotations
 
 import argparse
-import copy
 import json
 import logging
 import os
 import random
-import sys
 
 import numpy as np
 import torch

@@ -18,7 +18,6 @@ import argparse
 import copy
 import json
 import sys
-from types import SimpleNamespace
 
 import numpy as np
 import torch

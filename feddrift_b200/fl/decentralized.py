@@ -9,7 +9,7 @@ batched pass and the mixing is ONE ``ops.gossip_mix`` launch (``Wᵀ·X``).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import List
 
 import numpy as np
 import torch

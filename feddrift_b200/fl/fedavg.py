@@ -23,7 +23,7 @@ from .. import ops
 from ..core.managers import ClientManager, ServerManager
 from ..core.message import Message
 from ..core.robustness import RobustAggregator
-from ..drift.fedavg_ens import FedAvgEnsTrainer, _BaseAggregator
+from ..drift.fedavg_ens import _BaseAggregator
 from ..models import utils as mutils
 
 

@@ -8,7 +8,7 @@ that rebinds its loop variable, effectively returning client 0's α — intent r
 from __future__ import annotations
 
 import copy
-from typing import Dict, List
+from typing import Dict
 
 import torch
 from torch import nn

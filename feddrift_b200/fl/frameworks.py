@@ -9,7 +9,6 @@ from __future__ import annotations
 
 from typing import Dict, List
 
-from ..core.comm.inproc import World
 from ..core.managers import ClientManager, ServerManager
 from ..core.message import Message
 from ..core.topology import SymmetricTopologyManager

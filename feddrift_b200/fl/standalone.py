@@ -10,9 +10,8 @@ other ``torch.optim`` class.
 """
 from __future__ import annotations
 
-import copy
 import logging
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import numpy as np
 import torch

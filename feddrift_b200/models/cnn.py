@@ -9,7 +9,6 @@ The fully-connected layers are :class:`~feddrift_b200.ops.linear.TcLinear`
 """
 from __future__ import annotations
 
-import torch
 from torch import nn
 
 from ..ops.linear import TcLinear

@@ -9,7 +9,7 @@ map) instead of four near-identical files; state-dict keys follow the torchvisio
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional
+from typing import Callable, List
 
 import torch
 from torch import nn

@@ -6,7 +6,7 @@ compare the sm_100a kernels against.  Nothing here is tuned; clarity wins.
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Tuple
+from typing import Dict, Tuple
 
 import numpy as np
 import torch

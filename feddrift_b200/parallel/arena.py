@@ -15,8 +15,7 @@ Rows are padded to a multiple of 32 floats (128 B) so rows start on cache-line /
 from __future__ import annotations
 
 import copy
-from collections import OrderedDict
-from typing import Dict, Iterable, List, Optional
+from typing import Dict, List, Optional
 
 import torch
 from torch import nn

@@ -21,8 +21,6 @@ import urllib.request
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 from typing import Dict, Optional
 
-import torch
-
 from ..core.comm.mqtt import LocalBroker
 from ..fl.fedavg import FedAVGAggregator, FedAvgClientManager, FedAvgServerManager, FedAVGTrainer
 

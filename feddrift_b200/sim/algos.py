@@ -20,7 +20,6 @@ window baselines of ``fedavg_cont_one`` (README names ``win-1``, ``win-2``, ``al
 """
 from __future__ import annotations
 
-import json
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -29,7 +28,7 @@ import torch
 from .. import ops
 from ..data import changepoints as cpmod
 from ..data.drift import DEFAULT_DELTAS, select_iterations, poisson_bootstrap_index
-from ..drift.softcluster import SoftClusterState, parse_algo_arg
+from ..drift.softcluster import SoftClusterState
 from ..drift.states import AdaState, DriftSurfState, KueState, MultiModelAccState, aue_model_num
 
 BIG = 1 << 30

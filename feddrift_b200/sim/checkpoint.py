@@ -12,7 +12,6 @@ from __future__ import annotations
 import os
 from typing import Dict
 
-import numpy as np
 import torch
 
 FORMAT_VERSION = 1

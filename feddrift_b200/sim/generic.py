@@ -19,7 +19,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import ops
-from ..ops.reference import batch_hash, hash_choice, mix32
+from ..ops.reference import batch_hash, mix32
 
 
 def _pair_sampler(st: Dict, c: int, m: int, t: int, nb: torch.Tensor, B: int):

@@ -161,14 +161,14 @@ Tensor gossip_mix(Tensor X, Tensor Wm) {
     return out;
 }
 
-Tensor robust_clip(Tensor rows, Tensor g, double bound, c10::optional<Tensor> mask) {
+Tensor robust_clip(Tensor rows, Tensor g, double bound, c10::optional<Tensor> mask, double stddev, int64_t seed) {
     CHECK_CUDA_F32(rows); CHECK_CUDA_F32(g);
     c10::cuda::CUDAGuard guard(rows.device());
     const int R = (int)rows.size(0);
     auto scratch = torch::zeros({R}, rows.options());
     auto nrm = torch::zeros({R}, rows.options());
     CHECK_OK(fdb::robust_clip_launch(rows.data_ptr<float>(), g.data_ptr<float>(), opt_ptr<unsigned char>(mask), R, rows.size(1), (float)bound,
-                                     scratch.data_ptr<float>(), nrm.data_ptr<float>(), cur_stream()), "robust_clip");
+                                     scratch.data_ptr<float>(), nrm.data_ptr<float>(), (float)stddev, (unsigned)seed, cur_stream()), "robust_clip");
     return nrm;
 }
 
@@ -190,6 +190,23 @@ int64_t fedavg_reduce_apply_peer(Tensor cp, Tensor n, int64_t P, int64_t theta_s
                                                         (unsigned)grid_base, sms, timeout_ms, error_flag.data_ptr<int>(), cur_stream());
     CHECK_OK(rc, "fedavg_reduce_apply_peer");
     return sms;
+}
+
+int64_t gossip_mix_peer(std::vector<int64_t> x_ptrs, std::vector<int64_t> flag_ptrs, std::vector<double> w, int64_t P, int64_t world,
+                        int64_t rank, Tensor grid_sync, int64_t grid_base, int64_t epoch, int64_t timeout_ms, Tensor error_flag) {
+    CHECK_CUDA_I32(grid_sync); CHECK_CUDA_I32(error_flag);
+    c10::cuda::CUDAGuard guard(grid_sync.device());
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, grid_sync.device().index());
+    std::vector<long long> a(x_ptrs.begin(), x_ptrs.end()), b(flag_ptrs.begin(), flag_ptrs.end());
+    std::vector<float> wf(w.begin(), w.end());
+    wf.resize(8, 0.f);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(sms, (P / 4 + 511) / 512));
+    const int rc = fdb::gossip_mix_peer_launch(a.data(), b.data(), wf.data(), (int)P, (int)world, (int)rank,
+                                               reinterpret_cast<unsigned*>(grid_sync.data_ptr<int>()), (unsigned)grid_base, (unsigned)epoch,
+                                               grid, timeout_ms, error_flag.data_ptr<int>(), cur_stream());
+    CHECK_OK(rc, "gossip_mix_peer");
+    return grid;
 }
 
 // ---------------------------------------------------------------------------------- evaluation reductions
@@ -247,12 +264,16 @@ std::vector<Tensor> gram_cosine(Tensor U, double eps) {
     CHECK_CUDA_F32(U);
     c10::cuda::CUDAGuard guard(U.device());
     const int n = (int)U.size(0);
-    auto G = torch::zeros({n, n}, U.options().dtype(torch::kFloat64));
-    const int rc = fdb::gram_launch(U.data_ptr<float>(), n, U.size(1), G.data_ptr<double>(), cur_stream());
-    if (rc == -5) G = torch::matmul(U.to(torch::kFloat64), U.to(torch::kFloat64).t());  // > 22 rows: library GEMM (cold path)
-    else CHECK_OK(rc, "gram");
-    auto nrm = torch::sqrt(torch::diagonal(G));
-    auto S = G / (nrm.unsqueeze(1) * nrm.unsqueeze(0) + eps);
+    auto S = torch::empty({n, n}, U.options().dtype(torch::kFloat64));
+    auto nrm = torch::empty({n}, U.options().dtype(torch::kFloat64));
+    const int rc = fdb::gram_launch(U.data_ptr<float>(), n, U.size(1), eps, S.data_ptr<double>(), nrm.data_ptr<double>(), cur_stream());
+    if (rc == -5) {  // > 32 rows: library GEMM (cold path)
+        auto G = torch::matmul(U.to(torch::kFloat64), U.to(torch::kFloat64).t());
+        nrm = torch::sqrt(torch::diagonal(G));
+        S = G / (nrm.unsqueeze(1) * nrm.unsqueeze(0) + eps);
+    } else {
+        CHECK_OK(rc, "gram");
+    }
     return {S, nrm};
 }
 
@@ -312,6 +333,24 @@ Tensor gemm_tn_bias_act(Tensor A, Tensor B, c10::optional<Tensor> bias, bool rel
     return D;
 }
 
+// K2 (consumer-pull broadcast): the weight matrix B[N,K] stays in the OWNER GPU's symmetric-memory arena; `b_ptr` is
+// the peer-mapped device pointer.  The TMA producer of the GEMM pulls B tiles straight over NVLink inside the tile loop,
+// so "broadcast the model, then run the first layer" is one kernel and no local copy of the weights ever exists.
+Tensor gemm_tn_bias_act_peer(Tensor A, int64_t b_ptr, int64_t N, c10::optional<Tensor> bias, bool relu, bool out_fp32) {
+    TORCH_CHECK(A.is_cuda() && A.scalar_type() == torch::kBFloat16 && A.is_contiguous(), "gemm_tn_peer: A must be CUDA bf16 [M,K]");
+    TORCH_CHECK(b_ptr != 0 && N > 0, "gemm_tn_peer: null weight pointer");
+    c10::cuda::CUDAGuard guard(A.device());
+    const int M = (int)A.size(0), K = (int)A.size(1);
+    auto D = torch::empty({M, N}, A.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+    const float* bp = nullptr;
+    Tensor bias_f;
+    if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
+    const int rc = fdb::gemm_tn_launch(A.data_ptr(), reinterpret_cast<const void*>(b_ptr), D.data_ptr(), bp, M, (int)N, K, relu ? 1 : 0,
+                                       out_fp32 ? 1 : 0, cur_stream());
+    CHECK_OK(rc, "gemm_tn_peer (tcgen05)");
+    return D;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -338,4 +377,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("vfl_bce_grad", &vfl_bce_grad);
     m.def("group_norm_fwd", &group_norm_fwd);
     m.def("gemm_tn_bias_act", &gemm_tn_bias_act);
+    m.def("gemm_tn_bias_act_peer", &gemm_tn_bias_act_peer);
+    m.def("gossip_mix_peer", &gossip_mix_peer);
 }

@@ -15,6 +15,8 @@
 // The reference's equivalent is eager `nn.Linear` + separate bias/ReLU kernels in fp32 on cuBLAS
 // (fedml_api/model/fnn/fnn.py:11-15, cv/cnn.py:128-136).
 #include <cuda.h>
+
+#include <cstring>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -29,7 +31,8 @@ constexpr uint32_t kStageBytesA = BM * BK * 2;
 template <int BN> struct GemmCfg {
     static constexpr uint32_t kStageBytesB = BN * BK * 2;
     static constexpr uint32_t kTmemCols = 2 * BN;  // double-buffered accumulator (256 or 512 columns)
-    static constexpr uint32_t kSmemBytes = STAGES * (kStageBytesA + kStageBytesB) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t kStagingBytes = 4 /*epilogue warps*/ * 2 /*double buffer*/ * 4096;   // 32 rows × 128 B per buffer
+    static constexpr uint32_t kSmemBytes = STAGES * (kStageBytesA + kStageBytesB) + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     // c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
@@ -64,6 +67,22 @@ FDB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
 FDB_DEVICE void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+// TMA tile store / reduce-add (smem → global through the D tensor map; rows ≥ M and columns ≥ N are clipped by the hardware)
+FDB_DEVICE void tma_store_2d(const CUtensorMap* map, const void* src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+}
+FDB_DEVICE void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int x, int y) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y) : "memory");
+}
+FDB_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> FDB_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+FDB_DEVICE void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+FDB_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+FDB_DEVICE void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 FDB_DEVICE void tcgen05_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -101,14 +120,16 @@ FDB_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, void* __restrict__ D,
-               const float* __restrict__ bias, int M, int N, int K, int relu, int out_fp32, int splits) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_d, void* __restrict__ D, const float* __restrict__ bias, int M, int N, int K,
+               int relu, int out_fp32, int splits, int tma_out) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * kStageBytesA;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (kStageBytesA + Cfg::kStageBytesB));
+    uint8_t* staging = smem + STAGES * (kStageBytesA + Cfg::kStageBytesB);   // 1024-aligned: [4 warps][2][32 rows × 128 B]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -125,6 +146,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        if (tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
@@ -182,13 +204,75 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp >= 4 && nkb > 0) {
         // ===== epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) == output rows of the tile
         const int q = warp - 4;
-        uint32_t tl = 0;
+        uint32_t tl = 0, chunk_it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
             mbar_wait(tmem_full + acc, aph);
             tcgen05_fence_after();
             const int row = m_blk * BM + q * 32 + lane;
+            if (tma_out) {
+                // Coalesced path: the warp's 32-row slab goes TMEM → registers (bias/ReLU/cast) → 128B-swizzled smem
+                // staging (conflict-free 16-byte stores) → ONE TMA tile store (or fp32 reduce-add for split-K) per
+                // 128-byte column chunk.  Staging is double-buffered per warp; TMA clips the M/N edges.
+                const int cols_per_chunk = out_fp32 ? 32 : 64;
+                const int row0 = m_blk * BM + q * 32;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += cols_per_chunk, ++chunk_it) {
+                    const int col0 = n_blk * BN + c0;
+                    if (col0 >= N) break;   // warp-uniform
+                    uint8_t* buf = staging + (q * 2 + (chunk_it & 1)) * 4096;
+                    if (lane == 0 && chunk_it >= 2) tma_store_wait_read<1>();   // the store that last read this buffer is done
+                    __syncwarp();
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0;
+                    const uint32_t sbase = smem_u32(buf) + lane * 128;
+                    tmem_ld_32x32(taddr, v);
+                    if (out_fp32) {
+                        if (splits == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = __uint_as_float(v[j]);
+                                if (bias) x += (col0 + j < N) ? __ldg(bias + col0 + j) : 0.f;
+                                if (relu) x = fmaxf(x, 0.f);
+                                v[j] = __float_as_uint(x);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            st_shared_v4(sbase + ((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    } else {
+                        uint32_t w[32];
+                        tmem_ld_32x32(taddr + 32, w);
+                        uint32_t pk[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float x0 = __uint_as_float(v[j]), x1 = __uint_as_float(v[j + 1]);
+                            float y0 = __uint_as_float(w[j]), y1 = __uint_as_float(w[j + 1]);
+                            if (bias) {
+                                x0 += (col0 + j < N) ? __ldg(bias + col0 + j) : 0.f;
+                                x1 += (col0 + j + 1 < N) ? __ldg(bias + col0 + j + 1) : 0.f;
+                                y0 += (col0 + 32 + j < N) ? __ldg(bias + col0 + 32 + j) : 0.f;
+                                y1 += (col0 + 33 + j < N) ? __ldg(bias + col0 + 33 + j) : 0.f;
+                            }
+                            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                            __nv_bfloat162 a = __floats2bfloat162_rn(x0, x1), b = __floats2bfloat162_rn(y0, y1);
+                            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&a);
+                            pk[16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&b);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            st_shared_v4(sbase + ((c ^ (lane & 7)) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (splits > 1) tma_reduce_add_2d(&map_d, buf, col0, row0);
+                        else tma_store_2d(&map_d, buf, col0, row0);
+                        tma_store_commit();
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int col0 = n_blk * BN + c0;
@@ -226,10 +310,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + acc);   // 4 epilogue warps → the MMA warp may reuse the buffer
         }
+        if (tma_out && lane == 0) tma_store_wait_all();   // smem must outlive the in-flight bulk stores
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -281,9 +367,33 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols /*K*/
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// output map: 32-row × 128-byte boxes (32 fp32 or 64 bf16 columns), 128B swizzle — what one epilogue warp stages per chunk.
+// Returns 0 and sets *ok = 1 when D qualifies for TMA stores (16-byte aligned base and row pitch).
+static int make_out_map(CUtensorMap* map, void* D, int M, int N, int out_fp32, int* ok) {
+    *ok = 0;
+    memset(map, 0, sizeof(*map));
+    const size_t es = out_fp32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(D) & 15) || ((size_t)N * es) % 16 != 0) return 0;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)N * es};
+    cuuint32_t box[2] = {(cuuint32_t)(out_fp32 ? 32 : 64), 32u};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -2;
+    *ok = 1;
+    return 0;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
                        int out_fp32, int splits, int sms, cudaStream_t stream) {
+    CUtensorMap md;
+    int tma_out = 0;
+    if (make_out_map(&md, D, M, N, out_fp32, &tma_out) != 0) return -7;
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -292,7 +402,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     dim3 grid(min(tiles, max(1, sms / splits)), 1, splits);
-    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits);
+    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

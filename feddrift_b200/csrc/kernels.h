@@ -12,8 +12,11 @@ int weighted_average_launch(const float* rows, const float* w, int n, long long 
 int merge_axpby_launch(float* base_row, const float* second_row, float w1, float w2, long long P, cudaStream_t stream);
 int sq_diff_sum_launch(const float* a, const float* b, long long P, double* out, cudaStream_t stream);
 int gossip_mix_launch(const float* X, const float* Wm, int n, long long P, float* out, cudaStream_t stream);
+int gossip_mix_peer_launch(const long long* x_ptrs, const long long* flag_ptrs, const float* w, int P, int world, int rank,
+                           unsigned* grid_sync, unsigned grid_base, unsigned epoch, int grid, long long timeout_ms, int* error_flag,
+                           cudaStream_t stream);
 int robust_clip_launch(float* rows, const float* g, const unsigned char* mask, int R, long long P, float bound, float* scratch_nrm2,
-                       float* nrm_out, cudaStream_t stream);
+                       float* nrm_out, float stddev, unsigned seed, cudaStream_t stream);
 // aggregate_peer.cu : multi-GPU reduce-scatter + apply + all-gather over NVLink peer memory (cooperative launch)
 int fedavg_reduce_apply_peer_launch(const float* cp, const float* n, int C, int M, int P, int theta_stride, int world, int rank,
                                     const long long* part_ptrs, const long long* theta_ptrs, const long long* tot_ptrs,
@@ -29,7 +32,7 @@ int adam_amsgrad_rows_launch(float* p, const float* g, float* m, float* v, float
                              long long P, float lr, float wd, float b1, float b2, float eps, cudaStream_t stream);
 int sgd_rows_launch(float* p, const float* g, long long n, float lr, float wd, cudaStream_t stream);
 // cluster_ops.cu
-int gram_launch(const float* U, int n, long long P, double* G, cudaStream_t stream);
+int gram_launch(const float* U, int n, long long P, double eps, double* S, double* nrm, cudaStream_t stream);
 // mpc.cu
 int modp_matmul_launch(const long long* A, const long long* B, long long* C, int M, int K, int N, long long p, cudaStream_t stream);
 // misc.cu

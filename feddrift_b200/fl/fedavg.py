@@ -141,7 +141,6 @@ class FedAvgRobustAggregator(FedAVGAggregator):
         super().__init__(*a, **k)
         self.robust_aggregator = RobustAggregator(self.args)
         self.weight_mask = mutils.weight_param_mask(self.bank.spec).to(self.device)
-        self.noise_gen = torch.Generator(device="cpu").manual_seed(int(getattr(self.args, "dummy_arg", 0)) + 77)
 
     def _prepare_uploads(self) -> None:
         ra = self.robust_aggregator
@@ -151,10 +150,11 @@ class FedAvgRobustAggregator(FedAVGAggregator):
         active = self.upload_n[:, 0] > 0
         if bool(active.any()):
             sel = rows[active]
-            ops.robust_clip_(sel, self.bank.theta[0], ra.norm_bound, self.weight_mask)
-            if ra.defense_type == "weak_dp":
-                noise = torch.randn(sel.shape, generator=self.noise_gen).to(self.device) * ra.stddev
-                sel = sel + noise * self.weight_mask
+            # clip + (weak_dp) Gaussian noise on the weight parameters in ONE fused pass (K10)
+            self._noise_round = getattr(self, "_noise_round", 0) + 1
+            std = float(ra.stddev) if ra.defense_type == "weak_dp" else 0.0
+            ops.robust_clip_(sel, self.bank.theta[0], ra.norm_bound, self.weight_mask, std,
+                             int(getattr(self.args, "dummy_arg", 0)) * 7919 + 77 + self._noise_round)
             rows[active] = sel
 
 

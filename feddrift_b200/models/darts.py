@@ -217,13 +217,50 @@ class EvalCell(nn.Module):
         self._ops = nn.ModuleList(OPS[name](C, 2 if reduction and idx < 2 else 1, True) for name, idx in ops_idx)
         self._indices = [idx for _, idx in ops_idx]
 
-    def forward(self, s0, s1):
+    def forward(self, s0, s1, drop_prob: float = 0.0):
         states = [self.preprocess0(s0), self.preprocess1(s1)]
         for i in range(len(self._ops) // 2):
-            h1 = self._ops[2 * i](states[self._indices[2 * i]])
-            h2 = self._ops[2 * i + 1](states[self._indices[2 * i + 1]])
+            op1, op2 = self._ops[2 * i], self._ops[2 * i + 1]
+            h1, h2 = op1(states[self._indices[2 * i]]), op2(states[self._indices[2 * i + 1]])
+            if self.training and drop_prob > 0.0:   # ``model.py:52-57``: identity edges are never dropped
+                if not isinstance(op1, nn.Identity):
+                    h1 = drop_path(h1, drop_prob)
+                if not isinstance(op2, nn.Identity):
+                    h2 = drop_path(h2, drop_prob)
             states.append(h1 + h2)
         return torch.cat([states[i] for i in self._concat], dim=1)
+
+
+def drop_path(x: torch.Tensor, drop_prob: float) -> torch.Tensor:
+    """Per-sample stochastic depth (``darts/utils.py:82-88``)."""
+    if drop_prob > 0.0:
+        keep = 1.0 - drop_prob
+        mask = torch.empty(x.size(0), 1, 1, 1, device=x.device, dtype=x.dtype).bernoulli_(keep)
+        x = x / keep * mask
+    return x
+
+
+def count_parameters_in_MB(model: nn.Module) -> float:
+    """``darts/utils.py:62-63``: parameters excluding the auxiliary head, in units of 1e6."""
+    return sum(p.numel() for n, p in model.named_parameters() if "auxiliary" not in n) / 1e6
+
+
+def genotype_to_dot(genotype: Genotype, which: str = "normal") -> str:
+    """Graphviz DOT text of a cell (``darts/visualize.py:6-44`` renders the same graph through the graphviz package,
+    which this image does not ship; ``dot -Tpdf`` on the returned text gives the identical picture)."""
+    ops = genotype.normal if which == "normal" else genotype.reduce
+    lines = ["digraph cell {", "  rankdir=LR;", '  node [shape=rect, style=filled, fillcolor=lightblue];',
+             '  "c_{k-2}" [fillcolor=darkseagreen2]; "c_{k-1}" [fillcolor=darkseagreen2];']
+    steps = len(ops) // 2
+    for i in range(steps):
+        for k in (2 * i, 2 * i + 1):
+            name, j = ops[k]
+            src = "c_{k-2}" if j == 0 else "c_{k-1}" if j == 1 else str(j - 2)
+            lines.append(f'  "{src}" -> "{i}" [label="{name}"];')
+    lines.append('  "c_{k}" [fillcolor=palegoldenrod];')
+    lines += [f'  "{i}" -> "c_{{k}}";' for i in range(steps)]
+    lines.append("}")
+    return "\n".join(lines)
 
 
 class NetworkCIFAR(nn.Module):
@@ -257,7 +294,7 @@ class NetworkCIFAR(nn.Module):
         logits_aux = None
         s0 = s1 = self.stem(x)
         for i, cell in enumerate(self.cells):
-            s0, s1 = s1, cell(s0, s1)
+            s0, s1 = s1, cell(s0, s1, self.drop_path_prob)
             if i == 2 * self._layers // 3 and self._auxiliary and self.training:
                 logits_aux = self.auxiliary_head(s1)
         return self.classifier(self.global_pooling(s1).flatten(1)), logits_aux

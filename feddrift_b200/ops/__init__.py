@@ -65,11 +65,12 @@ def weighted_average(rows, weights, out=None):
     return res
 
 
-def robust_clip_(rows, global_row, bound: float, weight_mask=None):
+def robust_clip_(rows, global_row, bound: float, weight_mask=None, stddev: float = 0.0, seed: int = 0):
+    """K10: clip every row around ``global_row`` and (``stddev > 0``) add counter-hash Gaussian noise in the same pass."""
     if native(rows):
         mask = weight_mask.to(torch.uint8).contiguous() if weight_mask is not None else None
-        return _ext.load().robust_clip(rows, global_row.contiguous(), float(bound), mask)
-    return ref.robust_clip_(rows, global_row, bound, weight_mask)
+        return _ext.load().robust_clip(rows, global_row.contiguous(), float(bound), mask, float(stddev), int(seed) & 0xFFFFFFFF)
+    return ref.robust_clip_(rows, global_row, bound, weight_mask, stddev, seed)
 
 
 def server_opt_step_(theta, avg, state: Dict, opt: str, lr: float, **kw):

@@ -292,13 +292,42 @@ def weighted_average(rows: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
     return (rows * w[:, None]).sum(0)
 
 
-def robust_clip_(rows: torch.Tensor, global_row: torch.Tensor, bound: float, weight_mask=None) -> torch.Tensor:
-    """rows[i] <- global + (rows[i]-global)/max(1, ‖diff‖/bound); mask=False entries pass through (K10)."""
+def _mix32_np(x):
+    import numpy as np
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7FEB352D)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846CA68B)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def gauss_hash(seed: int, R: int, P: int) -> torch.Tensor:
+    """[R, P] standard-normal noise: Box–Muller on lowbias32 hashes of (seed, row, element) — bit-compatible inputs
+    with ``gauss_hash`` in csrc/aggregate.cu (P < 2³²)."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        i = np.arange(P, dtype=np.uint32)[None, :]
+        r = np.arange(R, dtype=np.uint32)[:, None]
+        base = _mix32_np(np.uint32(seed & M32) ^ _mix32_np(r * np.uint32(0x9E3779B9) + np.uint32(0x7F4A7C15)))
+        h1 = _mix32_np(base ^ (i * np.uint32(2) + np.uint32(1)))
+        h2 = _mix32_np(base ^ (i * np.uint32(2) + np.uint32(2)) ^ np.uint32(0x68E31DA4))
+    u1 = ((h1 >> np.uint32(8)).astype(np.float64) + 1.0) / 16777216.0
+    u2 = (h2 >> np.uint32(8)).astype(np.float64) / 16777216.0
+    return torch.from_numpy((np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)).astype(np.float32))
+
+
+def robust_clip_(rows: torch.Tensor, global_row: torch.Tensor, bound: float, weight_mask=None, stddev: float = 0.0,
+                 seed: int = 0) -> torch.Tensor:
+    """rows[i] <- global + (rows[i]-global)/max(1, ‖diff‖/bound) (+ stddev·N(0,1)); mask=False entries pass through (K10)."""
     diff = rows - global_row
     d = diff if weight_mask is None else diff * weight_mask
     norm = d.norm(dim=1, keepdim=True)
     scale = 1.0 / torch.clamp(norm / bound, min=1.0)
     new = global_row + diff * scale
+    if stddev:
+        new = new + stddev * gauss_hash(seed, rows.shape[0], rows.shape[1]).to(rows.device)
     if weight_mask is not None:
         new = torch.where(weight_mask.bool(), new, rows)
     rows.copy_(new)

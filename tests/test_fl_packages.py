@@ -85,6 +85,17 @@ def test_distributed_fedavg_inproc(robust):
     assert torch.isfinite(srv.aggregator.bank.theta).all()
 
 
+def test_weak_dp_noise_is_standard_normal_and_deterministic():
+    from feddrift_b200.ops import reference as ref
+    z = ref.gauss_hash(7, 4, 50000)
+    assert torch.equal(z, ref.gauss_hash(7, 4, 50000)) and not torch.equal(z, ref.gauss_hash(8, 4, 50000))
+    assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 1.0) < 0.01
+    assert abs(torch.corrcoef(z[:2])[0, 1].item()) < 0.02        # rows are independent streams
+    rows, g = torch.zeros(2, 1000), torch.zeros(1000)
+    ref.robust_clip_(rows, g, 1.0, None, 0.5, 3)
+    assert abs(rows.std().item() - 0.5) < 0.05
+
+
 def test_robust_clipping_bounds_the_update():
     from feddrift_b200.fl.fedavg import FedAvgRobustAggregator
     ds, _ = _dataset()
@@ -223,3 +234,15 @@ def test_turboaggregate_primitives_and_secure_average():
     Ux, w = torch.randn(6, 40), torch.rand(6) + 0.1
     out = agg.aggregate(Ux, w, dropped=[0, 5])
     assert (out - (Ux * (w / w.sum())[:, None]).sum(0)).abs().max() < 1e-3
+
+
+def test_darts_standalone_search_then_train(tmp_path):
+    """``darts/train_search.py`` + ``darts/train.py`` parity CLI: search (MiLeNAS step) → genotype.json → train it."""
+    from feddrift_b200.experiments import darts as cli
+    common = ["--epochs", "1", "--layers", "3", "--init_channels", "4", "--n_train", "64", "--batch_size", "32",
+              "--model_path", str(tmp_path)]
+    out = cli.main(["search", "--optimization", "DARTS_V2"] + common)
+    assert len(out["genotype"].normal) == 8 and (tmp_path / "genotype.json").exists()
+    assert "digraph" in (tmp_path / "normal.dot").read_text()
+    out = cli.main(["train", "--arch", str(tmp_path / "genotype.json"), "--auxiliary", "--cutout"] + common)
+    assert len(out["history"]) == 1 and (tmp_path / "weights.pt").exists()

@@ -266,7 +266,9 @@ std::vector<Tensor> gram_cosine(Tensor U, double eps) {
     const int n = (int)U.size(0);
     auto S = torch::empty({n, n}, U.options().dtype(torch::kFloat64));
     auto nrm = torch::empty({n}, U.options().dtype(torch::kFloat64));
-    const int rc = fdb::gram_launch(U.data_ptr<float>(), n, U.size(1), eps, S.data_ptr<double>(), nrm.data_ptr<double>(), cur_stream());
+    auto part = torch::empty({fdb::gram_workspace_doubles()}, S.options());   // caching allocator: no driver call on the hot path
+    const int rc = fdb::gram_launch(U.data_ptr<float>(), n, U.size(1), eps, S.data_ptr<double>(), nrm.data_ptr<double>(),
+                                    part.data_ptr<double>(), cur_stream());
     if (rc == -5) {  // > 32 rows: library GEMM (cold path)
         auto G = torch::matmul(U.to(torch::kFloat64), U.to(torch::kFloat64).t());
         nrm = torch::sqrt(torch::diagonal(G));
@@ -351,6 +353,30 @@ Tensor gemm_tn_bias_act_peer(Tensor A, int64_t b_ptr, int64_t N, c10::optional<T
     return D;
 }
 
+// conv-as-GEMM helpers (csrc/conv_im2col.cu): x may be NCHW or channels_last — strides are passed through
+Tensor im2col_bf16(Tensor x, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph, int64_t pw) {
+    CHECK_CUDA_F32(x);
+    TORCH_CHECK(x.dim() == 4, "im2col: x must be [B, C, H, W]");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int B = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+    const int Ho = (int)((H + 2 * ph - kh) / sh + 1), Wo = (int)((W + 2 * pw - kw) / sw + 1);
+    auto cols = torch::empty({(int64_t)B * Ho * Wo, (int64_t)C * kh * kw}, x.options().dtype(torch::kBFloat16));
+    CHECK_OK(fdb::im2col_bf16_launch(x.data_ptr<float>(), cols.data_ptr(), B, C, H, W, (int)kh, (int)kw, (int)sh, (int)sw, (int)ph, (int)pw,
+                                     Ho, Wo, x.stride(0), x.stride(1), x.stride(2), x.stride(3), cur_stream()), "im2col");
+    return cols;
+}
+Tensor col2im(Tensor dcols, int64_t B, int64_t C, int64_t H, int64_t W, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t ph,
+              int64_t pw) {
+    CHECK_CUDA_F32(dcols);
+    c10::cuda::CUDAGuard guard(dcols.device());
+    const int Ho = (int)((H + 2 * ph - kh) / sh + 1), Wo = (int)((W + 2 * pw - kw) / sw + 1);
+    TORCH_CHECK(dcols.is_contiguous() && dcols.size(0) == B * Ho * Wo && dcols.size(1) == C * kh * kw, "col2im: bad dcols shape");
+    auto dx = torch::empty({B, C, H, W}, dcols.options());
+    CHECK_OK(fdb::col2im_launch(dcols.data_ptr<float>(), dx.data_ptr<float>(), (int)B, (int)C, (int)H, (int)W, (int)kh, (int)kw, (int)sh,
+                                (int)sw, (int)ph, (int)pw, Ho, Wo, cur_stream()), "col2im");
+    return dx;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -379,4 +405,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("gemm_tn_bias_act", &gemm_tn_bias_act);
     m.def("gemm_tn_bias_act_peer", &gemm_tn_bias_act_peer);
     m.def("gossip_mix_peer", &gossip_mix_peer);
+    m.def("im2col_bf16", &im2col_bf16);
+    m.def("col2im", &col2im);
 }

@@ -12,6 +12,10 @@ int weighted_average_launch(const float* rows, const float* w, int n, long long 
 int merge_axpby_launch(float* base_row, const float* second_row, float w1, float w2, long long P, cudaStream_t stream);
 int sq_diff_sum_launch(const float* a, const float* b, long long P, double* out, cudaStream_t stream);
 int gossip_mix_launch(const float* X, const float* Wm, int n, long long P, float* out, cudaStream_t stream);
+int im2col_bf16_launch(const float* x, void* cols, int B, int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, int Ho, int Wo,
+                       long long sxb, long long sxc, long long sxh, long long sxw, cudaStream_t stream);
+int col2im_launch(const float* dcols, float* dx, int B, int C, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw, int Ho, int Wo,
+                  cudaStream_t stream);
 int gossip_mix_peer_launch(const long long* x_ptrs, const long long* flag_ptrs, const float* w, int P, int world, int rank,
                            unsigned* grid_sync, unsigned grid_base, unsigned epoch, int grid, long long timeout_ms, int* error_flag,
                            cudaStream_t stream);
@@ -32,7 +36,8 @@ int adam_amsgrad_rows_launch(float* p, const float* g, float* m, float* v, float
                              long long P, float lr, float wd, float b1, float b2, float eps, cudaStream_t stream);
 int sgd_rows_launch(float* p, const float* g, long long n, float lr, float wd, cudaStream_t stream);
 // cluster_ops.cu
-int gram_launch(const float* U, int n, long long P, double eps, double* S, double* nrm, cudaStream_t stream);
+long long gram_workspace_doubles();
+int gram_launch(const float* U, int n, long long P, double eps, double* S, double* nrm, double* part, cudaStream_t stream);
 // mpc.cu
 int modp_matmul_launch(const long long* A, const long long* B, long long* C, int M, int K, int N, long long p, cudaStream_t stream);
 // misc.cu

@@ -31,8 +31,14 @@ class LogisticRegression(nn.Module):
 class FeedForwardNN(nn.Module):
     def __init__(self, input_dim: int, output_dim: int, hidden_dim: int):
         super().__init__()
-        self.fc1 = nn.Linear(input_dim, hidden_dim)
-        self.relu = nn.ReLU()
+        if input_dim >= 64:
+            # fnn-MNIST (784→1568→10): first layer on the tcgen05 GEMM with the ReLU fused into its epilogue
+            from ..ops.linear import TcLinear
+            self.fc1 = TcLinear(input_dim, hidden_dim, activation="relu")
+            self.relu = nn.Identity()
+        else:
+            self.fc1 = nn.Linear(input_dim, hidden_dim)
+            self.relu = nn.ReLU()
         self.fc2 = nn.Linear(hidden_dim, output_dim)
 
     def forward(self, x):

@@ -20,6 +20,7 @@ from torch import nn
 
 from . import _ext
 
+TC_CALLS = 0      # number of forward passes that went through the tcgen05 kernel (tests assert the path is live)
 _MIN_TC_DIM = 64  # below this a GEMM is launch-bound; SIMT/cuBLASLt-free eager is fine
 
 
@@ -28,12 +29,15 @@ def _tc_eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
         return False
     n, k = weight.shape
     rows = x.numel() // max(k, 1)
-    return k % 16 == 0 and n % 16 == 0 and k >= _MIN_TC_DIM and n >= 16 and rows >= 16
+    # TMA needs a 16-byte row pitch (K % 8 for bf16); K / M / N tails are zero-filled / clipped by the tensor maps
+    return k % 8 == 0 and n % 8 == 0 and k >= _MIN_TC_DIM and n >= 16 and rows >= 16
 
 
 class _TcLinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, relu: bool):
+        global TC_CALLS
+        TC_CALLS += 1
         ext = _ext.load(required=True)
         x2 = x.reshape(-1, x.shape[-1])
         xb = x2.to(torch.bfloat16).contiguous()
@@ -58,8 +62,12 @@ class _TcLinearFn(torch.autograd.Function):
             # dX[B,K] = dY[B,N] · W[N,K]  ->  TN form with B-operand = Wᵀ [K,N] (K-major in N)
             gx = ext.gemm_tn_bias_act(gb, wb.t().contiguous(), None, False, True).reshape(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            # dW[N,K] = dYᵀ[N,B] · X[B,K]  ->  A = dYᵀ [N,B], B-operand = Xᵀ [K,B]
-            gw = ext.gemm_tn_bias_act(gb.t().contiguous(), xb.t().contiguous(), None, False, True)
+            # dW[N,K] = dYᵀ[N,B] · X[B,K]  ->  A = dYᵀ [N,B], B-operand = Xᵀ [K,B]; the reduction dim is the batch,
+            # which must give a 16-byte row pitch (B % 8) — odd federated batch sizes use the library GEMM
+            if gb.shape[0] % 8 == 0:
+                gw = ext.gemm_tn_bias_act(gb.t().contiguous(), xb.t().contiguous(), None, False, True)
+            else:
+                gw = (gb.t() @ xb).float()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gbias = g.sum(0)
         return gx, gw, gbias, None
@@ -82,8 +90,7 @@ class TcLinear(nn.Module):
 
     def forward(self, x):
         relu = self.activation == "relu"
-        if _tc_eligible(x, self.weight) and x.shape[-1] % 64 == 0 and _ext.available() \
-                and hasattr(_ext.load(), "gemm_tn_bias_act"):
+        if _tc_eligible(x, self.weight) and _ext.available() and hasattr(_ext.load(), "gemm_tn_bias_act"):
             return _TcLinearFn.apply(x, self.weight, self.bias, relu)
         y = F.linear(x, self.weight, self.bias)
         return F.relu(y) if relu else y

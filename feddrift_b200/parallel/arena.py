@@ -49,6 +49,13 @@ class ModelBank:
         self.storage = storage
         self.theta = storage[:, : self.P] if self.stride != self.P else storage
         self.mlp = self.template.mlp_spec() if hasattr(self.template, "mlp_spec") else None
+        if self.mlp is not None and self.device.type == "cuda":
+            # the register-resident MLP kernels are instantiated for the small drift-benchmark shapes only
+            # (csrc/mlp.cuh FDB_MLP_SHAPES); bigger MLPs (fnn-MNIST 784→1568→10) take the nn.Module / TcLinear path
+            from ..ops import small_round
+            s_ = self.mlp
+            if not small_round.supported(s_["kind"], s_["in"], s_["hidden"], s_["out"]):
+                self.mlp = None
         # "every re-initialised model is identical" (reference reseeds before reset_parameters)
         mutils.reinitialize(self.template)
         self.init_row = mutils.flatten_state_dict(self.template.state_dict()).to(self.device)

@@ -187,7 +187,7 @@ class DriftSim:
                 block = min(block, rpl)
             if self.multi is not None:
                 block = min(block, int(self.multi["metrics_rounds"]))
-            if self.spec is not None and self.algo.fused_ok():
+            if self.spec is not None and self.algo.fused_ok() and not getattr(self, "shard_clients", False):
                 st = self._small_state()
                 st["round0"] = self.round_in_step
                 out = ops.fed_round_small(st, block)

@@ -8,7 +8,14 @@ architecture and for algorithms that must look at raw client updates before aggr
 * local step: bank-bound ``nn.Module`` forward/backward (TcLinear → tcgen05 GEMM; convs/LSTMs → library kernels),
   gradients land in a flat scratch row, ``ops.adam_amsgrad_rows_`` / ``ops.sgd_rows_`` update the client row;
 * aggregation: ``ops.cluster_aggregate_`` over the ``[C, M, P]`` client arena (K1);
-* evaluation: ``ops.eval_logits`` device-side accumulation, ONE host copy per block of rounds.
+* evaluation: clients are grouped by the model they are scored with → one batched forward per (model, split), per-client
+  sums by masked reduction on device, ONE host copy per block of rounds.
+
+The per-(client, model) local step is launch-bound for every architecture in the zoo at federated batch sizes (a CNN
+step is ~60 small kernels), so on CUDA it is captured ONCE into a CUDA graph over static buffers (``_GraphedStep``:
+parameters, optimizer moments, gradient row, batch) and replayed for every pair and step; gradients accumulate directly
+into a flat row because each parameter's ``.grad`` is a view of it (no per-tensor gather).  ``FDB_NO_GRAPHS=1`` or a
+failed capture falls back to eager execution of the same ops.
 """
 from __future__ import annotations
 
@@ -121,20 +128,125 @@ def _cpu(x: Optional[torch.Tensor]):
     return x.cpu() if isinstance(x, torch.Tensor) else x
 
 
+class _GraphedStep:
+    """One local step (zero-grad → forward → CE → backward → fused optimizer row update) captured as a CUDA graph."""
+
+    def __init__(self, sim, batch_shape, use_adam: bool, lr: float, wd: float):
+        import copy
+        bank, dev = sim.bank, sim.device
+        P = bank.P
+        z = lambda: torch.zeros(P, dtype=torch.float32, device=dev)  # noqa: E731
+        self.row, self.g, self.m, self.v, self.vmax = z(), z(), z(), z(), z()
+        self.step = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.x = torch.zeros(batch_shape, dtype=sim.data.X.dtype, device=dev)
+        self.y = torch.zeros(batch_shape[0], dtype=torch.long, device=dev)
+        self.row.copy_(bank.theta[0])
+        self.mod = copy.deepcopy(bank.template).to(dev)
+        _bind(self.mod, bank, self.row)
+        self.mod.train()
+        from ..models.utils import unflatten_to_state_dict
+        gviews = unflatten_to_state_dict(self.g, bank.spec)
+        for name, p_ in self.mod.named_parameters():
+            p_.grad = gviews[name]          # backward accumulates straight into the flat gradient row
+        self.use_adam, self.lr, self.wd = use_adam, lr, wd
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):              # warm-up (cuDNN autotune, lazy inits) outside the capture
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches = 0
+
+    def _body(self):
+        self.g.zero_()
+        F.cross_entropy(self.mod(self.x), self.y).backward()
+        if self.use_adam:
+            ops.adam_amsgrad_rows_(self.row.view(1, -1), self.g.view(1, -1), self.m.view(1, -1), self.v.view(1, -1),
+                                   self.vmax.view(1, -1), self.step, self.lr, self.wd)
+        else:
+            ops.sgd_rows_(self.row.view(1, -1), self.g.view(1, -1), self.lr, 0.0)
+
+    def load(self, cl, c, m):
+        self.row.copy_(cl.params[c, m])
+        if self.use_adam:
+            self.m.copy_(cl.m[c, m]); self.v.copy_(cl.v[c, m]); self.vmax.copy_(cl.vmax[c, m])
+            self.step.copy_(cl.step[c, m].reshape(1))
+
+    def store(self, cl, c, m):
+        cl.params[c, m].copy_(self.row)
+        if self.use_adam:
+            cl.m[c, m].copy_(self.m); cl.v[c, m].copy_(self.v); cl.vmax[c, m].copy_(self.vmax)
+            cl.step[c, m].copy_(self.step[0])
+
+    def run(self, xb, yb):
+        self.x.copy_(xb)
+        self.y.copy_(yb)
+        self.graph.replay()
+        self.launches += 1
+
+
+def _graphed_step(sim, batch_shape, use_adam, lr, wd):
+    """Cached ``_GraphedStep`` for this (batch shape, optimizer, lr) or None when graphs are unavailable."""
+    import os
+    if sim.device.type != "cuda" or sim.bank.mlp is not None or os.environ.get("FDB_NO_GRAPHS") == "1" \
+            or getattr(sim, "_graphs_broken", False):
+        return None
+    cache = sim.__dict__.setdefault("_step_graphs", {})
+    key = (tuple(batch_shape), bool(use_adam), float(lr), float(wd))
+    gs = cache.get(key)
+    if gs is None:
+        if len(cache) >= 2:                 # e.g. Adaptive-FedAvg changes lr every round: keep the pool small
+            cache.pop(next(iter(cache)))
+        try:
+            gs = cache[key] = _GraphedStep(sim, batch_shape, use_adam, lr, wd)
+        except Exception as exc:  # noqa: BLE001  (capture is an optimisation; the eager path is always valid)
+            import logging
+            logging.warning("CUDA-graph capture of the local step failed (%s); running eagerly", exc)
+            sim._graphs_broken = True
+            torch.cuda.synchronize()
+            return None
+    return gs
+
+
 def _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, wd, feat_mask):
     bank, cl = sim.bank, sim.clients
     row = cl.params[c, m]
     mlp = bank.mlp
+    idxs = []
+    for step in range(E):
+        h1 = batch_hash(seed, rnd, c, m, step)
+        idxs.append(sampler(h1, mix32(h1 ^ 0x68E31DA4)))
+    # one H2D + one gather for all E minibatches of this pair when they have equal length (the common case)
+    same = all(i.numel() == idxs[0].numel() for i in idxs)
+    if same:
+        idx_all = torch.stack(idxs).to(Xc.device, non_blocking=True)
+        xs, ys = Xc[idx_all], Yc[idx_all].long()
+        if feat_mask is not None:
+            xs = xs * feat_mask[m].reshape((1, 1) + tuple(xs.shape[2:]))
+        batches = [(xs[e], ys[e]) for e in range(E)]
+    else:
+        batches = []
+        for i in idxs:
+            i = i.to(Xc.device)
+            xb = Xc[i]
+            if feat_mask is not None:
+                xb = xb * feat_mask[m].reshape((1,) + tuple(xb.shape[1:]))
+            batches.append((xb, Yc[i].long()))
+    gs = _graphed_step(sim, batches[0][0].shape, use_adam, lr, wd) if same else None
+    if gs is not None:
+        gs.load(cl, c, m)
+        for xb, yb in batches:
+            gs.run(xb, yb)
+        gs.store(cl, c, m)
+        return
     if mlp is None:
         mod = _scratch_module(sim)
         _bind(mod, bank, row)
         mod.train()
-    for step in range(E):
-        h1 = batch_hash(seed, rnd, c, m, step)
-        idx = sampler(h1, mix32(h1 ^ 0x68E31DA4)).to(Xc.device)
-        xb, yb = Xc[idx], Yc[idx].long()
-        if feat_mask is not None:
-            xb = xb * feat_mask[m].reshape((1,) + tuple(xb.shape[1:]))
+    for xb, yb in batches:
         if mlp is not None:
             th = row.detach().clone().requires_grad_(True)
             logits = ops.mlp_forward(th, xb.reshape(xb.shape[0], -1), mlp["kind"], mlp["in"], mlp["hidden"], mlp["out"])
@@ -182,39 +294,60 @@ def _flat_grads(mod, bank, row):
     return g
 
 
+def _eval_grouped(sim, tt: int, models, clients, out, col: int):
+    """Score client c with model ``models[c]`` on its time-``tt`` data for every c in ``clients``: ONE batched forward per
+    distinct model (chunked to ≤ ~8k samples), per-client (correct, loss-sum) by masked reduction → ``out[c, col:col+2]``."""
+    data, bank = sim.data, sim.bank
+    S = data.X.shape[2]
+    nsamp = sim.data_host.nsamp[tt]
+    by_model: Dict[int, list] = {}
+    for c in clients:
+        if int(nsamp[c]) > 0:
+            by_model.setdefault(int(models[c]), []).append(c)
+    per_chunk = max(1, 8192 // max(S, 1))
+    ar = torch.arange(S, device=sim.device)
+    for m, cs in by_model.items():
+        for i in range(0, len(cs), per_chunk):
+            ck = cs[i:i + per_chunk]
+            ct = torch.tensor(ck, device=sim.device)
+            X = data.X[tt].index_select(0, ct)
+            Y = data.Y[tt].index_select(0, ct).long()
+            mask = (ar[None, :] < nsamp[ck].to(sim.device)[:, None]).float()
+            logits = bank.forward(m, X.reshape(len(ck) * S, *X.shape[2:])).float()
+            loss = F.cross_entropy(logits, Y.reshape(-1), reduction="none").reshape(len(ck), S)
+            hit = (logits.argmax(-1) == Y.reshape(-1)).float().reshape(len(ck), S)
+            out[ct, col] = (hit * mask).sum(1)
+            out[ct, col + 1] = (loss * mask).sum(1)
+
+
 def _evaluate(sim, plan, st, r, metrics, ens_mode):
     data, bank, t, C = sim.data, sim.bank, sim.t, sim.C
     pick = st["W"][t].argmax(dim=0)
     etr, ete = plan.get("eval_train_model"), plan.get("eval_test_model")
-    acc = torch.zeros(3, dtype=torch.float32, device=sim.device)
     world, rank = _world_rank(sim)
+    mine = [c for c in range(C) if world == 1 or c % world == rank]
+    mtr = [int(etr[c]) if etr is not None and int(etr[c]) >= 0 else int(pick[c]) for c in range(C)]
+    mte = [int(ete[c]) if ete is not None and int(ete[c]) >= 0 else int(pick[c]) for c in range(C)]
     with torch.no_grad():
-        for c in range(C):
-            if world > 1 and c % world != rank:
-                continue
-            mtr = int(etr[c]) if etr is not None and int(etr[c]) >= 0 else int(pick[c])
-            mte = int(ete[c]) if ete is not None and int(ete[c]) >= 0 else int(pick[c])
-            n0 = int(sim.data_host.nsamp[t, c])
-            if n0:
-                acc.zero_()
-                ops.eval_logits(bank.forward(mtr, data.X[t, c, :n0]), data.Y[t, c, :n0], acc)
-                metrics[r, c, 0:2] = acc[0:2]
+        _eval_grouped(sim, t, mtr, mine, metrics[r], 0)
+        if ens_mode == 0 and t + 1 < data.steps:
+            _eval_grouped(sim, t + 1, mte, mine, metrics[r], 2)
+    if ens_mode == 0:
+        return
+    acc = torch.zeros(3, dtype=torch.float32, device=sim.device)
+    with torch.no_grad():
+        for c in mine:
             if t + 1 < data.steps:
                 n1 = int(sim.data_host.nsamp[t + 1, c])
                 if n1 == 0:
                     continue
                 x1, y1 = data.X[t + 1, c, :n1], data.Y[t + 1, c, :n1]
-                if ens_mode == 0:
-                    acc.zero_()
-                    ops.eval_logits(bank.forward(mte, x1), y1, acc)
-                    metrics[r, c, 2:4] = acc[0:2]
+                w = plan["ens_w"][c]
+                ks = [k for k in range(bank.num_models) if float(w[k]) > 0]
+                if ens_mode == 1:
+                    preds = torch.stack([bank.forward(k, x1).argmax(-1) for k in ks])
+                    vote = ops.ensemble_vote(preds, w[ks].to(sim.device), data.class_num)
                 else:
-                    w = plan["ens_w"][c]
-                    ks = [k for k in range(bank.num_models) if float(w[k]) > 0]
-                    if ens_mode == 1:
-                        preds = torch.stack([bank.forward(k, x1).argmax(-1) for k in ks])
-                        vote = ops.ensemble_vote(preds, w[ks].to(sim.device), data.class_num)
-                    else:
-                        probs = torch.stack([torch.softmax(bank.forward(k, x1), 1) for k in ks])
-                        vote = ops.soft_vote(probs, w[ks].to(sim.device))
-                    metrics[r, c, 2] = (vote == y1).sum().float()
+                    probs = torch.stack([torch.softmax(bank.forward(k, x1), 1) for k in ks])
+                    vote = ops.soft_vote(probs, w[ks].to(sim.device))
+                metrics[r, c, 2] = (vote == y1).sum().float()

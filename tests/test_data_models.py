@@ -82,3 +82,20 @@ def test_model_bank_views_and_flat_roundtrip():
     flat = flatten_state_dict(tmpl.state_dict())
     back = unflatten_to_state_dict(flat, flat_spec(tmpl))
     assert all(torch.equal(back[k], v) for k, v in tmpl.state_dict().items()) and flat_size(tmpl) == 38
+
+
+def test_tcconv2d_is_a_drop_in_for_nn_conv2d():
+    """Same state-dict keys / init law / CPU numerics as nn.Conv2d (the CUDA path is checked in tests/test_gpu_kernels.py)."""
+    import torch
+    from torch import nn
+    from feddrift_b200.ops.conv import TcConv2d
+    torch.manual_seed(3)
+    a = TcConv2d(8, 16, 3, stride=2, padding=1)
+    torch.manual_seed(3)
+    b = nn.Conv2d(8, 16, 3, stride=2, padding=1)
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    assert torch.equal(a.weight, b.weight) and torch.equal(a.bias, b.bias)
+    x = torch.randn(2, 8, 9, 9)
+    assert torch.allclose(a(x), b(x), atol=1e-6)
+    from feddrift_b200.models.cnn import CNN_DropOut
+    assert sum(p.numel() for p in CNN_DropOut().parameters()) == 1_199_882

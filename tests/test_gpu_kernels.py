@@ -131,12 +131,16 @@ def test_tcgen05_gemm(mnk):
     assert err < 2e-2 * max(1.0, want.abs().max().item()), err
 
 
-def test_tclinear_forward_backward():
+@pytest.mark.parametrize("batch", [100, 104, 50])   # 104: dW on tcgen05 too (B % 8 == 0); 100 / 50: library dW
+def test_tclinear_forward_backward(batch):
+    from feddrift_b200.ops import linear
     from feddrift_b200.ops.linear import TcLinear
     torch.manual_seed(0)
-    lin = TcLinear(784, 1568, activation="relu").cuda()
-    x = torch.randn(100, 784, device="cuda", requires_grad=True)
+    lin = TcLinear(784, 1568, activation="relu").cuda()   # K = 784 is not a multiple of the 64-wide k-block: TMA zero-fill
+    x = torch.randn(batch, 784, device="cuda", requires_grad=True)
+    before = linear.TC_CALLS
     y = lin(x)
+    assert linear.TC_CALLS == before + 1, "TcLinear did not take the tcgen05 path"
     y.square().mean().backward()
     xr = x.detach().clone().requires_grad_(True)
     yr = torch.relu(F.linear(xr, lin.weight.detach(), lin.bias.detach()))
@@ -146,3 +150,28 @@ def test_tclinear_forward_backward():
     assert torch.allclose(y, yr, rtol=3e-2, atol=3e-2)
     assert torch.allclose(x.grad, xr.grad, rtol=5e-2, atol=2e-3)
     assert torch.allclose(lin.weight.grad, wr.grad, rtol=5e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("geom", [(32, 64, 3, 1, 0, 28), (64, 128, 3, 2, 1, 17), (32, 64, 5, 1, 2, 14), (64, 64, 1, 1, 0, 8)])
+def test_tcconv2d_forward_backward_matches_conv2d(geom):
+    """im2col + tcgen05 GEMM conv vs F.conv2d in fp32 (bf16 operand tolerance), incl. stride 2 / padding / 1×1."""
+    from feddrift_b200.ops import conv
+    cin, cout, k, stride, pad, hw = geom
+    torch.manual_seed(1)
+    layer = conv.TcConv2d(cin, cout, k, stride=stride, padding=pad, activation="relu").cuda()
+    x = torch.randn(10, cin, hw, hw, device="cuda", requires_grad=True)
+    before = conv.TC_CONV_CALLS
+    y = layer(x)
+    assert conv.TC_CONV_CALLS == before + 1, "TcConv2d did not take the tcgen05 path"
+    y.square().mean().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    wr = layer.weight.detach().clone().requires_grad_(True)
+    br = layer.bias.detach().clone().requires_grad_(True)
+    yr = torch.relu(F.conv2d(xr, wr, br, stride, pad))
+    yr.square().mean().backward()
+    assert y.shape == yr.shape
+    assert torch.allclose(y, yr, rtol=3e-2, atol=3e-2)
+    scale = xr.grad.abs().max().item()
+    assert (x.grad - xr.grad).abs().max().item() < 3e-2 * scale + 1e-5
+    assert (layer.weight.grad - wr.grad).abs().max().item() < 3e-2 * wr.grad.abs().max().item() + 1e-5
+    assert (layer.bias.grad - br.grad).abs().max().item() < 3e-2 * br.grad.abs().max().item() + 1e-5

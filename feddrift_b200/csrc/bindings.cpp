@@ -335,6 +335,24 @@ Tensor gemm_tn_bias_act(Tensor A, Tensor B, c10::optional<Tensor> bias, bool rel
     return D;
 }
 
+// General operand layouts: A is [M,K] (a_mn = false) or [K,M] (a_mn = true); B is [N,K] (b_mn = false) or [K,N] (b_mn = true);
+// D[M,N] = act(A·B + bias) with the reduction over K.  Lets the backward GEMMs consume row-major tensors without transposes.
+Tensor gemm_bias_act(Tensor A, Tensor B, bool a_mn, bool b_mn, c10::optional<Tensor> bias, bool relu, bool out_fp32) {
+    TORCH_CHECK(A.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm needs CUDA bf16 operands");
+    TORCH_CHECK(A.is_contiguous() && B.is_contiguous() && A.dim() == 2 && B.dim() == 2, "gemm: contiguous 2-D operands");
+    c10::cuda::CUDAGuard guard(A.device());
+    const int M = (int)A.size(a_mn ? 1 : 0), K = (int)A.size(a_mn ? 0 : 1), N = (int)B.size(b_mn ? 1 : 0);
+    TORCH_CHECK(B.size(b_mn ? 0 : 1) == K, "gemm: reduction lengths differ");
+    auto D = torch::empty({M, N}, A.options().dtype(out_fp32 ? torch::kFloat32 : torch::kBFloat16));
+    const float* bp = nullptr;
+    Tensor bias_f;
+    if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
+    const int rc = fdb::gemm_launch(A.data_ptr(), B.data_ptr(), D.data_ptr(), bp, M, N, K, a_mn ? 1 : 0, b_mn ? 1 : 0, relu ? 1 : 0,
+                                    out_fp32 ? 1 : 0, cur_stream());
+    CHECK_OK(rc, "gemm (tcgen05)");
+    return D;
+}
+
 // K2 (consumer-pull broadcast): the weight matrix B[N,K] stays in the OWNER GPU's symmetric-memory arena; `b_ptr` is
 // the peer-mapped device pointer.  The TMA producer of the GEMM pulls B tiles straight over NVLink inside the tile loop,
 // so "broadcast the model, then run the first layer" is one kernel and no local copy of the weights ever exists.
@@ -404,6 +422,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("group_norm_fwd", &group_norm_fwd);
     m.def("gemm_tn_bias_act", &gemm_tn_bias_act);
     m.def("gemm_tn_bias_act_peer", &gemm_tn_bias_act_peer);
+    m.def("gemm_bias_act", &gemm_bias_act);
     m.def("gossip_mix_peer", &gossip_mix_peer);
     m.def("im2col_bf16", &im2col_bf16);
     m.def("col2im", &col2im);

@@ -11,6 +11,11 @@
 //     (tmem_full / tmem_empty mbarrier pair per buffer);
 //   * split-K (grid.z) for skinny outputs (e.g. 512×128×9216): partial tiles are accumulated with fp32 atomics into a
 //     zeroed output and bias/activation are applied by a small second kernel.
+//   * operand layouts: each of A and B may be K-major ([rows, K], the "TN" form) or MN-major ([K, rows], rows
+//     contiguous).  MN-major tiles are fetched as 64×64 TMA boxes (128-byte rows along M/N, 8-row swizzle atoms along
+//     K) and described to the tensor core with the MN-major canonical layout (LBO = 8 KB between 64-wide M/N groups,
+//     SBO = 1 KB between 8-row K groups, a_major/b_major bits of the instruction descriptor), so the backward GEMMs
+//     dX = dY·W and dW = dYᵀ·X run directly on the row-major tensors autograd hands us — no transpose kernels.
 // All waits are bounded (trap after 2 s) so a protocol bug faults the context instead of hanging the GPU.
 // The reference's equivalent is eager `nn.Linear` + separate bias/ReLU kernels in fp32 on cuBLAS
 // (fedml_api/model/fnn/fnn.py:11-15, cv/cnn.py:128-136).
@@ -105,6 +110,17 @@ FDB_DEVICE uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
     return d;
 }
+// MN-major, 128B-swizzled operand tile: 64-element (128 B) rows along M/N, 8 K-rows per 1024-B atom (SBO); the next
+// 64-wide M/N group starts 64 K-rows × 128 B = 8192 B later (LBO)
+FDB_DEVICE uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((8192u) >> 4) << 16;                 // leading byte offset
+    d |= (uint64_t)((1024u) >> 4) << 32;                 // stride byte offset
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 FDB_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -122,7 +138,7 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, void* __restrict__ D, const float* __restrict__ bias, int M, int N, int K,
-               int relu, int out_fp32, int splits, int tma_out) {
+               int relu, int out_fp32, int splits, int tma_out, int a_mn, int b_mn) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -172,8 +188,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar + s, ph ^ 1);
                     mbar_expect_tx(full_bar + s, kStageBytesA + Cfg::kStageBytesB);
-                    tma_load_2d(&map_a, full_bar + s, smem_a + s * kStageBytesA, kb * BK, m_blk * BM);
-                    tma_load_2d(&map_b, full_bar + s, smem_b + s * Cfg::kStageBytesB, kb * BK, n_blk * BN);
+                    uint8_t* sa = smem_a + s * kStageBytesA;
+                    uint8_t* sb = smem_b + s * Cfg::kStageBytesB;
+                    if (a_mn) {   // [K, M] tensor: two 64(M)×64(K) boxes
+#pragma unroll
+                        for (int h = 0; h < BM / 64; ++h) tma_load_2d(&map_a, full_bar + s, sa + h * 8192, m_blk * BM + h * 64, kb * BK);
+                    } else {
+                        tma_load_2d(&map_a, full_bar + s, sa, kb * BK, m_blk * BM);
+                    }
+                    if (b_mn) {
+#pragma unroll
+                        for (int h = 0; h < BN / 64; ++h) tma_load_2d(&map_b, full_bar + s, sb + h * 8192, n_blk * BN + h * 64, kb * BK);
+                    } else {
+                        tma_load_2d(&map_b, full_bar + s, sb, kb * BK, n_blk * BN);
+                    }
                 }
             }
         }
@@ -185,6 +213,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(tmem_empty + acc, aph ^ 1);   // epilogue has drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t d_addr = tmem_base + acc * BN;
+                const uint32_t idesc = Cfg::kIdesc | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -194,8 +223,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint32_t b_addr = smem_u32(smem_b + s * Cfg::kStageBytesB);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_f16(d_addr, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2),
-                                 Cfg::kIdesc, (kb | k) != 0 ? 1u : 0u);
+                    {
+                        // K-major: 16 K-elements = 32 B along the row; MN-major: 16 K-rows = two 1024-B atoms
+                        const uint64_t da = a_mn ? make_smem_desc_mn(a_addr + k * 2048) : make_smem_desc(a_addr + k * UMMA_K * 2);
+                        const uint64_t db = b_mn ? make_smem_desc_mn(b_addr + k * 2048) : make_smem_desc(b_addr + k * UMMA_K * 2);
+                        umma_f16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     tcgen05_commit(empty_bar + s);  // frees the smem stage once these MMAs retire
                 }
                 tcgen05_commit(tmem_full + acc);    // accumulator complete → epilogue
@@ -388,9 +421,23 @@ static int make_out_map(CUtensorMap* map, void* D, int M, int N, int out_fp32, i
     return 0;
 }
 
+// MN-major operand X'[K, rows] (rows contiguous): 64×64 boxes, 128-byte rows
+static int make_map_mn(CUtensorMap* map, const void* base, int rows, int K) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)K};
+    cuuint64_t strides[1] = {(cuuint64_t)rows * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)BK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
-                       int out_fp32, int splits, int sms, cudaStream_t stream) {
+                       int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream) {
     CUtensorMap md;
     int tma_out = 0;
     if (make_out_map(&md, D, M, N, out_fp32, &tma_out) != 0) return -7;
@@ -402,20 +449,23 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     dim3 grid(min(tiles, max(1, sms / splits)), 1, splits);
-    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out);
+    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out, a_mn, b_mn);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
-int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
-                   cudaStream_t stream) {
-    if (K % 8 != 0 || M <= 0 || N <= 0) return -5;  // TMA global stride must be a multiple of 16 B
+int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int a_mn, int b_mn, int relu, int out_fp32,
+                cudaStream_t stream) {
+    // TMA global strides must be multiples of 16 B: the contiguous extent of each operand must be a multiple of 8 bf16
+    if (M <= 0 || N <= 0 || K <= 0) return -5;
+    if ((a_mn ? M : K) % 8 != 0 || (b_mn ? N : K) % 8 != 0) return -5;
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -6;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int bn = (N > 128) ? 256 : 128;
     CUtensorMap ma, mb;
-    if (make_map(&ma, A, M, K, BM) != 0 || make_map(&mb, B, N, K, bn) != 0) return -7;
+    if ((a_mn ? make_map_mn(&ma, A, M, K) : make_map(&ma, A, M, K, BM)) != 0) return -7;
+    if ((b_mn ? make_map_mn(&mb, B, N, K) : make_map(&mb, B, N, K, bn)) != 0) return -7;
     const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     const int kb_total = (K + BK - 1) / BK;
     // split-K when the output has too few tiles to fill the machine and K is long
@@ -430,8 +480,8 @@ int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int
         if (out_fp32) acc = reinterpret_cast<float*>(D);
         else if (cudaMallocAsync(&acc, bytes, stream) != cudaSuccess) return -8;
         cudaMemsetAsync(acc, 0, bytes, stream);
-        int rc = (bn == 256) ? launch_gemm<256>(ma, mb, acc, nullptr, M, N, K, 0, 1, splits, sms, stream)
-                             : launch_gemm<128>(ma, mb, acc, nullptr, M, N, K, 0, 1, splits, sms, stream);
+        int rc = (bn == 256) ? launch_gemm<256>(ma, mb, acc, nullptr, M, N, K, 0, 1, splits, sms, a_mn, b_mn, stream)
+                             : launch_gemm<128>(ma, mb, acc, nullptr, M, N, K, 0, 1, splits, sms, a_mn, b_mn, stream);
         if (rc != 0) return rc;
         if (bias || relu || !out_fp32) {
             const long long MN = (long long)M * N;
@@ -440,8 +490,13 @@ int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int
         if (!out_fp32) cudaFreeAsync(acc, stream);
         return cudaGetLastError() == cudaSuccess ? 0 : -4;
     }
-    return (bn == 256) ? launch_gemm<256>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, stream)
-                       : launch_gemm<128>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, stream);
+    return (bn == 256) ? launch_gemm<256>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, a_mn, b_mn, stream)
+                       : launch_gemm<128>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, a_mn, b_mn, stream);
+}
+
+int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
+                   cudaStream_t stream) {
+    return gemm_launch(A, B, D, bias, M, N, K, 0, 0, relu, out_fp32, stream);
 }
 
 }  // namespace fdb

@@ -4,16 +4,24 @@ Parity: ``fedml_api/model/cv/cnn.py:5-68`` (CNN_OriginalFedAvg, 1 663 370 params
 and ``:71-136`` (CNN_DropOut, 1 199 882 params: conv3×3(1→32) → conv3×3(32→64)
 with NO ReLU between the convs, maxpool2, dropout .25, fc 9216→128 ReLU,
 dropout .5, fc →10, **Softmax before CrossEntropy**; flat 784 input reshaped).
-The fully-connected layers are :class:`~feddrift_b200.ops.linear.TcLinear` and the 32→64 convolutions
-:class:`~feddrift_b200.ops.conv.TcConv2d` (im2col + tcgen05 GEMM with fused bias epilogue on sm_100a; plain
-``F.linear`` / ``F.conv2d`` on CPU).  The 1-channel stems (reduction length 9 / 25) stay on the library conv.
+The fully-connected layers are :class:`~feddrift_b200.ops.linear.TcLinear` (tcgen05 GEMM with fused bias/ReLU
+epilogue on sm_100a, plain ``F.linear`` on CPU).  The 32→64 convolutions can run on
+:class:`~feddrift_b200.ops.conv.TcConv2d` (im2col + the same tcgen05 GEMM) with ``FDB_TC_CONV=1``; measured on B200
+(``profiles/README.md``, conv table) cuDNN is still 1.1–2.2× faster than the explicit-im2col formulation at these
+shapes, so the library conv is the default until the TMA-im2col (implicit GEMM) producer lands.
 """
 from __future__ import annotations
 
 from torch import nn
 
+import os
+
 from ..ops.conv import TcConv2d
 from ..ops.linear import TcLinear
+
+
+def _conv(*a, **k):
+    return TcConv2d(*a, **k) if os.environ.get("FDB_TC_CONV") == "1" else nn.Conv2d(*a, **k)
 
 
 class CNN_OriginalFedAvg(nn.Module):
@@ -22,7 +30,7 @@ class CNN_OriginalFedAvg(nn.Module):
         self.only_digits = only_digits
         self.conv2d_1 = nn.Conv2d(1, 32, kernel_size=5, padding=2)
         self.max_pooling = nn.MaxPool2d(2, stride=2)
-        self.conv2d_2 = TcConv2d(32, 64, kernel_size=5, padding=2)
+        self.conv2d_2 = _conv(32, 64, kernel_size=5, padding=2)
         self.flatten = nn.Flatten()
         self.linear_1 = TcLinear(3136, 512, activation="relu")
         self.linear_2 = TcLinear(512, 10 if only_digits else 62)
@@ -43,7 +51,7 @@ class CNN_DropOut(nn.Module):
         super().__init__()
         self.conv2d_1 = nn.Conv2d(1, 32, kernel_size=3)
         self.max_pooling = nn.MaxPool2d(2, stride=2)
-        self.conv2d_2 = TcConv2d(32, 64, kernel_size=3)
+        self.conv2d_2 = _conv(32, 64, kernel_size=3)
         self.dropout_1 = nn.Dropout(0.25)
         self.flatten = nn.Flatten()
         self.linear_1 = TcLinear(9216, 128, activation="relu")

@@ -3,7 +3,8 @@ the hand-written tcgen05 GEMM with fused bias(+ReLU) epilogue (``csrc/gemm_tc.cu
 
 * forward : cols = im2col(x) [B·Ho·Wo, Cin·kh·kw] bf16;  y = act(cols · Wᵀ + b) written as NHWC and returned as an
             NCHW *view* in channels_last memory format (no transpose kernel);
-* backward: dcols = dy · W → dx = col2im(dcols) (gather form, no atomics);  dW = dyᵀ · cols;  db = Σ dy.
+* backward: dcols = dy · W → dx = col2im(dcols) (gather form, no atomics);  dW = dyᵀ · cols;  db = Σ dy.  Both GEMMs
+            use the kernel's MN-major operand descriptors, so no tensor is transposed in memory.
 
 bf16 operands, fp32 accumulation in TMEM, fp32 master weights.  Ineligible shapes (groups/dilation ≠ 1, reduction
 length Cin·kh·kw not a multiple of 8 or < 64 — e.g. a 1-channel stem) and CPU tensors use ``F.conv2d``.  State-dict
@@ -54,13 +55,10 @@ class _TcConvFn(torch.autograd.Function):
         gb = g.to(torch.bfloat16).contiguous()
         gx = gw = gbias = None
         if ctx.needs_input_grad[0]:
-            dcols = ext.gemm_tn_bias_act(gb, wb.t().contiguous(), None, False, True)       # [BHW, K] fp32
+            dcols = ext.gemm_bias_act(gb, wb, False, True, None, False, True)               # dy · W  → [BHW, K] fp32
             gx = ext.col2im(dcols, B, C, H, W, kh, kw, stride[0], stride[1], padding[0], padding[1])
         if ctx.needs_input_grad[1]:
-            if gb.shape[0] % 8 == 0:
-                gw = ext.gemm_tn_bias_act(gb.t().contiguous(), cols.t().contiguous(), None, False, True)
-            else:
-                gw = (gb.t() @ cols).float()
+            gw = ext.gemm_bias_act(gb, cols, True, True, None, False, True)                 # dyᵀ · cols, no transposes
             gw = gw.view(Co, C, kh, kw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gbias = g.sum(0)

@@ -2,9 +2,9 @@
 tcgen05/TMEM/TMA GEMM (``csrc/gemm_tc.cu``) with fused bias(+ReLU) epilogue.
 
 * forward  : Y = act(X · Wᵀ + b)         (A = X [B,K], B = W [N,K], both K-major)
-* backward : dX = dY · W, dW = dYᵀ · X   (same TN kernel on transposed bf16 copies
-             produced by the fused cast-transpose kernel), db = column sum fused
-             into the cast kernel.
+* backward : dX = dY · W, dW = dYᵀ · X   (same kernel with MN-major operand
+             descriptors: the row-major dY / W / X tensors are consumed as they
+             are, no transpose kernels), db = column sum.
 
 Compute dtype on CUDA is bf16 with fp32 accumulation in TMEM (master weights
 stay fp32 in the parameter arena).  CPU / tiny shapes use ``F.linear`` in fp32.
@@ -59,15 +59,11 @@ class _TcLinearFn(torch.autograd.Function):
         gb = g.to(torch.bfloat16).contiguous()
         gx = gw = gbias = None
         if ctx.needs_input_grad[0]:
-            # dX[B,K] = dY[B,N] · W[N,K]  ->  TN form with B-operand = Wᵀ [K,N] (K-major in N)
-            gx = ext.gemm_tn_bias_act(gb, wb.t().contiguous(), None, False, True).reshape(ctx.x_shape)
+            # dX[B,K] = dY[B,N] · W[N,K]: W is consumed as an MN-major B operand ([reduction N, K contiguous]) — no transpose
+            gx = ext.gemm_bias_act(gb, wb, False, True, None, False, True).reshape(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            # dW[N,K] = dYᵀ[N,B] · X[B,K]  ->  A = dYᵀ [N,B], B-operand = Xᵀ [K,B]; the reduction dim is the batch,
-            # which must give a 16-byte row pitch (B % 8) — odd federated batch sizes use the library GEMM
-            if gb.shape[0] % 8 == 0:
-                gw = ext.gemm_tn_bias_act(gb.t().contiguous(), xb.t().contiguous(), None, False, True)
-            else:
-                gw = (gb.t() @ xb).float()
+            # dW[N,K] = dYᵀ · X: both operands MN-major ([reduction B, N] and [reduction B, K]); any batch size
+            gw = ext.gemm_bias_act(gb, xb, True, True, None, False, True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gbias = g.sum(0)
         return gx, gw, gbias, None

@@ -175,3 +175,24 @@ def test_tcconv2d_forward_backward_matches_conv2d(geom):
     assert (x.grad - xr.grad).abs().max().item() < 3e-2 * scale + 1e-5
     assert (layer.weight.grad - wr.grad).abs().max().item() < 3e-2 * wr.grad.abs().max().item() + 1e-5
     assert (layer.bias.grad - br.grad).abs().max().item() < 3e-2 * br.grad.abs().max().item() + 1e-5
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (200, 320, 136), (504, 1568, 104), (64, 288, 28800)])
+def test_tcgen05_gemm_operand_layouts(shape, a_mn, b_mn):
+    """K-major and MN-major (transposed, row-contiguous) A / B operands of the tcgen05 GEMM vs an fp32 matmul."""
+    from feddrift_b200.ops import _ext
+    ext = _ext.load(required=True)
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    Ab, Bb = A.bfloat16(), B.bfloat16()
+    want = Ab.float() @ Bb.float().t() + bias
+    a_dev = (Ab.t().contiguous() if a_mn else Ab).cuda()
+    b_dev = (Bb.t().contiguous() if b_mn else Bb).cuda()
+    got = ext.gemm_bias_act(a_dev, b_dev, a_mn, b_mn, bias.cuda(), False, True).cpu()
+    tol = 2e-3 * (K ** 0.5) + 1e-2
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < tol, (shape, a_mn, b_mn, (got - want).abs().max().item())

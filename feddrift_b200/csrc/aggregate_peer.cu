@@ -8,6 +8,8 @@
 //            model; it pulls that slice of every peer's partial with 128-bit peer loads (W independent loads in
 //            flight per thread), divides by the global weight total and pushes the finished slice into EVERY rank's
 //            θ buffer with peer stores — the broadcast of the new cluster models is the epilogue of the reduction
+//            — or, when the symmetric buffer has an NVLS multicast mapping, ONE multimem.ld_reduce (in-switch add of the
+//            W partials) and ONE multimem.st (in-switch replication of the finished slice) per 16 bytes
 //   barrier  cross-GPU epoch flag so θ is complete everywhere when the kernel retires
 //
 // Wire bytes per rank: (W-1)/W·M·P·4 in + the same out — the reduce-scatter/all-gather minimum; the reference moves
@@ -27,6 +29,8 @@ struct PeerAggParams {
     float* part[8];       // part[r]: rank r's symmetric partial buffer [M, P] (part[rank] is local)
     float* theta[8];      // theta[r]: rank r's symmetric model buffer  [M, theta_stride]
     float* tot_inbox[8];  // tot_inbox[r]: rank r's [world, M] weight-total inbox
+    float* mc_part;       // NVLS: multicast alias of the partial buffers (nullptr → peer loads)
+    float* mc_theta;      // NVLS: multicast alias of the θ buffers      (nullptr → peer stores)
     unsigned* flags[8];   // flags[r]: rank r's [3, world] epoch words
     unsigned* grid_sync;  // local monotonically increasing grid-barrier counter
     unsigned epoch;       // this launch's epoch (monotonic across launches)
@@ -74,6 +78,18 @@ FDB_DEVICE float4 ld_peer_f4(const float* ptr) {
 }
 FDB_DEVICE void st_peer_f4(float* ptr, float4 v) {
     asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// NVLS (NVLink SHARP): one instruction reduces the same address on every GPU inside the switch / broadcasts a store
+FDB_DEVICE float4 multimem_ld_reduce_f4(const float* mc_ptr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_ptr) : "memory");
+    return v;
+}
+FDB_DEVICE void multimem_st_f4(float* mc_ptr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
 }
 
 __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __grid_constant__ PeerAggParams p) {
@@ -139,6 +155,16 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
         const float tot = tot_s[m];
         if (!(tot > 0.f)) continue;  // unused cluster: leave θ untouched everywhere
         const float inv = 1.0f / tot;
+        if (p.mc_part != nullptr) {
+            // NVLS path: the switch adds the W partials (multimem.ld_reduce) and replicates the finished slice into
+            // every rank's θ (multimem.st): 1 load + 1 store per element instead of W + W
+            for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+                float4 acc = multimem_ld_reduce_f4(p.mc_part + (size_t)m * P + (size_t)i * 4);
+                acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+                multimem_st_f4(p.mc_theta + (size_t)m * p.theta_stride + (size_t)i * 4, acc);
+            }
+            continue;
+        }
         for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 v[8];
@@ -161,8 +187,8 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
 
 int fedavg_reduce_apply_peer_launch(const float* cp, const float* n, int C, int M, int P, int theta_stride, int world, int rank,
                                     const long long* part_ptrs, const long long* theta_ptrs, const long long* tot_ptrs,
-                                    const long long* flag_ptrs, unsigned* grid_sync, unsigned epoch, unsigned grid_base, int grid,
-                                    long long timeout_ms, int* error_flag, cudaStream_t stream) {
+                                    const long long* flag_ptrs, long long mc_part, long long mc_theta, unsigned* grid_sync, unsigned epoch,
+                                    unsigned grid_base, int grid, long long timeout_ms, int* error_flag, cudaStream_t stream) {
     if (world < 1 || world > 8 || (P & 3)) return -5;
     PeerAggParams p{};
     p.cp = cp; p.n = n; p.C = C; p.M = M; p.P = P; p.theta_stride = theta_stride; p.world = world; p.rank = rank;
@@ -172,6 +198,7 @@ int fedavg_reduce_apply_peer_launch(const float* cp, const float* n, int C, int 
         p.tot_inbox[r] = reinterpret_cast<float*>(tot_ptrs[r]);
         p.flags[r] = reinterpret_cast<unsigned*>(flag_ptrs[r]);
     }
+    p.mc_part = reinterpret_cast<float*>(mc_part); p.mc_theta = reinterpret_cast<float*>(mc_theta);
     p.grid_sync = grid_sync; p.epoch = epoch; p.grid_base = grid_base;
     p.spin_timeout_ns = timeout_ms * 1000000LL; p.error_flag = error_flag;
     const int smem = (C + M + 8) * (int)sizeof(float);

@@ -27,7 +27,7 @@ std::vector<int64_t> fed_round_small(
     c10::optional<Tensor> eval_train_model, c10::optional<Tensor> eval_test_model, c10::optional<Tensor> ens_w,
     c10::optional<Tensor> client_out, c10::optional<Tensor> lr_dev, Tensor metrics, c10::optional<Tensor> timers,
     std::vector<double> fcfg, std::vector<int64_t> icfg, std::vector<int64_t> peer_inbox, std::vector<int64_t> peer_flags,
-    c10::optional<Tensor> error_flag, c10::optional<Tensor> counters, std::vector<int64_t> peer_metrics) {
+    c10::optional<Tensor> error_flag, c10::optional<Tensor> counters, std::vector<int64_t> peer_metrics, std::vector<int64_t> host_io) {
     CHECK_CUDA_F32(X); CHECK_CUDA_I32(Y); CHECK_CUDA_I32(nsamp); CHECK_CUDA_F32(W); CHECK_CUDA_F32(theta); CHECK_CUDA_I32(opt_step);
     CHECK_CUDA_F32(metrics);
     TORCH_CHECK(X.is_contiguous() && Y.is_contiguous() && nsamp.is_contiguous() && W.is_contiguous() && metrics.is_contiguous(),
@@ -73,6 +73,14 @@ std::vector<int64_t> fed_round_small(
     p.error_flag = opt_ptr<int>(error_flag);
     p.counters = opt_ptr<int>(counters);
     for (int g = 0; g < fdb::kMaxPeers; ++g) p.metrics_peer[g] = nullptr;
+    if (host_io.size() == 5) {   // {pinned X ptr, pinned Y ptr, pinned metrics ptr, t0, steps}: fused host I/O (see fed_round_small.h)
+        p.host_x = reinterpret_cast<const float*>(host_io[0]);
+        p.host_y = reinterpret_cast<const int*>(host_io[1]);
+        p.host_metrics = reinterpret_cast<float*>(host_io[2]);
+        p.host_t0 = (int)host_io[3];
+        p.host_steps = (int)host_io[4];
+        TORCH_CHECK(p.host_t0 >= 0 && p.host_t0 + p.host_steps <= p.T1, "fed_round_small: host_io time range out of bounds");
+    }
     if (p.world > 1 && (int)peer_metrics.size() == p.world)
         for (int g = 0; g < p.world; ++g) p.metrics_peer[g] = reinterpret_cast<float*>(peer_metrics[g]);
     if (p.use_adam) TORCH_CHECK(p.opt_m && p.opt_v && p.opt_vmax, "adam needs optimizer state tensors");
@@ -175,7 +183,7 @@ Tensor robust_clip(Tensor rows, Tensor g, double bound, c10::optional<Tensor> ma
 int64_t fedavg_reduce_apply_peer(Tensor cp, Tensor n, int64_t P, int64_t theta_stride, int64_t world, int64_t rank,
                                  std::vector<int64_t> part_ptrs, std::vector<int64_t> theta_ptrs, std::vector<int64_t> tot_ptrs,
                                  std::vector<int64_t> flag_ptrs, Tensor grid_sync, int64_t epoch, int64_t grid_base, int64_t timeout_ms,
-                                 Tensor error_flag) {
+                                 Tensor error_flag, int64_t mc_part, int64_t mc_theta) {
     CHECK_CUDA_F32(cp); CHECK_CUDA_F32(n); CHECK_CUDA_I32(grid_sync); CHECK_CUDA_I32(error_flag);
     c10::cuda::CUDAGuard guard(cp.device());
     const int C = (int)cp.size(0), M = (int)cp.size(1);
@@ -185,7 +193,7 @@ int64_t fedavg_reduce_apply_peer(Tensor cp, Tensor n, int64_t P, int64_t theta_s
     std::vector<long long> a(part_ptrs.begin(), part_ptrs.end()), b(theta_ptrs.begin(), theta_ptrs.end()),
         c(tot_ptrs.begin(), tot_ptrs.end()), d(flag_ptrs.begin(), flag_ptrs.end());
     const int rc = fdb::fedavg_reduce_apply_peer_launch(cp.data_ptr<float>(), n.data_ptr<float>(), C, M, (int)P, (int)theta_stride, (int)world,
-                                                        (int)rank, a.data(), b.data(), c.data(), d.data(),
+                                                        (int)rank, a.data(), b.data(), c.data(), d.data(), (long long)mc_part, (long long)mc_theta,
                                                         reinterpret_cast<unsigned*>(grid_sync.data_ptr<int>()), (unsigned)epoch,
                                                         (unsigned)grid_base, sms, timeout_ms, error_flag.data_ptr<int>(), cur_stream());
     CHECK_OK(rc, "fedavg_reduce_apply_peer");

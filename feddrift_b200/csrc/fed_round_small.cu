@@ -117,9 +117,40 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
     int* pairs_s = reinterpret_cast<int*>(smem + L.pairs);
     int* misc_s = reinterpret_cast<int*>(smem + L.misc);  // [0] = npairs
 
-    // ---- cold-start: pull the working set (samples of steps ≤ t+1, labels) into L2 with one wave of prefetches ----
+    if (p.host_x != nullptr) {
+        // ---- fused H2D: this round's inputs come straight from pinned host memory (each CTA copies 1/G of the range)
+        const size_t gthreads = (size_t)G * blockDim.x, gt = (size_t)crank * blockDim.x + tid;
+        const size_t xoff = (size_t)p.host_t0 * C * S * IN, xn = (size_t)p.host_steps * C * S * IN;
+        const size_t yoff = (size_t)p.host_t0 * C * S, yn = (size_t)p.host_steps * C * S;
+        float* Xd = const_cast<float*>(p.X) + xoff;
+        int* Yd = const_cast<int*>(p.Y) + yoff;
+        if (((xoff | xn) & 3) == 0) {
+            for (size_t i = gt; i < xn / 4; i += gthreads) {
+                float4 v;
+                asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p.host_x + 4 * i) : "memory");
+                reinterpret_cast<float4*>(Xd)[i] = v;
+            }
+        } else {
+            for (size_t i = gt; i < xn; i += gthreads) Xd[i] = ld_relaxed_sys_f32(p.host_x + i);
+        }
+        if (((yoff | yn) & 3) == 0) {
+            for (size_t i = gt; i < yn / 4; i += gthreads) {
+                int4 v;
+                asm volatile("ld.global.relaxed.sys.v4.s32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p.host_y + 4 * i) : "memory");
+                reinterpret_cast<int4*>(Yd)[i] = v;
+            }
+        } else {
+            for (size_t i = gt; i < yn; i += gthreads) Yd[i] = __float_as_int(ld_relaxed_sys_f32(reinterpret_cast<const float*>(p.host_y) + i));
+        }
+        __threadfence();
+        if (G > 1) cluster.sync(); else __syncthreads();   // every CTA sees the whole copied range
+    }
+    // ---- cold-start: pull the (remaining) working set — samples of the steps that were not just copied in — into L2
+    //      with one wave of prefetches
     {
-        const int steps = min(t + 2, p.T1);
+        const int steps = p.host_x ? min(p.host_t0, p.T1) : min(t + 2, p.T1);
         const size_t xb = (size_t)steps * C * S * IN * sizeof(float), yb = (size_t)steps * C * S * sizeof(int);
         const size_t gthreads = (size_t)G * blockDim.x, gt = (size_t)crank * blockDim.x + tid;
         for (size_t off = gt * 128; off < xb; off += gthreads * 128)
@@ -526,6 +557,10 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                     }
                 } else {
                     *reinterpret_cast<float2*>(p.metrics + moff) = make_float2(corr, loss);
+                }
+                if (p.host_metrics) {   // fused D2H: posted writes over PCIe, visible to the host when the kernel retires
+                    st_relaxed_sys_f32(p.host_metrics + moff, corr);
+                    st_relaxed_sys_f32(p.host_metrics + moff + 1, loss);
                 }
             }
         }

@@ -51,6 +51,13 @@ struct RoundParams {
     unsigned flag_base;          // monotonically increasing epoch base (per launch)
     long long spin_timeout_ns;   // bail out instead of hanging the GPU if a peer never arrives
     int* error_flag;             // set to nonzero on timeout
+    // fused host I/O (single-GPU end-to-end round): the kernel itself performs the host→device copy of the round's inputs
+    // from PINNED host memory (UVA pointers; 16-byte system-scope loads over PCIe) into the X / Y arenas before round 0,
+    // and mirrors every metric row into a pinned host buffer — the whole round is ONE graph node, no memcpy nodes.
+    const float* host_x;         // pinned [host_steps, C, S, IN] or nullptr
+    const int* host_y;           // pinned [host_steps, C, S]
+    float* host_metrics;         // pinned [rounds, C, 4] or nullptr
+    int host_t0, host_steps;     // destination time steps [host_t0, host_t0 + host_steps)
 };
 
 struct SmallLaunchInfo {

@@ -24,8 +24,8 @@ int robust_clip_launch(float* rows, const float* g, const unsigned char* mask, i
 // aggregate_peer.cu : multi-GPU reduce-scatter + apply + all-gather over NVLink peer memory (cooperative launch)
 int fedavg_reduce_apply_peer_launch(const float* cp, const float* n, int C, int M, int P, int theta_stride, int world, int rank,
                                     const long long* part_ptrs, const long long* theta_ptrs, const long long* tot_ptrs,
-                                    const long long* flag_ptrs, unsigned* grid_sync, unsigned epoch, unsigned grid_base, int grid,
-                                    long long timeout_ms, int* error_flag, cudaStream_t stream);
+                                    const long long* flag_ptrs, long long mc_part, long long mc_theta, unsigned* grid_sync, unsigned epoch,
+                                    unsigned grid_base, int grid, long long timeout_ms, int* error_flag, cudaStream_t stream);
 // eval.cu
 int eval_logits_launch(const float* logits, const int* target, int B, int K, float* acc3, cudaStream_t stream);
 int aue_sqerr_launch(const float* logits, const int* target, int B, int K, float* out1, cudaStream_t stream);

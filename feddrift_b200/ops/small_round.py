@@ -117,7 +117,7 @@ def run_native(st: Dict, rounds: int, metrics_out: Optional[torch.Tensor] = None
         cache["train_index"], cache["train_count"], cache["feat_mask"], cache["eval_train_model"], cache["eval_test_model"],
         ens_w, st.get("client_out"), lr_dev, metrics_out, st.get("timers"), fcfg, icfg,
         list(mg["inbox_ptrs"]) if mg else [], list(mg["flag_ptrs"]) if mg else [], mg.get("error_flag") if mg else None,
-        st.get("counters"), peer_metrics)
+        st.get("counters"), peer_metrics, [int(v) for v in st["host_io"]] if st.get("host_io") else [])
     if mg:
         mg["flag_base"] = int(mg["flag_base"]) + rounds
     if st.get("counters") is not None:

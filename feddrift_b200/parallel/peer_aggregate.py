@@ -29,6 +29,7 @@ class PeerAggregator:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         if self.world == 1:
             self.theta_full = torch.zeros(num_models, self.Pp, device=self.device)
+            self.nvls = False
         else:
             import torch.distributed._symmetric_memory as symm_mem
             mp = num_models * self.Pp
@@ -42,6 +43,12 @@ class PeerAggregator:
             self.theta_ptrs = [p + 4 * mp for p in base]
             self.tot_ptrs = [p + 4 * 2 * mp for p in base]
             self.flag_ptrs = [p + 4 * (2 * mp + tot_f) for p in base]
+            # NVLS: if the allocation has a multicast mapping, phase 2 uses multimem.ld_reduce / multimem.st (in-switch
+            # reduction + replication) instead of W peer loads + W peer stores per element
+            import os
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+            self.nvls = bool(mc) and os.environ.get("FDB_NO_NVLS") != "1"
+            self.mc_part, self.mc_theta = (mc, mc + 4 * mp) if self.nvls else (0, 0)
             self.theta_full = self.buf[mp:2 * mp].view(num_models, self.Pp)
             self.grid_sync = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -63,7 +70,8 @@ class PeerAggregator:
         self.epoch += 1
         grid = _ext.load(required=True).fedavg_reduce_apply_peer(
             cp.contiguous(), n.float().contiguous(), self.Pp, self.Pp, self.world, self.rank, self.part_ptrs, self.theta_ptrs,
-            self.tot_ptrs, self.flag_ptrs, self.grid_sync, self.epoch, self.grid_base, 5000, self.error_flag)
+            self.tot_ptrs, self.flag_ptrs, self.grid_sync, self.epoch, self.grid_base, 5000, self.error_flag,
+            self.mc_part, self.mc_theta)
         self.grid_base += 2 * int(grid)
         return self.theta
 

@@ -55,6 +55,9 @@ def make_args(**kw) -> SimpleNamespace:
     return SimpleNamespace(**d)
 
 
+from ..ops.small_round import LAUNCH_COUNT as _SMALL_LAUNCHES  # noqa: E402
+
+
 class DriftSim:
     def __init__(self, args, data: Optional[DriftData] = None, device=None, sink: Optional[MetricsSink] = None,
                  algo=None):
@@ -250,13 +253,21 @@ class DriftSim:
         return int(n * (self.data_host.feature_num * 4 + 4)), int(self.C * 4 * 4)
 
     def _build_round_graph(self, host_inputs: Dict[str, torch.Tensor]):
-        """Capture [H2D inputs → fused round kernel → D2H metrics] into ONE CUDA graph (replayed once per round)."""
+        """Capture one end-to-end round into ONE CUDA graph (replayed once per round).
+
+        Single GPU: the graph is a single kernel node — ``fed_round_small_kernel`` itself copies the round's inputs from
+        the pinned host tensors into the device arena (16-byte system-scope loads over PCIe) and mirrors the metric rows
+        into the pinned host buffer (fused H2D / D2H, ``host_io``).  Multi-GPU (metrics arrive by peer stores in the
+        symmetric buffer): [H2D memcpy nodes → kernel → D2H memcpy node]."""
         from ..ops import small_round
         st = self._small_state()
         cache = small_round.prepare(st)
         t = self.t
         hi = t + host_inputs["X"].shape[0]
         hm = self._host_metrics
+        fused_io = (self.multi is None and host_inputs["X"].is_pinned() and host_inputs["Y"].is_pinned() and hm.is_pinned()
+                    and host_inputs["X"].dtype == torch.float32 and host_inputs["Y"].dtype == torch.int32
+                    and host_inputs["X"].is_contiguous() and host_inputs["Y"].is_contiguous())
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up outside capture (allocations, attribute sets)
@@ -264,16 +275,24 @@ class DriftSim:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            cache["X"][t:hi].copy_(host_inputs["X"], non_blocking=True)
-            cache["Y"][t:hi].copy_(host_inputs["Y"], non_blocking=True)
-            met = self.run_rounds_device(1)
-            hm.copy_(met[0], non_blocking=True)
+        if fused_io:
+            st["host_io"] = (host_inputs["X"].data_ptr(), host_inputs["Y"].data_ptr(), hm.data_ptr(), t, hi - t)
+        try:
+            with torch.cuda.graph(g):
+                if not fused_io:
+                    cache["X"][t:hi].copy_(host_inputs["X"], non_blocking=True)
+                    cache["Y"][t:hi].copy_(host_inputs["Y"], non_blocking=True)
+                met = self.run_rounds_device(1)
+                if not fused_io:
+                    hm.copy_(met[0], non_blocking=True)
+        finally:
+            st.pop("host_io", None)
         self.round_in_step -= 1   # the capture itself executed nothing
         self.global_round -= 1
         small_round.LAUNCH_COUNT["fed_round_small"] -= 1
         if self.multi is not None:
             self.multi["flag_base"] = int(self.multi["flag_base"]) - 1
+        self._graph_keep = (host_inputs, hm)   # the graph holds raw host pointers: keep the pinned tensors alive
         return g
 
     def run_round(self, host_inputs: Optional[Dict[str, torch.Tensor]] = None, log: bool = False,
@@ -281,22 +300,23 @@ class DriftSim:
         """ONE end-to-end FL round through the public API: (optional) host→device copy of the round's inputs
         from pinned memory, the fused round kernel, device→host copy of the per-client metrics, host reduction.
         Synchronises (the caller gets real numbers back)."""
-        st = self._small_state()
-        t = self.t
         if use_graph and host_inputs is not None and self.device.type == "cuda":
-            from ..ops import small_round
-            if getattr(self, "_host_metrics", None) is None or not self._host_metrics.is_pinned():
-                self._host_metrics = torch.zeros(self.C, 4, dtype=torch.float32).pin_memory()
-            if getattr(self, "_graph", None) is None or self._graph[1] is not host_inputs:
-                self._graph = (self._build_round_graph(host_inputs), host_inputs)
-            self._graph[0].replay()
+            gr = getattr(self, "_graph", None)
+            if gr is None or gr[1] is not host_inputs:
+                if getattr(self, "_host_metrics", None) is None or not self._host_metrics.is_pinned():
+                    self._host_metrics = torch.zeros(self.C, 4, dtype=torch.float32).pin_memory()
+                gr = self._graph = (self._build_round_graph(host_inputs), host_inputs, self._host_metrics.numpy(),
+                                    torch.cuda.current_stream())
+            gr[0].replay()
             self.round_in_step += 1
             self.global_round += 1
-            small_round.LAUNCH_COUNT["fed_round_small"] += 1
+            _SMALL_LAUNCHES["fed_round_small"] += 1
             if self.multi is not None:
                 self.multi["flag_base"] = int(self.multi["flag_base"]) + 1
-            torch.cuda.current_stream().synchronize()
-            return self._round_result(self._host_metrics.numpy(), log)
+            gr[3].synchronize()
+            return self._round_result(gr[2], log)
+        st = self._small_state()
+        t = self.t
         if host_inputs is not None:
             if self.device.type == "cuda":
                 from ..ops import small_round
@@ -319,13 +339,14 @@ class DriftSim:
 
     def _round_result(self, m, log: bool) -> Dict:
         t = self.t
-        if getattr(self, "_counts_host", None) is None:
-            self._counts_host = self._last_counts.cpu()
-        c = self._counts_host.numpy()
-        ntr, nte = max(float(c[:, 0].sum()), 1.0), max(float(c[:, 1].sum()), 1.0)
-        res = {"round": self.round_in_step - 1, "iteration": t, "train_acc": float(m[:, 0].sum()) / ntr,
-               "train_loss": float(m[:, 1].sum()) / ntr, "test_acc": float(m[:, 2].sum()) / nte,
-               "test_loss": float(m[:, 3].sum()) / nte}
+        nn_ = getattr(self, "_counts_tot", None)
+        if nn_ is None or nn_[0] != t:
+            c = self._last_counts.cpu().numpy()
+            nn_ = self._counts_tot = (t, max(float(c[:, 0].sum()), 1.0), max(float(c[:, 1].sum()), 1.0))
+        ntr, nte = nn_[1], nn_[2]
+        tot = m.sum(0).tolist()     # one reduction over the [C, 4] host buffer
+        res = {"round": self.round_in_step - 1, "iteration": t, "train_acc": tot[0] / ntr, "train_loss": tot[1] / ntr,
+               "test_acc": tot[2] / nte, "test_loss": tot[3] / nte}
         if log:
             for k_, key in (("train_acc", "Train/Acc"), ("train_loss", "Train/Loss"), ("test_acc", "Test/Acc"),
                             ("test_loss", "Test/Loss")):

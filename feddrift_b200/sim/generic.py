@@ -62,6 +62,8 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
         active = (st["train_count"] > 0).any(dim=1) if st["sample_mode"] == "index" else (Wt != 0).any(dim=1)
         cl.n.zero_()
         world, rank = _world_rank(sim)
+        slots = _stream_slots(sim)          # K side streams: independent (client, model) pairs replay concurrently
+        pair_i = 0
         for c in range(C):
             if world > 1 and c % world != rank:   # clients are sharded over the ranks (one process per GPU)
                 continue
@@ -73,9 +75,16 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
                 n_cm, sampler = _pair_sampler(st, c, m, t, nb, B)
                 if n_cm <= 0:
                     continue
-                cl.params[c, m].copy_(bank.theta[m])
-                _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, a.wd, feat_mask)
+                if slots:
+                    with torch.cuda.stream(slots[pair_i % len(slots)]):
+                        cl.params[c, m].copy_(bank.theta[m])
+                        _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, a.wd, feat_mask, pair_i % len(slots))
+                else:
+                    cl.params[c, m].copy_(bank.theta[m])
+                    _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, a.wd, feat_mask)
+                pair_i += 1
                 cl.n[c, m] = n_cm
+        _join_slots(sim, slots)
         # raw-update hooks (CFL family) may veto the aggregation of this round
         skip = False
         if hasattr(sim.algo, "state") and "cfl" in getattr(sim.algo, "arg", ""):
@@ -188,17 +197,44 @@ class _GraphedStep:
         self.launches += 1
 
 
-def _graphed_step(sim, batch_shape, use_adam, lr, wd):
+def _stream_slots(sim):
+    """Side streams for concurrent pair execution (CUDA + graphed module path only).  A federated local step is ~60
+    small dependent kernels, i.e. latency-bound even inside a CUDA graph; replaying K pairs' graphs on K streams lets the
+    SMs overlap them.  ``FDB_GRAPH_STREAMS`` (default 8; 1 disables) sets K."""
+    import os
+    if sim.device.type != "cuda" or sim.bank.mlp is not None or os.environ.get("FDB_NO_GRAPHS") == "1":
+        return []
+    k = int(os.environ.get("FDB_GRAPH_STREAMS", "8"))
+    if k <= 1:
+        return []
+    slots = sim.__dict__.get("_slot_streams")
+    if slots is None or len(slots) != k:
+        slots = sim._slot_streams = [torch.cuda.Stream(device=sim.device) for _ in range(k)]
+    main = torch.cuda.current_stream(sim.device)
+    for s_ in slots:                        # the side streams must see θ / data produced on the main stream
+        s_.wait_stream(main)
+    return slots
+
+
+def _join_slots(sim, slots):
+    if slots:
+        main = torch.cuda.current_stream(sim.device)
+        for s_ in slots:
+            main.wait_stream(s_)
+
+
+def _graphed_step(sim, batch_shape, use_adam, lr, wd, slot: int = 0):
     """Cached ``_GraphedStep`` for this (batch shape, optimizer, lr) or None when graphs are unavailable."""
     import os
     if sim.device.type != "cuda" or sim.bank.mlp is not None or os.environ.get("FDB_NO_GRAPHS") == "1" \
             or getattr(sim, "_graphs_broken", False):
         return None
     cache = sim.__dict__.setdefault("_step_graphs", {})
-    key = (tuple(batch_shape), bool(use_adam), float(lr), float(wd))
+    key = (tuple(batch_shape), bool(use_adam), float(lr), float(wd), int(slot))
     gs = cache.get(key)
     if gs is None:
-        if len(cache) >= 2:                 # e.g. Adaptive-FedAvg changes lr every round: keep the pool small
+        nslots = max(1, len(sim.__dict__.get("_slot_streams") or [1]))
+        if len(cache) >= 2 * nslots:        # e.g. Adaptive-FedAvg changes lr every round: keep the pool small
             cache.pop(next(iter(cache)))
         try:
             gs = cache[key] = _GraphedStep(sim, batch_shape, use_adam, lr, wd)
@@ -211,7 +247,7 @@ def _graphed_step(sim, batch_shape, use_adam, lr, wd):
     return gs
 
 
-def _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, wd, feat_mask):
+def _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, wd, feat_mask, slot: int = 0):
     bank, cl = sim.bank, sim.clients
     row = cl.params[c, m]
     mlp = bank.mlp
@@ -235,7 +271,7 @@ def _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, wd, fea
             if feat_mask is not None:
                 xb = xb * feat_mask[m].reshape((1,) + tuple(xb.shape[1:]))
             batches.append((xb, Yc[i].long()))
-    gs = _graphed_step(sim, batches[0][0].shape, use_adam, lr, wd) if same else None
+    gs = _graphed_step(sim, batches[0][0].shape, use_adam, lr, wd, slot) if same else None
     if gs is not None:
         gs.load(cl, c, m)
         for xb, yb in batches:

@@ -121,3 +121,35 @@ def test_drift_sim_runs_on_gpu_with_native_kernel():
     out = sim.run()
     assert small_round.LAUNCH_COUNT["fed_round_small"] > before
     assert out["history"][-1]["train_acc"] > 0.7
+
+
+def test_end_to_end_round_graph_with_fused_host_io_matches_copy_path():
+    """`run_round(host_inputs, use_graph=True)` (ONE kernel node: the kernel pulls the inputs from pinned host memory and
+    mirrors the metrics into pinned host memory) must equal the explicit H2D-copy / D2H-copy path, and must really read
+    the host buffers on every replay."""
+    from feddrift_b200.sim import DriftSim, make_args
+
+    def make():
+        sim = DriftSim(make_args(comm_round=6, total_train_iteration=4), device="cuda")
+        for t in range(2):
+            sim.run_time_step(t, rounds=4)
+        sim.begin_time_step(2)
+        sim.args.rounds_per_launch = 1
+        return sim
+
+    a, b = make(), make()
+    ha, hb = a.make_host_round_inputs(), b.make_host_round_inputs()
+    assert ha["X"].is_pinned() and torch.equal(ha["X"], hb["X"])
+    for _ in range(3):
+        ra = a.run_round(ha, use_graph=True)
+        rb = b.run_round(hb, use_graph=False)
+        for k in ("train_acc", "train_loss", "test_acc", "test_loss"):
+            assert abs(ra[k] - rb[k]) < 1e-5, (k, ra, rb)
+    assert torch.allclose(a.bank.theta, b.bank.theta, atol=1e-6)
+    # new data in the SAME pinned buffers must be picked up by the next replay (the graph holds only the pointers)
+    ha["Y"].copy_(1 - ha["Y"])
+    hb["Y"].copy_(1 - hb["Y"])
+    ra = a.run_round(ha, use_graph=True)
+    rb = b.run_round(hb, use_graph=False)
+    assert abs(ra["train_acc"] - rb["train_acc"]) < 1e-5 and ra["train_acc"] < 0.5
+    assert torch.allclose(a.bank.theta, b.bank.theta, atol=1e-6)

@@ -50,6 +50,11 @@ for name, M, P, C in CONFIGS:
     agg = PeerAggregator(M, P, dev)
     ms = timed(lambda: agg.aggregate(cp, n))
     agg.check()
+    nvls, ms_p2p = bool(getattr(agg, "nvls", False)), None
+    if nvls:   # same kernel with the multicast path disabled: W peer loads + W peer stores per element
+        agg.mc_part, agg.mc_theta = 0, 0
+        ms_p2p = timed(lambda: agg.aggregate(cp, n))
+        agg.check()
     theta = torch.zeros(M, P4, device=dev)
 
     def nccl_path():
@@ -63,7 +68,7 @@ for name, M, P, C in CONFIGS:
     ms_nccl = timed(nccl_path)
     wire = (world - 1) / world * M * P4 * 4
     if rank == 0:
-        print(json.dumps({"config": name, "world": world, "fused_ms": ms, "nccl_path_ms": ms_nccl,
+        print(json.dumps({"config": name, "world": world, "fused_ms": ms, "nvls": nvls, "fused_p2p_ms": ms_p2p, "nccl_path_ms": ms_nccl,
                           "local_hbm_bytes": Cl * M * P4 * 4, "nvlink_bytes_each_way": wire,
                           "nvlink_GBps_each_way": wire / ms / 1e6 if world > 1 else None,
                           "frac_of_770GBps": (wire / ms / 1e6) / 770.0 if world > 1 else None}))

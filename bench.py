@@ -173,7 +173,11 @@ def run_ours(args):
                        "local_steps": 5, "model_slots": 4, "algo": "softcluster H_A_C_1_10_0 (FedDrift), change points A",
                        "time_step": BENCH_TIME_STEP, "parallelism": f"clients-sharded x{world}" if world > 1 else "1gpu",
                        "l2": "256 MiB flush write between timed rounds, outside the event brackets",
-                       "timing": "CUDA events per round on the launching stream, summed; max over ranks"},
+                       "timing": "CUDA events per round on the launching stream, summed; max over ranks",
+                       "e2e_path": ("DriftSim.run_round(host_inputs, use_graph=True): one CUDA-graph replay per round + stream sync; "
+                                    + ("the round kernel itself copies the pinned host inputs in (PCIe loads) and mirrors the metrics "
+                                       "into pinned host memory" if world == 1 else
+                                       "H2D memcpy nodes -> round kernel -> D2H memcpy node"))},
             "e2e": {"value": K / (e2e_ms / 1e3), "unit": "rounds/s", "h2d_bytes_per_step": sim.host_round_bytes()[0],
                     "d2h_bytes_per_step": sim.host_round_bytes()[1]},
             "gpu_launches": launches,

@@ -157,6 +157,19 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.X) + off));
         for (size_t off = gt * 128; off < yb; off += gthreads * 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.Y) + off));
+        // optimizer moments / step counters / plan tables: small, but every pair's first touch would be a DRAM miss
+        const size_t ob = (size_t)CM * P * sizeof(float);
+        if (p.use_adam && p.opt_m)
+            for (size_t off = gt * 128; off < ob; off += gthreads * 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.opt_m) + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.opt_v) + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.opt_vmax) + off));
+            }
+        const size_t wb = (size_t)(t + 1) * CM * sizeof(float);
+        for (size_t off = gt * 128; off < wb; off += gthreads * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.W) + off));
+        if (gt * 128 < (size_t)CM * sizeof(int)) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.opt_step) + gt * 128));
+        if (gt * 128 < (size_t)p.T1 * C * sizeof(int)) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.nsamp) + gt * 128));
     }
     // ---- load the cluster models once (broadcast == this smem fill; afterwards θ never leaves the SM) ----
     for (int e = tid; e < MP; e += blockDim.x) theta_s[e] = p.theta[(e / P) * p.theta_stride + (e % P)];

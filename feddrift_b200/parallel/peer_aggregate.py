@@ -47,7 +47,10 @@ class PeerAggregator:
             # reduction + replication) instead of W peer loads + W peer stores per element
             import os
             mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
-            self.nvls = bool(mc) and os.environ.get("FDB_NO_NVLS") != "1"
+            # measured (profiles/peer_agg_r1.jsonl): in-switch reduction wins from 4 GPUs up (0.35 vs 0.41 ms at N = 8 for
+            # ResNet-18 × 2 clusters) and loses at N = 2 (0.55 vs 0.45 ms), where a peer load is a single hop anyway
+            force = os.environ.get("FDB_NVLS")
+            self.nvls = bool(mc) and (force == "1" or (force != "0" and self.world >= 4))
             self.mc_part, self.mc_theta = (mc, mc + 4 * mp) if self.nvls else (0, 0)
             self.theta_full = self.buf[mp:2 * mp].view(num_models, self.Pp)
             self.grid_sync = torch.zeros(1, dtype=torch.int32, device=self.device)

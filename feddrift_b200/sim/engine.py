@@ -268,11 +268,25 @@ class DriftSim:
         fused_io = (self.multi is None and host_inputs["X"].is_pinned() and host_inputs["Y"].is_pinned() and hm.is_pinned()
                     and host_inputs["X"].dtype == torch.float32 and host_inputs["Y"].dtype == torch.int32
                     and host_inputs["X"].is_contiguous() and host_inputs["Y"].is_contiguous())
+        # warm-up launch outside the capture (lazy allocations, function attributes) — on a snapshot: building the graph
+        # must not advance the experiment (models, optimizer state, RNG round counter are restored afterwards; only the
+        # cross-GPU epoch stays advanced because the peers have seen it)
+        cl = self.clients
+        snap = [(x, x.clone()) for x in (self.bank.theta, cl.m, cl.v, cl.vmax, cl.step, st.get("W")) if isinstance(x, torch.Tensor)]
+        cnt = st.get("counters")
+        cnt0 = cnt[0:1].clone() if isinstance(cnt, torch.Tensor) else None
+        r0, g0, l0 = self.round_in_step, self.global_round, small_round.LAUNCH_COUNT["fed_round_small"]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up outside capture (allocations, attribute sets)
+        with torch.cuda.stream(side):
             self.run_rounds_device(1)
         torch.cuda.current_stream().wait_stream(side)
+        for dst, src in snap:
+            dst.copy_(src)
+        if cnt0 is not None:
+            cnt[0:1].copy_(cnt0)
+        self.round_in_step, self.global_round = r0, g0
+        small_round.LAUNCH_COUNT["fed_round_small"] = l0
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         if fused_io:

@@ -175,9 +175,8 @@ def run_ours(args):
                        "l2": "256 MiB flush write between timed rounds, outside the event brackets",
                        "timing": "CUDA events per round on the launching stream, summed; max over ranks",
                        "e2e_path": ("DriftSim.run_round(host_inputs, use_graph=True): one CUDA-graph replay per round + stream sync; "
-                                    + ("the round kernel itself copies the pinned host inputs in (PCIe loads) and mirrors the metrics "
-                                       "into pinned host memory" if world == 1 else
-                                       "H2D memcpy nodes -> round kernel -> D2H memcpy node"))},
+                                    "the round kernel itself copies the pinned host inputs in (PCIe loads) and mirrors the metrics "
+                                    "into pinned host memory (single graph node)")},
             "e2e": {"value": K / (e2e_ms / 1e3), "unit": "rounds/s", "h2d_bytes_per_step": sim.host_round_bytes()[0],
                     "d2h_bytes_per_step": sim.host_round_bytes()[1]},
             "gpu_launches": launches,

@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                 } else {
                     *reinterpret_cast<float2*>(p.metrics + moff) = make_float2(corr, loss);
                 }
-                if (p.host_metrics) {   // fused D2H: posted writes over PCIe, visible to the host when the kernel retires
+                if (p.host_metrics && p.world == 1) {   // fused D2H: posted writes over PCIe, visible to the host when the kernel retires
                     st_relaxed_sys_f32(p.host_metrics + moff, corr);
                     st_relaxed_sys_f32(p.host_metrics + moff + 1, loss);
                 }
@@ -595,6 +595,15 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                     if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 2); break; }
                 }
             }
+        }
+    }
+    // ---- multi-GPU fused D2H: after the handshake every rank's symmetric metrics buffer holds ALL clients' rows; mirror
+    //      this launch's rows into the pinned host buffer (a few hundred bytes of posted PCIe writes)
+    if (p.world > 1 && p.metrics_peer[0] && p.host_metrics) {
+        __syncthreads();
+        if (crank == 0) {
+            const float* src = p.metrics_peer[p.rank];
+            for (int e = tid; e < p.rounds * C * 4; e += blockDim.x) st_relaxed_sys_f32(p.host_metrics + e, ld_relaxed_sys_f32(src + e));
         }
     }
     if (p.counters && crank == 0 && tid == 0) { p.counters[0] = round0 + p.rounds; p.counters[1] = (int)(flag_base + (unsigned)p.rounds); }

@@ -255,17 +255,18 @@ class DriftSim:
     def _build_round_graph(self, host_inputs: Dict[str, torch.Tensor]):
         """Capture one end-to-end round into ONE CUDA graph (replayed once per round).
 
-        Single GPU: the graph is a single kernel node — ``fed_round_small_kernel`` itself copies the round's inputs from
-        the pinned host tensors into the device arena (16-byte system-scope loads over PCIe) and mirrors the metric rows
-        into the pinned host buffer (fused H2D / D2H, ``host_io``).  Multi-GPU (metrics arrive by peer stores in the
-        symmetric buffer): [H2D memcpy nodes → kernel → D2H memcpy node]."""
+        The graph is a single kernel node — ``fed_round_small_kernel`` itself copies the round's inputs from the pinned
+        host tensors into the device arena (16-byte system-scope loads over PCIe) and mirrors the metric rows into the
+        pinned host buffer (fused H2D / D2H, ``host_io``); with several GPUs every rank copies its own inputs in and
+        mirrors the complete rows after the end-of-launch peer handshake.  Non-pinned inputs fall back to
+        [H2D memcpy nodes → kernel → D2H memcpy node]."""
         from ..ops import small_round
         st = self._small_state()
         cache = small_round.prepare(st)
         t = self.t
         hi = t + host_inputs["X"].shape[0]
         hm = self._host_metrics
-        fused_io = (self.multi is None and host_inputs["X"].is_pinned() and host_inputs["Y"].is_pinned() and hm.is_pinned()
+        fused_io = (host_inputs["X"].is_pinned() and host_inputs["Y"].is_pinned() and hm.is_pinned()
                     and host_inputs["X"].dtype == torch.float32 and host_inputs["Y"].dtype == torch.int32
                     and host_inputs["X"].is_contiguous() and host_inputs["Y"].is_contiguous())
         # warm-up launch outside the capture (lazy allocations, function attributes) — on a snapshot: building the graph

@@ -25,7 +25,24 @@ ref = DriftSim(make_args(comm_round=6, total_train_iteration=3), device=f"cuda:{
 oref = ref.run()
 err = (sim.bank.theta - ref.bank.theta).abs().max().item()
 ok = err < 1e-4 and abs(out["history"][-1]["train_acc"] - oref["history"][-1]["train_acc"]) < 0.02
-print(json.dumps({"rank": rank, "err": err, "ok": bool(ok), "acc": out["history"][-1]["train_acc"]}))
+# end-to-end round graph (fused host I/O on every rank) vs the single-GPU explicit-copy path
+def mk(multi):
+    s_ = DriftSim(make_args(comm_round=6, total_train_iteration=4), device=f"cuda:{rank}")
+    if multi:
+        attach_multi_gpu(s_, world, rank)
+    for t_ in range(2):
+        s_.run_time_step(t_, rounds=4)
+    s_.begin_time_step(2)
+    s_.args.rounds_per_launch = 1
+    return s_
+a, b = mk(True), mk(False)
+ha, hb = a.make_host_round_inputs(), b.make_host_round_inputs()
+for _ in range(3):
+    ra, rb = a.run_round(ha, use_graph=True), b.run_round(hb, use_graph=False)
+    ok = ok and abs(ra["train_acc"] - rb["train_acc"]) < 1e-5 and abs(ra["test_loss"] - rb["test_loss"]) < 1e-3
+check_error(a)
+ok = ok and (a.bank.theta - b.bank.theta).abs().max().item() < 1e-4
+print(json.dumps({"rank": rank, "err": err, "ok": bool(ok), "acc": out["history"][-1]["train_acc"], "e2e": ra, "e2e_ref": rb}))
 dist.destroy_process_group()
 sys.exit(0 if ok else 3)
 '''

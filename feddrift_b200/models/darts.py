@@ -25,11 +25,38 @@ Genotype = namedtuple("Genotype", "normal normal_concat reduce reduce_concat")
 PRIMITIVES = ["none", "max_pool_3x3", "avg_pool_3x3", "skip_connect", "sep_conv_3x3", "sep_conv_5x5", "dil_conv_3x3",
               "dil_conv_5x5"]
 
-FedNAS_V1 = Genotype(
+# Published architecture constants (``darts/genotypes.py:16-93``): NASNet-A, AmoebaNet-A, DARTS first/second order, and
+# the FedNAS search result.
+NASNet = Genotype(
+    normal=[("sep_conv_5x5", 1), ("sep_conv_3x3", 0), ("sep_conv_5x5", 0), ("sep_conv_3x3", 0), ("avg_pool_3x3", 1),
+            ("skip_connect", 0), ("avg_pool_3x3", 0), ("avg_pool_3x3", 0), ("sep_conv_3x3", 1), ("skip_connect", 1)],
+    normal_concat=[2, 3, 4, 5, 6],
+    reduce=[("sep_conv_5x5", 1), ("sep_conv_7x7", 0), ("max_pool_3x3", 1), ("sep_conv_7x7", 0), ("avg_pool_3x3", 1),
+            ("sep_conv_5x5", 0), ("skip_connect", 3), ("avg_pool_3x3", 2), ("sep_conv_3x3", 2), ("max_pool_3x3", 1)],
+    reduce_concat=[4, 5, 6])
+AmoebaNet = Genotype(
+    normal=[("avg_pool_3x3", 0), ("max_pool_3x3", 1), ("sep_conv_3x3", 0), ("sep_conv_5x5", 2), ("sep_conv_3x3", 0),
+            ("avg_pool_3x3", 3), ("sep_conv_3x3", 1), ("skip_connect", 1), ("skip_connect", 0), ("avg_pool_3x3", 1)],
+    normal_concat=[4, 5, 6],
+    reduce=[("avg_pool_3x3", 0), ("sep_conv_3x3", 1), ("max_pool_3x3", 0), ("sep_conv_7x7", 2), ("sep_conv_7x7", 0),
+            ("avg_pool_3x3", 1), ("max_pool_3x3", 0), ("max_pool_3x3", 1), ("conv_7x1_1x7", 0), ("sep_conv_3x3", 5)],
+    reduce_concat=[3, 4, 6])
+DARTS_V1 = Genotype(
+    normal=[("sep_conv_3x3", 1), ("sep_conv_3x3", 0), ("skip_connect", 0), ("sep_conv_3x3", 1), ("skip_connect", 0),
+            ("sep_conv_3x3", 1), ("sep_conv_3x3", 0), ("skip_connect", 2)], normal_concat=[2, 3, 4, 5],
+    reduce=[("max_pool_3x3", 0), ("max_pool_3x3", 1), ("skip_connect", 2), ("max_pool_3x3", 0), ("max_pool_3x3", 0),
+            ("skip_connect", 2), ("skip_connect", 2), ("avg_pool_3x3", 0)], reduce_concat=[2, 3, 4, 5])
+DARTS_V2 = Genotype(
     normal=[("sep_conv_3x3", 0), ("sep_conv_3x3", 1), ("sep_conv_3x3", 0), ("sep_conv_3x3", 1), ("sep_conv_3x3", 1),
-            ("skip_connect", 0), ("skip_connect", 0), ("dil_conv_3x3", 2)], normal_concat=range(2, 6),
+            ("skip_connect", 0), ("skip_connect", 0), ("dil_conv_3x3", 2)], normal_concat=[2, 3, 4, 5],
     reduce=[("max_pool_3x3", 0), ("max_pool_3x3", 1), ("skip_connect", 2), ("max_pool_3x3", 1), ("max_pool_3x3", 0),
-            ("skip_connect", 2), ("skip_connect", 2), ("max_pool_3x3", 1)], reduce_concat=range(2, 6))
+            ("skip_connect", 2), ("skip_connect", 2), ("max_pool_3x3", 1)], reduce_concat=[2, 3, 4, 5])
+DARTS = DARTS_V2
+FedNAS_V1 = Genotype(
+    normal=[("sep_conv_3x3", 1), ("sep_conv_3x3", 0), ("sep_conv_3x3", 2), ("sep_conv_5x5", 0), ("sep_conv_3x3", 1),
+            ("sep_conv_5x5", 3), ("dil_conv_5x5", 3), ("sep_conv_3x3", 4)], normal_concat=range(2, 6),
+    reduce=[("max_pool_3x3", 0), ("skip_connect", 1), ("max_pool_3x3", 0), ("max_pool_3x3", 2), ("max_pool_3x3", 0),
+            ("dil_conv_5x5", 1), ("max_pool_3x3", 0), ("dil_conv_5x5", 2)], reduce_concat=range(2, 6))
 
 
 class Zero(nn.Module):
@@ -83,6 +110,11 @@ OPS = {
     "sep_conv_5x5": lambda C, s, a: SepConv(C, C, 5, s, 2, a),
     "dil_conv_3x3": lambda C, s, a: DilConv(C, C, 3, s, 2, 2, a),
     "dil_conv_5x5": lambda C, s, a: DilConv(C, C, 5, s, 4, 2, a),
+    # only used by the NASNet / AmoebaNet evaluation genotypes (``operations.py:13-19``)
+    "sep_conv_7x7": lambda C, s, a: SepConv(C, C, 7, s, 3, a),
+    "conv_7x1_1x7": lambda C, s, a: nn.Sequential(
+        nn.ReLU(inplace=False), nn.Conv2d(C, C, (1, 7), stride=(1, s), padding=(0, 3), bias=False),
+        nn.Conv2d(C, C, (7, 1), stride=(s, 1), padding=(3, 0), bias=False), nn.BatchNorm2d(C, affine=a)),
 }
 
 
@@ -293,6 +325,49 @@ class NetworkCIFAR(nn.Module):
     def forward(self, x):
         logits_aux = None
         s0 = s1 = self.stem(x)
+        for i, cell in enumerate(self.cells):
+            s0, s1 = s1, cell(s0, s1, self.drop_path_prob)
+            if i == 2 * self._layers // 3 and self._auxiliary and self.training:
+                logits_aux = self.auxiliary_head(s1)
+        return self.classifier(self.global_pooling(s1).flatten(1)), logits_aux
+
+
+class NetworkImageNet(nn.Module):
+    """ImageNet-sized evaluation network (``model.py:161-217``): two stride-2 stems (224² → 28²), cells as in
+    ``NetworkCIFAR`` with ``reduction_prev = True`` for the first cell, 7×7 average pool, optional auxiliary head."""
+
+    def __init__(self, C, num_classes, layers, auxiliary, genotype):
+        super().__init__()
+        self._layers, self._auxiliary, self.drop_path_prob = layers, auxiliary, 0.0
+        self.stem0 = nn.Sequential(nn.Conv2d(3, C // 2, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(C // 2),
+                                   nn.ReLU(inplace=True), nn.Conv2d(C // 2, C, 3, stride=2, padding=1, bias=False),
+                                   nn.BatchNorm2d(C))
+        self.stem1 = nn.Sequential(nn.ReLU(inplace=True), nn.Conv2d(C, C, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(C))
+        C_pp, C_p, C_curr = C, C, C
+        self.cells = nn.ModuleList()
+        reduction_prev, C_aux = True, None
+        for i in range(layers):
+            reduction = layers >= 3 and i in (layers // 3, 2 * layers // 3)
+            if reduction:
+                C_curr *= 2
+            cell = EvalCell(genotype, C_pp, C_p, C_curr, reduction, reduction_prev)
+            reduction_prev = reduction
+            self.cells.append(cell)
+            C_pp, C_p = C_p, cell.multiplier * C_curr
+            if i == 2 * layers // 3:
+                C_aux = C_p
+        if auxiliary and C_aux is not None:
+            self.auxiliary_head = nn.Sequential(nn.ReLU(inplace=True), nn.AvgPool2d(5, stride=2, padding=0, count_include_pad=False),
+                                                nn.Conv2d(C_aux, 128, 1, bias=False), nn.BatchNorm2d(128), nn.ReLU(inplace=True),
+                                                nn.Conv2d(128, 768, 2, bias=False), nn.ReLU(inplace=True), nn.Flatten(),
+                                                TcLinear(768, num_classes))
+        self.global_pooling = nn.AvgPool2d(7)
+        self.classifier = TcLinear(C_p, num_classes)
+
+    def forward(self, x):
+        logits_aux = None
+        s0 = self.stem0(x)
+        s1 = self.stem1(s0)
         for i, cell in enumerate(self.cells):
             s0, s1 = s1, cell(s0, s1, self.drop_path_prob)
             if i == 2 * self._layers // 3 and self._auxiliary and self.training:

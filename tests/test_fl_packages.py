@@ -246,3 +246,15 @@ def test_darts_standalone_search_then_train(tmp_path):
     assert "digraph" in (tmp_path / "normal.dot").read_text()
     out = cli.main(["train", "--arch", str(tmp_path / "genotype.json"), "--auxiliary", "--cutout"] + common)
     assert len(out["history"]) == 1 and (tmp_path / "weights.pt").exists()
+
+
+def test_darts_published_genotypes_and_imagenet_network():
+    from feddrift_b200.models import darts
+    for name in ("NASNet", "AmoebaNet", "DARTS_V1", "DARTS_V2", "FedNAS_V1"):
+        g = getattr(darts, name)
+        net = darts.NetworkCIFAR(8, 10, 3, False, g).eval()
+        assert net(torch.randn(2, 3, 32, 32))[0].shape == (2, 10), name
+    assert darts.DARTS is darts.DARTS_V2 and darts.FedNAS_V1.normal[2] == ("sep_conv_3x3", 2)
+    inet = darts.NetworkImageNet(16, 20, 3, True, darts.DARTS_V2).train()
+    logits, aux = inet(torch.randn(2, 3, 224, 224))
+    assert logits.shape == (2, 20) and aux.shape == (2, 20)

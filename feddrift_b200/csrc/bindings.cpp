@@ -403,6 +403,20 @@ Tensor col2im(Tensor dcols, int64_t B, int64_t C, int64_t H, int64_t W, int64_t 
     return dx;
 }
 
+// Launch an instantiated CUDA graph on the current stream and (optionally) wait for it, with the GIL released: the
+// end-to-end round path calls this once per round instead of CUDAGraph.replay() + Stream.synchronize() (two Python →
+// C++ round trips).  `exec` is `torch.cuda.CUDAGraph.raw_cuda_graph_exec()`.
+void graph_launch_sync(int64_t exec, bool sync) {
+    cudaStream_t stream = cur_stream();
+    pybind11::gil_scoped_release nogil;
+    cudaError_t e = cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(exec), stream);
+    if (e == cudaSuccess && sync) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        pybind11::gil_scoped_acquire gil;
+        TORCH_CHECK(false, "graph_launch_sync: ", cudaGetErrorString(e));
+    }
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -432,6 +446,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("gemm_tn_bias_act_peer", &gemm_tn_bias_act_peer);
     m.def("gemm_bias_act", &gemm_bias_act);
     m.def("gossip_mix_peer", &gossip_mix_peer);
+    m.def("graph_launch_sync", &graph_launch_sync);
     m.def("im2col_bf16", &im2col_bf16);
     m.def("col2im", &col2im);
 }

@@ -320,15 +320,27 @@ class DriftSim:
             if gr is None or gr[1] is not host_inputs:
                 if getattr(self, "_host_metrics", None) is None or not self._host_metrics.is_pinned():
                     self._host_metrics = torch.zeros(self.C, 4, dtype=torch.float32).pin_memory()
-                gr = self._graph = (self._build_round_graph(host_inputs), host_inputs, self._host_metrics.numpy(),
-                                    torch.cuda.current_stream())
-            gr[0].replay()
+                g = self._build_round_graph(host_inputs)
+                fast = None
+                try:   # one C++ call per round (graph launch + stream sync, GIL released) when the raw handle is exposed
+                    from ..ops import _ext
+                    ext = _ext.load()
+                    if ext is not None and hasattr(ext, "graph_launch_sync") and hasattr(g, "raw_cuda_graph_exec"):
+                        handle = int(g.raw_cuda_graph_exec())
+                        fast = (ext.graph_launch_sync, handle)
+                except Exception:  # noqa: BLE001  (older torch: fall back to replay() + synchronize())
+                    fast = None
+                gr = self._graph = (g, host_inputs, self._host_metrics.numpy(), torch.cuda.current_stream(), fast)
+            if gr[4] is not None:
+                gr[4][0](gr[4][1], True)
+            else:
+                gr[0].replay()
+                gr[3].synchronize()
             self.round_in_step += 1
             self.global_round += 1
             _SMALL_LAUNCHES["fed_round_small"] += 1
             if self.multi is not None:
                 self.multi["flag_base"] = int(self.multi["flag_base"]) + 1
-            gr[3].synchronize()
             return self._round_result(gr[2], log)
         st = self._small_state()
         t = self.t

@@ -73,12 +73,25 @@ class Evaluator:
             acc = (corr / ns).double().cpu().numpy()
             acc[:, (self.data.nsamp[t] == 0).cpu().numpy()] = 0.0
             return acc
-        out = np.zeros((len(model_ids), C))
-        for r, m in enumerate(model_ids):
-            for c in range(C):
-                k, n, _ = self.infer_client(m, c, t)
-                out[r, c] = k / n if n else 0.0
-        return out
+        # module path: ONE batched forward per model over (chunks of) all clients' samples, per-client correct counts by
+        # a masked reduction on device, a single host copy for the whole matrix (instead of M·C forwards + .tolist()s)
+        dev = self.bank.device
+        S = self.data.X.shape[2]
+        X, Y = self.data.X[t].to(dev), self.data.Y[t].to(dev).long()
+        ns = self.data.nsamp[t].to(dev)
+        mask = (torch.arange(S, device=dev)[None, :] < ns[:, None]).float()
+        per_chunk = max(1, self.eval_batch * 8 // max(S, 1))
+        corr = torch.zeros(len(model_ids), C, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for r, m in enumerate(model_ids):
+                for c0 in range(0, C, per_chunk):
+                    c1 = min(C, c0 + per_chunk)
+                    logits = self.bank.forward(m, X[c0:c1].reshape((c1 - c0) * S, *X.shape[2:]))
+                    hit = (logits.argmax(-1) == Y[c0:c1].reshape(-1)).float().reshape(c1 - c0, S)
+                    corr[r, c0:c1] = (hit * mask[c0:c1]).sum(1)
+        acc = (corr / ns.clamp(min=1).float()[None, :]).double().cpu().numpy()
+        acc[:, (self.data.nsamp[t] == 0).cpu().numpy()] = 0.0
+        return acc
 
     def pooled_acc(self, m: int, pairs: List[Tuple[int, int]], max_batches: int, rng) -> float:
         """Accuracy of model m on the pooled, shuffled batches of the (client, time) pairs — at most

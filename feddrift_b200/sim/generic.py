@@ -67,8 +67,7 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
         for c in range(C):
             if world > 1 and c % world != rank:   # clients are sharded over the ranks (one process per GPU)
                 continue
-            Xc = Xc_all[:, c].reshape(T1 * S, *data.X.shape[3:])
-            Yc = data.Y[:, c].reshape(T1 * S)
+            xy = _lazy_client_xy(Xc_all, data, c, T1, S)
             for m in range(M):
                 if not bool(active[m]):
                     continue
@@ -78,10 +77,10 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
                 if slots:
                     with torch.cuda.stream(slots[pair_i % len(slots)]):
                         cl.params[c, m].copy_(bank.theta[m])
-                        _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, a.wd, feat_mask, pair_i % len(slots))
+                        _local_steps(sim, c, m, xy, sampler, seed, rnd, E, use_adam, lr, a.wd, feat_mask, pair_i % len(slots))
                 else:
                     cl.params[c, m].copy_(bank.theta[m])
-                    _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, a.wd, feat_mask)
+                    _local_steps(sim, c, m, xy, sampler, seed, rnd, E, use_adam, lr, a.wd, feat_mask)
                 pair_i += 1
                 cl.n[c, m] = n_cm
         _join_slots(sim, slots)
@@ -133,14 +132,31 @@ def _peer_aggregate(sim, world, rank):
     sim.bank.theta.copy_(theta)
 
 
+def _lazy_client_xy(Xc_all, data, c, T1, S):
+    cache = []
+
+    def xy():
+        if not cache:
+            cache.append((Xc_all[:, c].reshape(T1 * S, *data.X.shape[3:]), data.Y[:, c].reshape(T1 * S)))
+        return cache[0]
+    return xy
+
+
 def _cpu(x: Optional[torch.Tensor]):
     return x.cpu() if isinstance(x, torch.Tensor) else x
 
 
 class _GraphedStep:
-    """One local step (zero-grad → forward → CE → backward → fused optimizer row update) captured as a CUDA graph."""
+    """Local training captured as a CUDA graph over static buffers.
 
-    def __init__(self, sim, batch_shape, use_adam: bool, lr: float, wd: float):
+    * per-step mode (``indexed=False``): ONE step (zero-grad → forward → CE → backward → fused optimizer row update);
+      the caller copies each minibatch into ``x`` / ``y`` and replays;
+    * per-pair mode (``indexed=True``): ALL ``steps`` local steps of a (client, model) pair in one graph; every step
+      starts with a gather node that pulls its minibatch out of the device-resident dataset through the static index
+      buffer ``idx[e]`` (global sample ids), so a pair costs one index upload, one multi-tensor state load, ONE replay
+      and one multi-tensor state store on the host side."""
+
+    def __init__(self, sim, batch_shape, use_adam: bool, lr: float, wd: float, steps: int = 1, indexed: bool = False):
         import copy
         bank, dev = sim.bank, sim.device
         P = bank.P
@@ -149,6 +165,11 @@ class _GraphedStep:
         self.step = torch.zeros(1, dtype=torch.int32, device=dev)
         self.x = torch.zeros(batch_shape, dtype=sim.data.X.dtype, device=dev)
         self.y = torch.zeros(batch_shape[0], dtype=torch.long, device=dev)
+        self.steps, self.indexed = int(steps), bool(indexed)
+        if self.indexed:
+            self.idx = torch.zeros(self.steps, batch_shape[0], dtype=torch.long, device=dev)
+            self.Xf = sim.data.X.reshape(-1, *sim.data.X.shape[3:])      # [T1·C·S, …] view of the resident dataset
+            self.Yf = sim.data.Y.reshape(-1)
         self.row.copy_(bank.theta[0])
         self.mod = copy.deepcopy(bank.template).to(dev)
         _bind(self.mod, bank, self.row)
@@ -170,25 +191,38 @@ class _GraphedStep:
         self.launches = 0
 
     def _body(self):
-        self.g.zero_()
-        F.cross_entropy(self.mod(self.x), self.y).backward()
-        if self.use_adam:
-            ops.adam_amsgrad_rows_(self.row.view(1, -1), self.g.view(1, -1), self.m.view(1, -1), self.v.view(1, -1),
-                                   self.vmax.view(1, -1), self.step, self.lr, self.wd)
-        else:
-            ops.sgd_rows_(self.row.view(1, -1), self.g.view(1, -1), self.lr, 0.0)
+        for e in range(self.steps if self.indexed else 1):
+            if self.indexed:
+                x, y = self.Xf.index_select(0, self.idx[e]), self.Yf.index_select(0, self.idx[e]).long()
+            else:
+                x, y = self.x, self.y
+            self.g.zero_()
+            F.cross_entropy(self.mod(x), y).backward()
+            if self.use_adam:
+                ops.adam_amsgrad_rows_(self.row.view(1, -1), self.g.view(1, -1), self.m.view(1, -1), self.v.view(1, -1),
+                                       self.vmax.view(1, -1), self.step, self.lr, self.wd)
+            else:
+                ops.sgd_rows_(self.row.view(1, -1), self.g.view(1, -1), self.lr, 0.0)
 
     def load(self, cl, c, m):
-        self.row.copy_(cl.params[c, m])
-        if self.use_adam:
-            self.m.copy_(cl.m[c, m]); self.v.copy_(cl.v[c, m]); self.vmax.copy_(cl.vmax[c, m])
+        if self.use_adam:   # one multi-tensor copy kernel instead of four
+            torch._foreach_copy_([self.row, self.m, self.v, self.vmax], [cl.params[c, m], cl.m[c, m], cl.v[c, m], cl.vmax[c, m]])
             self.step.copy_(cl.step[c, m].reshape(1))
+        else:
+            self.row.copy_(cl.params[c, m])
 
     def store(self, cl, c, m):
-        cl.params[c, m].copy_(self.row)
         if self.use_adam:
-            cl.m[c, m].copy_(self.m); cl.v[c, m].copy_(self.v); cl.vmax[c, m].copy_(self.vmax)
+            torch._foreach_copy_([cl.params[c, m], cl.m[c, m], cl.v[c, m], cl.vmax[c, m]], [self.row, self.m, self.v, self.vmax])
             cl.step[c, m].copy_(self.step[0])
+        else:
+            cl.params[c, m].copy_(self.row)
+
+    def run_pair(self, gidx_cpu: torch.Tensor):
+        """Per-pair mode: upload the [steps, B] global sample ids and replay the whole local training of the pair."""
+        self.idx.copy_(gidx_cpu, non_blocking=True)
+        self.graph.replay()
+        self.launches += 1
 
     def run(self, xb, yb):
         self.x.copy_(xb)
@@ -223,21 +257,21 @@ def _join_slots(sim, slots):
             main.wait_stream(s_)
 
 
-def _graphed_step(sim, batch_shape, use_adam, lr, wd, slot: int = 0):
+def _graphed_step(sim, batch_shape, use_adam, lr, wd, slot: int = 0, steps: int = 1, indexed: bool = False):
     """Cached ``_GraphedStep`` for this (batch shape, optimizer, lr) or None when graphs are unavailable."""
     import os
     if sim.device.type != "cuda" or sim.bank.mlp is not None or os.environ.get("FDB_NO_GRAPHS") == "1" \
             or getattr(sim, "_graphs_broken", False):
         return None
     cache = sim.__dict__.setdefault("_step_graphs", {})
-    key = (tuple(batch_shape), bool(use_adam), float(lr), float(wd), int(slot))
+    key = (tuple(batch_shape), bool(use_adam), float(lr), float(wd), int(slot), int(steps), bool(indexed))
     gs = cache.get(key)
     if gs is None:
         nslots = max(1, len(sim.__dict__.get("_slot_streams") or [1]))
         if len(cache) >= 2 * nslots:        # e.g. Adaptive-FedAvg changes lr every round: keep the pool small
             cache.pop(next(iter(cache)))
         try:
-            gs = cache[key] = _GraphedStep(sim, batch_shape, use_adam, lr, wd)
+            gs = cache[key] = _GraphedStep(sim, batch_shape, use_adam, lr, wd, steps, indexed)
         except Exception as exc:  # noqa: BLE001  (capture is an optimisation; the eager path is always valid)
             import logging
             logging.warning("CUDA-graph capture of the local step failed (%s); running eagerly", exc)
@@ -247,7 +281,9 @@ def _graphed_step(sim, batch_shape, use_adam, lr, wd, slot: int = 0):
     return gs
 
 
-def _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, wd, feat_mask, slot: int = 0):
+def _local_steps(sim, c, m, xy, sampler, seed, rnd, E, use_adam, lr, wd, feat_mask, slot: int = 0):
+    """``xy()`` lazily materialises the client's flattened samples (only the non-indexed paths need that copy)."""
+    Xc = Yc = None
     bank, cl = sim.bank, sim.clients
     row = cl.params[c, m]
     mlp = bank.mlp
@@ -257,6 +293,19 @@ def _local_steps(sim, c, m, Xc, Yc, sampler, seed, rnd, E, use_adam, lr, wd, fea
         idxs.append(sampler(h1, mix32(h1 ^ 0x68E31DA4)))
     # one H2D + one gather for all E minibatches of this pair when they have equal length (the common case)
     same = all(i.numel() == idxs[0].numel() for i in idxs)
+    if same and feat_mask is None and mlp is None and sim.device.type == "cuda":
+        # per-pair graph: the minibatch gathers are graph nodes reading the resident dataset through global sample ids
+        S_, C_ = sim.data.X.shape[2], sim.C
+        loc = torch.stack(idxs)                                              # [E, B] ids into the client's [T1·S] axis
+        gidx = (loc // S_) * (C_ * S_) + c * S_ + (loc % S_)
+        gs = _graphed_step(sim, (loc.shape[1],) + tuple(sim.data.X.shape[3:]), use_adam, lr, wd, slot, steps=E, indexed=True)
+        if gs is not None:
+            gs.load(cl, c, m)
+            gs.run_pair(gidx)
+            gs.store(cl, c, m)
+            return
+    if Xc is None:
+        Xc, Yc = xy()
     if same:
         idx_all = torch.stack(idxs).to(Xc.device, non_blocking=True)
         xs, ys = Xc[idx_all], Yc[idx_all].long()

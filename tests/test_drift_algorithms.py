@@ -153,3 +153,20 @@ def test_generic_path_equals_fused_reference_path():
     s2.run()
     assert torch.allclose(s1.bank.theta, s2.bank.theta, rtol=1e-4, atol=1e-5)
     assert abs(s1.history[-1]["test_acc"] - s2.history[-1]["test_acc"]) < 1e-6
+
+
+def test_batched_acc_matrix_equals_per_client_inference_for_module_models():
+    """Evaluator.acc_matrix on the nn.Module path (one batched forward per model) vs M·C separate `infer_client` calls."""
+    from feddrift_b200.sim import DriftSim, make_args
+    sim = DriftSim(make_args(model="cnn", dataset="MNIST", client_num_in_total=5, client_num_per_round=5, sample_num=12,
+                             batch_size=4, comm_round=1, total_train_iteration=2, concept_drift_algo="win-1"), device="cpu")
+    ev = sim.evaluator
+    for m in range(sim.M):
+        sim.bank.reset_parameters_random(m, torch.Generator().manual_seed(m))
+    sim.data.nsamp[0, 2] = 7          # a partially filled client and an empty one
+    sim.data.nsamp[0, 4] = 0
+    got = ev.acc_matrix(list(range(sim.M)), 0)
+    for m in range(sim.M):
+        for c in range(5):
+            k, n, _ = ev.infer_client(m, c, 0)
+            assert abs(got[m, c] - (k / n if n else 0.0)) < 1e-6, (m, c)

@@ -153,3 +153,22 @@ def test_end_to_end_round_graph_with_fused_host_io_matches_copy_path():
     rb = b.run_round(hb, use_graph=False)
     assert abs(ra["train_acc"] - rb["train_acc"]) < 1e-5 and ra["train_acc"] < 0.5
     assert torch.allclose(a.bank.theta, b.bank.theta, atol=1e-6)
+
+
+def test_generic_executor_graphed_pairs_match_eager(monkeypatch):
+    """The CUDA-graphed per-pair local training (in-graph minibatch gathers, 8 concurrent streams) must reproduce the
+    eager execution of the same ops (fnn-MNIST: no dropout, so both runs consume identical randomness)."""
+    from feddrift_b200.sim import DriftSim, make_args
+    from feddrift_b200.utils.metrics import MetricsSink
+    kw = dict(model="fnn", dataset="MNIST", client_num_in_total=6, client_num_per_round=6, concept_drift_algo="softcluster",
+              concept_drift_algo_arg="H_A_C_1_10_0", concept_num=2, change_points="A", sample_num=16, batch_size=8, comm_round=2,
+              total_train_iteration=2, epochs=3)
+    monkeypatch.setenv("FDB_NO_GRAPHS", "1")
+    eager = DriftSim(make_args(**kw), device="cuda", sink=MetricsSink())
+    out_e = eager.run()
+    monkeypatch.delenv("FDB_NO_GRAPHS")
+    graphed = DriftSim(make_args(**kw), device="cuda", sink=MetricsSink())
+    out_g = graphed.run()
+    assert any(g.indexed and g.launches > 0 for g in graphed.__dict__.get("_step_graphs", {}).values()), "per-pair graphs not used"
+    assert (eager.bank.theta - graphed.bank.theta).abs().max().item() < 5e-3
+    assert abs(out_e["history"][-1]["train_loss"] - out_g["history"][-1]["train_loss"]) < 5e-2

@@ -185,8 +185,12 @@ class _GraphedStep:
             for _ in range(2):              # warm-up (cuDNN autotune, lazy inits) outside the capture
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
+        # a DEDICATED capture stream per graph: cuBLAS keeps one workspace per (handle, stream), and torch.cuda.graph's
+        # default capture stream is shared by all captures — graphs captured there would share a split-K workspace and
+        # race when they are replayed concurrently on the slot streams
+        self._capture_stream = torch.cuda.Stream(device=dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=self._capture_stream):
             self._body()
         self.launches = 0
 
@@ -293,7 +297,8 @@ def _local_steps(sim, c, m, xy, sampler, seed, rnd, E, use_adam, lr, wd, feat_ma
         idxs.append(sampler(h1, mix32(h1 ^ 0x68E31DA4)))
     # one H2D + one gather for all E minibatches of this pair when they have equal length (the common case)
     same = all(i.numel() == idxs[0].numel() for i in idxs)
-    if same and feat_mask is None and mlp is None and sim.device.type == "cuda":
+    import os
+    if same and feat_mask is None and mlp is None and sim.device.type == "cuda" and os.environ.get("FDB_NO_PAIR_GRAPH") != "1":
         # per-pair graph: the minibatch gathers are graph nodes reading the resident dataset through global sample ids
         S_, C_ = sim.data.X.shape[2], sim.C
         loc = torch.stack(idxs)                                              # [E, B] ids into the client's [T1·S] axis

@@ -132,6 +132,12 @@ def _peer_aggregate(sim, world, rank):
     sim.bank.theta.copy_(theta)
 
 
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Image batches enter conv nets in channels_last: cuDNN's tensor-core kernels are NHWC, and with NCHW activations
+    28 % of a ResNet-18 step's GPU time was nchwToNhwc / nhwcToNchw conversion kernels (profiles/README.md)."""
+    return x.contiguous(memory_format=torch.channels_last) if x.is_cuda and x.dim() == 4 else x
+
+
 def _lazy_client_xy(Xc_all, data, c, T1, S):
     cache = []
 
@@ -201,7 +207,7 @@ class _GraphedStep:
             else:
                 x, y = self.x, self.y
             self.g.zero_()
-            F.cross_entropy(self.mod(x), y).backward()
+            F.cross_entropy(self.mod(_nhwc(x)), y).backward()
             if self.use_adam:
                 ops.adam_amsgrad_rows_(self.row.view(1, -1), self.g.view(1, -1), self.m.view(1, -1), self.v.view(1, -1),
                                        self.vmax.view(1, -1), self.step, self.lr, self.wd)
@@ -344,7 +350,7 @@ def _local_steps(sim, c, m, xy, sampler, seed, rnd, E, use_adam, lr, wd, feat_ma
         else:
             for p_ in mod.parameters():
                 p_.grad = None
-            F.cross_entropy(mod(xb), yb).backward()
+            F.cross_entropy(mod(_nhwc(xb)), yb).backward()
             g = _flat_grads(mod, bank, row)
         r2 = row.reshape(1, -1)
         if use_adam:

@@ -130,8 +130,6 @@ class ModelBank:
             return mlp_forward(self.theta[m], x.reshape(x.shape[0], -1), s["kind"], s["in"], s["hidden"], s["out"])
         mod = self.module(m)
         mod.train(train)
-        if x.is_cuda and x.dim() == 4:      # NHWC activations for cuDNN's tensor-core conv kernels (see sim/generic._nhwc)
-            x = x.contiguous(memory_format=torch.channels_last)
         return mod(x)
 
 

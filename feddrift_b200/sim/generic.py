@@ -133,9 +133,14 @@ def _peer_aggregate(sim, world, rank):
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
-    """Image batches enter conv nets in channels_last: cuDNN's tensor-core kernels are NHWC, and with NCHW activations
-    28 % of a ResNet-18 step's GPU time was nchwToNhwc / nhwcToNchw conversion kernels (profiles/README.md)."""
-    return x.contiguous(memory_format=torch.channels_last) if x.is_cuda and x.dim() == 4 else x
+    """Opt-in (``FDB_NHWC=1``) channels_last activations for conv nets.  With NCHW activations 28 % of a ResNet-18 step's
+    GPU time is cuDNN's nchwToNhwc / nhwcToNchw conversion kernels (tools/profile_generic.py), but NHWC kernels need
+    16-byte aligned weight pointers and the conv weights are 4-byte aligned views into the flat parameter row (a first
+    attempt faulted with "misaligned address"): the arena needs 16-byte aligned tensor offsets first."""
+    import os
+    if os.environ.get("FDB_NHWC") == "1" and x.is_cuda and x.dim() == 4:
+        return x.contiguous(memory_format=torch.channels_last)
+    return x
 
 
 def _lazy_client_xy(Xc_all, data, c, T1, S):

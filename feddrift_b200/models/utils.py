@@ -40,25 +40,53 @@ def create_model(model_name: str, output_dim: int, feature_dim: int = None, **kw
 
 
 # ----------------------------------------------------------------------------- flat views
+_ALIGN_MIN_NUMEL = 256   # tensors at least this big start on a 16-byte boundary of the flat row
+_ALIGN_FLOATS = 4
+
+
 def flat_spec(module_or_sd) -> List[Tuple[str, torch.Size, torch.dtype, int, int]]:
-    """(key, shape, dtype, offset, numel) for every state_dict entry, in state_dict order."""
+    """(key, shape, dtype, offset, numel) for every state_dict entry, in state_dict order.
+
+    Big tensors (conv / linear weights) are placed at offsets that are multiples of 4 floats so that the views the
+    modules train through are 16-byte aligned (cuDNN's NHWC tensor-core kernels, TMA and 128-bit loads require it);
+    the gaps are zero and ride along in every row operation.  Small-MLP layouts (every tensor < 256 elements) stay
+    densely packed — the register-resident MLP kernels index W1 | b1 | W2 | b2 contiguously."""
     sd = module_or_sd.state_dict() if isinstance(module_or_sd, nn.Module) else module_or_sd
     out, off = [], 0
     for k, v in sd.items():
         n = v.numel()
+        if n >= _ALIGN_MIN_NUMEL:
+            off = (off + _ALIGN_FLOATS - 1) // _ALIGN_FLOATS * _ALIGN_FLOATS
         out.append((k, v.shape, v.dtype, off, n))
         off += n
     return out
 
 
 def flat_size(module_or_sd) -> int:
+    """Row length: end of the last tensor, rounded up to 4 floats for models with aligned (big) tensors so that every
+    row of a dense ``[C, M, P]`` arena starts on a 16-byte boundary too."""
     spec = flat_spec(module_or_sd)
-    return spec[-1][3] + spec[-1][4] if spec else 0
+    if not spec:
+        return 0
+    end = spec[-1][3] + spec[-1][4]
+    if any(n >= _ALIGN_MIN_NUMEL for _, _, _, _, n in spec):
+        end = (end + _ALIGN_FLOATS - 1) // _ALIGN_FLOATS * _ALIGN_FLOATS
+    return end
 
 
 def flatten_state_dict(sd: Dict[str, torch.Tensor], out: torch.Tensor = None) -> torch.Tensor:
-    parts = [v.reshape(-1).to(torch.float32) for v in sd.values()]
-    flat = torch.cat(parts) if parts else torch.zeros(0)
+    """state_dict → flat fp32 row laid out by ``flat_spec(sd)`` (alignment gaps are zero)."""
+    spec = flat_spec(sd)
+    total = flat_size(sd)
+    vals = list(sd.values())
+    dev = vals[0].device if vals else "cpu"
+    dense = all(spec[i][3] + spec[i][4] == spec[i + 1][3] for i in range(len(spec) - 1))
+    if dense and (not spec or spec[-1][3] + spec[-1][4] == total):   # dense layout: one cat
+        flat = torch.cat([v.reshape(-1).to(torch.float32) for v in vals]) if vals else torch.zeros(0)
+    else:
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        for (_, _, _, off, n), v in zip(spec, vals):
+            flat[off:off + n] = v.reshape(-1).to(torch.float32)
     if out is not None:
         out.copy_(flat)
         return out
@@ -76,6 +104,8 @@ def weight_param_mask(spec) -> torch.Tensor:
     """1 for learnable weights, 0 for BN running stats / counters (robust aggregation excludes them)."""
     from ..core.robustness import is_weight_param
     total = spec[-1][3] + spec[-1][4] if spec else 0
+    if any(n >= _ALIGN_MIN_NUMEL for _, _, _, _, n in spec):
+        total = (total + _ALIGN_FLOATS - 1) // _ALIGN_FLOATS * _ALIGN_FLOATS
     mask = torch.zeros(total, dtype=torch.bool)
     for k, _, _, off, n in spec:
         if is_weight_param(k):

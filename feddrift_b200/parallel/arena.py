@@ -62,8 +62,9 @@ class ModelBank:
         for m in range(num_models):
             self.theta[m].copy_(self.init_row)
         self._modules: Dict[int, nn.Module] = {}
-        self.float_mask = torch.tensor([dt.is_floating_point for _, _, dt, _, n in self.spec for _ in range(n)],
-                                       dtype=torch.bool) if self.spec else torch.zeros(0, dtype=torch.bool)
+        self.float_mask = torch.zeros(self.P, dtype=torch.bool)
+        for _, _, dt, off, n in self.spec:
+            self.float_mask[off:off + n] = bool(dt.is_floating_point)
 
     # -- state_dict interop ---------------------------------------------------------------
     def state_dict(self, m: int) -> "OrderedDict[str, torch.Tensor]":

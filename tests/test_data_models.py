@@ -99,3 +99,20 @@ def test_tcconv2d_is_a_drop_in_for_nn_conv2d():
     assert torch.allclose(a(x), b(x), atol=1e-6)
     from feddrift_b200.models.cnn import CNN_DropOut
     assert sum(p.numel() for p in CNN_DropOut().parameters()) == 1_199_882
+
+
+def test_flat_arena_layout_aligns_big_tensors_and_round_trips():
+    import torch
+    from feddrift_b200.models import create_model
+    from feddrift_b200.models import utils as mu
+    for name, kw in (("cnn", {}), ("resnet56", {}), ("rnn", {})):
+        net = create_model(name, 10, 784, **kw)
+        spec = mu.flat_spec(net)
+        assert all(off % 4 == 0 for _, _, _, off, n in spec if n >= 256), name
+        sd = net.state_dict()
+        flat = mu.flatten_state_dict(sd)
+        assert flat.numel() == mu.flat_size(net)
+        back = mu.unflatten_to_state_dict(flat, spec)
+        assert all(torch.equal(back[k].float(), v.float()) for k, v in sd.items()), name
+    mlp = create_model("fnn", 2, 3)   # SEA fnn: dense W1 | b1 | W2 | b2 (the fused kernel's layout), P = 38
+    assert mu.flat_size(mlp) == 38 and [s[3] for s in mu.flat_spec(mlp)] == [0, 18, 24, 36]

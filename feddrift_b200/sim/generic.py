@@ -433,22 +433,42 @@ def _evaluate(sim, plan, st, r, metrics, ens_mode):
         _eval_grouped(sim, t, mtr, mine, metrics[r], 0)
         if ens_mode == 0 and t + 1 < data.steps:
             _eval_grouped(sim, t + 1, mte, mine, metrics[r], 2)
-    if ens_mode == 0:
+    if ens_mode == 0 or t + 1 >= data.steps:
         return
-    acc = torch.zeros(3, dtype=torch.float32, device=sim.device)
+    _eval_ensemble_grouped(sim, plan, t + 1, mine, metrics[r], ens_mode)
+
+
+def _eval_ensemble_grouped(sim, plan, tt: int, clients, out, ens_mode: int):
+    """Ensemble test metric (AUE / AUE-PC weighted hard vote, KUE weighted soft vote) with ONE batched forward per
+    ensemble member over all clients (chunked) instead of a forward per (client, member): per-sample tallies
+    ``Σ_k w[c,k]·onehot(pred_k)`` (hard) or ``Σ_k w[c,k]·softmax_k`` (soft) are accumulated on device, the vote is the
+    arg-max class, correct counts go to ``out[c, 2]``."""
+    data, bank, dev = sim.data, sim.bank, sim.device
+    S, classes = data.X.shape[2], int(data.class_num)
+    nsamp = sim.data_host.nsamp[tt]
+    cs = [c for c in clients if int(nsamp[c]) > 0]
+    if not cs:
+        return
+    Wc = torch.as_tensor(plan["ens_w"]).double().cpu()[cs].clamp(min=0).to(dev)     # [n, M]; non-positive weights do not vote
+    members = [k for k in range(bank.num_models) if bool((Wc[:, k] > 0).any())]
+    per_chunk = max(1, 8192 // max(S, 1))
+    ar = torch.arange(S, device=dev)
     with torch.no_grad():
-        for c in mine:
-            if t + 1 < data.steps:
-                n1 = int(sim.data_host.nsamp[t + 1, c])
-                if n1 == 0:
-                    continue
-                x1, y1 = data.X[t + 1, c, :n1], data.Y[t + 1, c, :n1]
-                w = plan["ens_w"][c]
-                ks = [k for k in range(bank.num_models) if float(w[k]) > 0]
+        for i in range(0, len(cs), per_chunk):
+            ck = cs[i:i + per_chunk]
+            ct = torch.tensor(ck, device=dev)
+            X = data.X[tt].index_select(0, ct)
+            Y = data.Y[tt].index_select(0, ct).long()
+            mask = ar[None, :] < nsamp[ck].to(dev)[:, None]
+            tally = torch.zeros(len(ck), S, classes, dtype=torch.float64, device=dev)
+            wck = Wc[i:i + per_chunk]
+            for k in members:
+                logits = bank.forward(k, X.reshape(len(ck) * S, *X.shape[2:])).float()
+                wk = wck[:, k][:, None, None]
                 if ens_mode == 1:
-                    preds = torch.stack([bank.forward(k, x1).argmax(-1) for k in ks])
-                    vote = ops.ensemble_vote(preds, w[ks].to(sim.device), data.class_num)
+                    pred = logits.argmax(-1).reshape(len(ck), S, 1)
+                    tally.scatter_add_(2, pred, wk.expand(len(ck), S, 1).contiguous())
                 else:
-                    probs = torch.stack([torch.softmax(bank.forward(k, x1), 1) for k in ks])
-                    vote = ops.soft_vote(probs, w[ks].to(sim.device))
-                metrics[r, c, 2] = (vote == y1).sum().float()
+                    tally += wk * torch.softmax(logits, 1).reshape(len(ck), S, classes).double()
+            hit = (tally.argmax(-1) == Y) & mask
+            out[ct, 2] = hit.sum(1).float()

@@ -170,3 +170,32 @@ def test_batched_acc_matrix_equals_per_client_inference_for_module_models():
         for c in range(5):
             k, n, _ = ev.infer_client(m, c, 0)
             assert abs(got[m, c] - (k / n if n else 0.0)) < 1e-6, (m, c)
+
+
+@pytest.mark.parametrize("ens_mode", [1, 2])
+def test_grouped_ensemble_evaluation_equals_per_client_votes(ens_mode):
+    """generic._eval_ensemble_grouped (one batched forward per member) vs per-client ops.ensemble_vote / soft_vote."""
+    from feddrift_b200 import ops
+    from feddrift_b200.sim import DriftSim, generic, make_args
+    sim = DriftSim(make_args(model="cnn", dataset="MNIST", client_num_in_total=5, client_num_per_round=5, sample_num=12,
+                             batch_size=4, comm_round=1, total_train_iteration=2, concept_drift_algo="aue", ensemble_window=3),
+                   device="cpu")
+    for m in range(sim.M):
+        sim.bank.reset_parameters_random(m, torch.Generator().manual_seed(10 + m))
+    sim.data.nsamp[1, 3] = 5
+    sim.data_host.nsamp[1, 3] = 5
+    g = torch.Generator().manual_seed(0)
+    w = torch.rand(5, sim.M, generator=g)
+    w[2, 0] = 0.0
+    out = torch.zeros(5, 4)
+    generic._eval_ensemble_grouped(sim, {"ens_w": w}, 1, list(range(5)), out, ens_mode)
+    for c in range(5):
+        n1 = int(sim.data_host.nsamp[1, c])
+        x1, y1 = sim.data.X[1, c, :n1], sim.data.Y[1, c, :n1]
+        ks = [k for k in range(sim.M) if float(w[c, k]) > 0]
+        with torch.no_grad():
+            if ens_mode == 1:
+                vote = ops.ensemble_vote(torch.stack([sim.bank.forward(k, x1).argmax(-1) for k in ks]), w[c, ks], sim.data.class_num)
+            else:
+                vote = ops.soft_vote(torch.stack([torch.softmax(sim.bank.forward(k, x1), 1) for k in ks]), w[c, ks])
+        assert float(out[c, 2]) == float((vote == y1).sum()), (c, ens_mode)

@@ -1,6 +1,4 @@
 """L1 core runtime: Message / Observer / managers / transports / topology / robustness (CPU)."""
-import json
-
 import numpy as np
 import torch
 

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 import pytest
-import torch
+import torch  # noqa: F401  (imported for its side effects before the facade modules)
 
 from feddrift_b200.experiments.fedavg_cont_ens import add_args, run_facade
 from feddrift_b200.utils.metrics import MetricsSink, set_sink

@@ -158,7 +158,7 @@ def test_splitnn_round_robin():
 
 def test_fedgkt_two_stage_training():
     from feddrift_b200.fl.split import FedML_FedGKT_distributed
-    from feddrift_b200.models.resnet import resnet8_56, resnet56_server, ResNet, Bottleneck
+    from feddrift_b200.models.resnet import resnet8_56, ResNet, Bottleneck
     sink = set_sink(MetricsSink())
     a = SimpleNamespace(comm_round=2, epochs_client=1, epochs_server=1, lr=0.01, wd=1e-4, optimizer="SGD", temperature=3.0,
                         alpha=1.0, whether_training_on_client=1, whether_distill_on_the_server=1)

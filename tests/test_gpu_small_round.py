@@ -1,7 +1,6 @@
 """GPU numerics: the fused persistent round kernel vs the fp32 PyTorch reference of the same op."""
 import copy
 
-import numpy as np
 import pytest
 import torch
 

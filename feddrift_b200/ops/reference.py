@@ -113,12 +113,25 @@ def mlp_eval_matrix(theta, X, Y, nsamp, kind, din, hid, dout):
     return correct, loss
 
 
+def _np_view(st, nb):
+    """Host-side numpy mirrors of the plan tensors (built once per `st`): scalar indexing of torch tensors costs a few
+    µs per access, which dominated the per-pair sampler of the generic executor."""
+    cache = st.get("_np")
+    if cache is None or cache["W_id"] is not st["W"]:
+        cache = st["_np"] = {"W_id": st["W"], "W": st["W"].detach().cpu().double().numpy(),
+                             "nsamp": st["nsamp"].detach().cpu().numpy().astype(np.int64),
+                             "nb": nb.detach().cpu().numpy().astype(np.int64),
+                             "tc": st["train_count"].detach().cpu().numpy() if st.get("train_count") is not None else None}
+    return cache
+
+
 def _pair_plan(st, c, m, t, nb, B):
     """-> (n_cm, sampler) for (client c, model m); sampler(h1, h2) -> (sample index tensor into X[·, c])."""
-    W, nsamp = st["W"], st["nsamp"]
+    v = _np_view(st, nb)
+    Wn, nsn, nbn = v["W"], v["nsamp"], v["nb"]
     mode = st.get("sample_mode", "pool")
     if mode == "index":
-        cnt = int(st["train_count"][m, c])
+        cnt = int(v["tc"][m, c])
         if cnt <= 0:
             return 0.0, None
         lst = st["train_index"][m, c, :cnt].long()
@@ -129,34 +142,35 @@ def _pair_plan(st, c, m, t, nb, B):
             return lst[b * B:min((b + 1) * B, cnt)]
         return float(cnt), sampler
     S = st["X"].shape[2]
-    wcol = W[: t + 1, m, c]
+    wcol = Wn[: t + 1, m, c]
+    nbc, nsc = nbn[: t + 1, c], nsn[: t + 1, c]
     if mode == "time":
-        tot = float(wcol.double().sum())
+        tot = float(wcol.sum())
         if tot <= 0:
             return 0.0, None
-        n_cm = float(nb[: t + 1, c].sum())
-        cum = torch.cumsum(wcol.float(), 0)
+        n_cm = float(nbc.sum())
+        cum = np.cumsum(wcol.astype(np.float32), dtype=np.float32)
 
         def sampler(h1, h2):
             u = np.float32(h1 >> 8) * np.float32(1.0 / 16777216.0) * np.float32(cum[-1])
-            tt = int((cum <= u).sum().clamp(max=t))
-            while int(nb[tt, c]) == 0 and tt > 0:
+            tt = min(int((cum <= u).sum()), t)
+            while int(nbc[tt]) == 0 and tt > 0:
                 tt -= 1
-            b = hash_choice(h2, max(int(nb[tt, c]), 1))
-            lo, hi = b * B, min((b + 1) * B, int(nsamp[tt, c]))
-            return tt * S + torch.arange(lo, hi)
+            b = hash_choice(h2, max(int(nbc[tt]), 1))
+            lo, hi = b * B, min((b + 1) * B, int(nsc[tt]))
+            return torch.from_numpy(np.arange(tt * S + lo, tt * S + hi, dtype=np.int64))
         return n_cm, sampler
-    n_cm = float((wcol.double() * nb[: t + 1, c].double()).sum())
+    n_cm = float((wcol * nbc).sum())
     if n_cm <= 0:
         return 0.0, None
-    pool = [(tt, b) for tt in range(t + 1) if float(wcol[tt]) * int(nb[tt, c]) > 0 for b in range(int(nb[tt, c]))]
+    pool = [(tt, b) for tt in range(t + 1) if wcol[tt] * nbc[tt] > 0 for b in range(int(nbc[tt]))]
     if st.get("n_mode", "batches") == "samples":
-        n_cm = float((wcol.double() * nsamp[: t + 1, c].double()).sum())
+        n_cm = float((wcol * nsc).sum())
 
     def sampler(h1, h2):
         tt, b = pool[hash_choice(h1, len(pool))]
-        lo, hi = b * B, min((b + 1) * B, int(nsamp[tt, c]))
-        return tt * S + torch.arange(lo, hi)
+        lo, hi = b * B, min((b + 1) * B, int(nsc[tt]))
+        return torch.from_numpy(np.arange(tt * S + lo, tt * S + hi, dtype=np.int64))
     return n_cm, sampler
 
 
@@ -243,6 +257,7 @@ def fed_round_small(st: Dict, rounds: int = 1) -> Dict[str, torch.Tensor]:
             best = accm.argmax(dim=0)  # first max == np.argmax tie-break
             W[t].zero_()
             W[t][best, torch.arange(C)] = 1.0
+            st.pop("_np", None)   # the numpy mirror of W is stale
         pick = W[t].argmax(dim=0)
         etr, ete = st.get("eval_train_model"), st.get("eval_test_model")
         for c in range(C):

@@ -103,6 +103,7 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
             best = np.argmax(acc, axis=0)
             st["W"][t].zero_()
             st["W"][t][torch.from_numpy(best), torch.arange(C)] = 1.0
+            st.pop("_np", None)   # the host numpy mirror of W used by the pair planner is stale
             plan["W"] = st["W"].clone()
             sim.algo.absorb_weights(t, st["W"])
         _evaluate(sim, plan, st, r, metrics, ens_mode)

@@ -173,6 +173,10 @@ class DistCommunicationManager(BaseCommunicationManager):
         header, flat = pack_payload(msg.to_string())
         self.ep.q_send.put((int(msg.get_receiver_id()), header, flat))
 
+    def post_local(self, msg: Message) -> None:
+        """Deliver ``msg`` to this rank's own dispatch loop (thread-safe; used by the round watchdog timer)."""
+        self.ep.q_recv.put(msg)
+
     def handle_receive_message(self) -> None:
         while self.is_running:
             msg = self.ep.q_recv.get()

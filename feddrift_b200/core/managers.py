@@ -25,7 +25,7 @@ from __future__ import annotations
 
 import logging
 from abc import abstractmethod
-from typing import Callable, Dict
+from typing import Optional, Callable, Dict
 
 from .comm.base import BaseCommunicationManager
 from .comm.inproc import InProcCommunicationManager, World
@@ -91,10 +91,70 @@ class _Manager(Observer):
     def register_message_receive_handler(self, msg_type, handler_callback_func) -> None:
         self.message_handler_dict[msg_type] = handler_callback_func
 
+    def post_local(self, message: Message) -> bool:
+        """Queue a message for this manager's own handlers (timers, watchdogs); False if the transport cannot."""
+        fn = getattr(self.com_manager, "post_local", None)
+        if fn is None:
+            return False
+        fn(message)
+        return True
+
     def finish(self) -> None:
         logging.info("__finish %s rank %d", self.node_type, self.rank)
         self.finished = True
         self.com_manager.stop_receive_message()
+
+
+class RoundWatchdog:
+    """Straggler / failure tolerance for synchronous FL rounds (the reference has none: a missing client blocks the round
+    forever, ``check_whether_all_receive``).  The server arms it when it broadcasts round r; if the round is still open
+    after ``timeout_s`` (threaded transports: a ``threading.Timer`` posts a local ``MSG_TYPE_ROUND_TIMEOUT``; the
+    deterministic INPROC event loop: as soon as the fabric is quiescent, i.e. nothing more can arrive) and at least
+    ``min_workers`` uploads are in, the round is closed with the uploads that arrived — missing workers contribute
+    weight 0 and receive the next broadcast like everybody else; uploads tagged with an older round are dropped.
+
+    Enabled by ``args.round_timeout_s > 0`` (``args.min_workers_per_round`` defaults to 1)."""
+
+    MSG_TYPE_ROUND_TIMEOUT = 9
+
+    def __init__(self, manager: "_Manager", timeout_s: float, min_workers: int = 1):
+        self.manager, self.timeout_s, self.min_workers = manager, float(timeout_s or 0.0), max(int(min_workers or 1), 1)
+        self.round_open: Optional[int] = None
+        self._timer = None
+        self.timeouts = 0
+
+    @property
+    def enabled(self) -> bool:
+        return self.timeout_s > 0
+
+    def arm(self, round_idx: int) -> None:
+        self.cancel()
+        self.round_open = round_idx
+        if not self.enabled or self.manager.backend in ("INPROC", "STREAM"):
+            return   # INPROC: the quiescence hook plays the timer's role
+        import threading
+        self._timer = threading.Timer(self.timeout_s, self._fire, args=(round_idx,))
+        self._timer.daemon = True
+        self._timer.start()
+
+    def _fire(self, round_idx: int) -> None:
+        msg = Message(self.MSG_TYPE_ROUND_TIMEOUT, self.manager.rank, self.manager.rank)
+        msg.add_params("round_idx", round_idx)
+        self.manager.post_local(msg)
+
+    def fire_if_open(self) -> bool:
+        """INPROC quiescence hook: post the timeout for the open round (once)."""
+        if not self.enabled or self.round_open is None:
+            return False
+        r, self.round_open = self.round_open, None
+        self._fire(r)
+        return True
+
+    def cancel(self) -> None:
+        if self._timer is not None:
+            self._timer.cancel()
+            self._timer = None
+        self.round_open = None
 
 
 class ServerManager(_Manager):

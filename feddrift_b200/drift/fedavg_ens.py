@@ -28,7 +28,7 @@ from torch import nn
 
 from .. import ops
 from ..core.comm.inproc import World
-from ..core.managers import ClientManager, ServerManager
+from ..core.managers import RoundWatchdog, ClientManager, ServerManager
 from ..core.message import DeviceRef, Message
 from ..data import changepoints as cpmod
 from ..data.drift import DEFAULT_DELTAS, DriftData
@@ -843,6 +843,12 @@ class FedAvgEnsServerManager(ServerManager):
         # logical workers may be PACKED onto fewer physical ranks (worker w lives on rank 1 + w % (size-1));
         # the reference needs one MPI rank per worker (FedAvgEnsAPI.py:86-92)
         self.worker_num = aggregator.worker_num
+        # straggler tolerance (off unless args.round_timeout_s > 0): close a round with the uploads that arrived
+        self.watchdog = RoundWatchdog(self, getattr(args, "round_timeout_s", 0.0), getattr(args, "min_workers_per_round", 1))
+        self.dropped_uploads = 0
+
+    def on_quiescent(self) -> bool:   # INPROC event loop: nothing more can arrive → treat as the round timeout
+        return self.watchdog.fire_if_open()
 
     def _rank_of(self, worker: int) -> int:
         return 1 + worker % (self.size - 1)
@@ -852,18 +858,47 @@ class FedAvgEnsServerManager(ServerManager):
         params, extra = self.aggregator.get_global_model_params(), self.aggregator.extra_info(self.round_idx)
         for w in range(self.worker_num):
             self._send(MyMessage.MSG_TYPE_S2C_INIT_CONFIG, self._rank_of(w), params, idx[w], extra, w)
+        self.watchdog.arm(self.round_idx)
 
     def register_message_receive_handlers(self):
         self.register_message_receive_handler(MyMessage.MSG_TYPE_C2S_SEND_MODEL_TO_SERVER,
                                               self.handle_message_receive_model_from_client)
+        self.register_message_receive_handler(RoundWatchdog.MSG_TYPE_ROUND_TIMEOUT, self.handle_round_timeout)
+
+    def handle_round_timeout(self, msg_params):
+        """The watchdog fired: if round ``round_idx`` is still open and enough uploads arrived, close it without the
+        stragglers (their weight is 0 in this round's aggregation)."""
+        if int(msg_params.get("round_idx")) != self.round_idx or self.finished:
+            return
+        flags = self.aggregator.flag_client_model_uploaded_dict
+        got = sum(1 for w in range(self.worker_num) if flags[w])
+        if got < self.watchdog.min_workers:
+            self.watchdog.arm(self.round_idx)      # keep waiting (threaded transports re-arm the timer)
+            return
+        missing = [w for w in range(self.worker_num) if not flags[w]]
+        logging.warning("round %d: closing without workers %s (timeout)", self.round_idx, missing)
+        self.watchdog.timeouts += 1
+        self.args.watchdog_timeouts = getattr(self.args, "watchdog_timeouts", 0) + 1   # visible to the experiment driver
+        for w in missing:
+            self.aggregator.add_local_trained_result(w, {m: (None, 0) for m in range(self.aggregator.bank.num_models)})
+        self.aggregator.check_whether_all_receive()
+        self._complete_round()
 
     def handle_message_receive_model_from_client(self, msg_params):
         sender = msg_params.get(MyMessage.MSG_ARG_KEY_SENDER)
         worker = msg_params.get("worker_id")
         worker = sender - 1 if worker is None else int(worker)
+        r = msg_params.get("round_idx")
+        if r is not None and int(r) != self.round_idx:   # a straggler's upload for a round that was already closed
+            self.dropped_uploads += 1
+            return
         self.aggregator.add_local_trained_result(worker, msg_params.get(MyMessage.MSG_ARG_KEY_MODEL_AND_NUM_SAMPLES))
         if not self.aggregator.check_whether_all_receive():
             return
+        self._complete_round()
+
+    def _complete_round(self):
+        self.watchdog.cancel()
         params = self.aggregator.aggregate(self.round_idx)
         self.aggregator.test_on_all_clients(self.round_idx)
         self.round_idx += 1
@@ -875,6 +910,7 @@ class FedAvgEnsServerManager(ServerManager):
         extra = self.aggregator.extra_info(self.round_idx)
         for w in range(self.worker_num):
             self._send(MyMessage.MSG_TYPE_S2C_SYNC_MODEL_TO_CLIENT, self._rank_of(w), params, idx[w], extra, w)
+        self.watchdog.arm(self.round_idx)
 
     def _send(self, mtype, rid, params, client_index, extra, worker=None):
         msg = Message(mtype, self.get_sender_id(), rid)
@@ -937,11 +973,19 @@ class FedAvgEnsClientManager(ClientManager):
         msg.add_params(MyMessage.MSG_ARG_KEY_MODEL_AND_NUM_SAMPLES, weights_and_num_samples)
         if worker is not None:
             msg.add_params("worker_id", worker)
+            msg.add_params("round_idx", self.rounds.get(worker, self.round_idx))
         self.send_message(msg)
 
     def _train(self, w=None):
         w = next(iter(self.trainers)) if w is None else w
-        self.send_model_to_server(0, self.trainers[w].train(), w)
+        # fault injection for tests / chaos runs: args.fault_drop = {round: [worker, ...]} — the worker trains but its
+        # upload is lost (a crashed or partitioned client)
+        drop = getattr(self.args, "fault_drop", None) or {}
+        result = self.trainers[w].train()
+        if w in drop.get(self.rounds.get(w, self.round_idx), ()):
+            logging.warning("fault injection: dropping the upload of worker %d in round %d", w, self.rounds.get(w, 0))
+            return
+        self.send_model_to_server(0, result, w)
 
 
 # ====================================================================================== API entry points

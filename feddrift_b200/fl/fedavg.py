@@ -13,6 +13,7 @@ averaging (the reference computes the noised tensor but sums the un-noised one â
 from __future__ import annotations
 
 import copy
+import logging
 from typing import Dict, Optional
 
 import numpy as np
@@ -20,7 +21,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from ..core.managers import ClientManager, ServerManager
+from ..core.managers import ClientManager, RoundWatchdog, ServerManager
 from ..core.message import Message
 from ..core.robustness import RobustAggregator
 from ..drift.fedavg_ens import _BaseAggregator
@@ -164,23 +165,56 @@ class FedAvgServerManager(ServerManager):
     def __init__(self, args, aggregator, comm=None, rank=0, size=0, backend="MPI"):
         super().__init__(args, comm, rank, size, backend)
         self.aggregator, self.round_num, self.round_idx = aggregator, args.comm_round, 0
+        # straggler tolerance (core.managers.RoundWatchdog; off unless args.round_timeout_s > 0) â€” mobile devices drop out
+        self.watchdog = RoundWatchdog(self, getattr(args, "round_timeout_s", 0.0), getattr(args, "min_workers_per_round", 1))
+        self.dropped_uploads = 0
+
+    def on_quiescent(self) -> bool:
+        return self.watchdog.fire_if_open()
 
     def send_init_msg(self):
         idx = self.aggregator.client_sampling(self.round_idx, self.args.client_num_in_total, self.args.client_num_per_round)
         params = self.aggregator.get_global_model_params()
         for pid in range(1, self.size):
             self.send_message_init_config(pid, params, idx[pid - 1])
+        self.watchdog.arm(self.round_idx)
 
     def register_message_receive_handlers(self):
         self.register_message_receive_handler(MyMessage.MSG_TYPE_C2S_SEND_MODEL_TO_SERVER,
                                               self.handle_message_receive_model_from_client)
+        self.register_message_receive_handler(RoundWatchdog.MSG_TYPE_ROUND_TIMEOUT, self.handle_round_timeout)
+
+    def handle_round_timeout(self, msg_params):
+        if int(msg_params.get("round_idx")) != self.round_idx or self.finished:
+            return
+        flags = self.aggregator.flag_client_model_uploaded_dict
+        workers = range(self.size - 1)
+        if sum(1 for w in workers if flags[w]) < self.watchdog.min_workers:
+            self.watchdog.arm(self.round_idx)
+            return
+        missing = [w for w in workers if not flags[w]]
+        logging.warning("round %d: closing without workers %s (timeout)", self.round_idx, missing)
+        self.watchdog.timeouts += 1
+        self.args.watchdog_timeouts = getattr(self.args, "watchdog_timeouts", 0) + 1
+        for w in missing:
+            self.aggregator.add_local_trained_result(w, None, 0)
+        self.aggregator.check_whether_all_receive()
+        self._complete_round()
 
     def handle_message_receive_model_from_client(self, msg_params):
         sender = int(msg_params.get(MyMessage.MSG_ARG_KEY_SENDER))
+        r = msg_params.get("round_idx")
+        if r is not None and int(r) != self.round_idx:   # upload of an already closed round
+            self.dropped_uploads += 1
+            return
         self.aggregator.add_local_trained_result(sender - 1, msg_params.get(MyMessage.MSG_ARG_KEY_MODEL_PARAMS),
                                                  msg_params.get(MyMessage.MSG_ARG_KEY_NUM_SAMPLES))
         if not self.aggregator.check_whether_all_receive():
             return
+        self._complete_round()
+
+    def _complete_round(self):
+        self.watchdog.cancel()
         params = self.aggregator.aggregate(self.round_idx)
         self.aggregator.test_on_all_clients(self.round_idx)
         self.round_idx += 1
@@ -191,6 +225,7 @@ class FedAvgServerManager(ServerManager):
         idx = self.aggregator.client_sampling(self.round_idx, self.args.client_num_in_total, self.args.client_num_per_round)
         for rid in range(1, self.size):
             self.send_message_sync_model_to_client(rid, params, idx[rid - 1])
+        self.watchdog.arm(self.round_idx)
 
     def _send(self, mtype, rid, params, client_index):
         msg = Message(mtype, self.get_sender_id(), rid)
@@ -240,10 +275,15 @@ class FedAvgClientManager(ClientManager):
         msg = Message(MyMessage.MSG_TYPE_C2S_SEND_MODEL_TO_SERVER, self.get_sender_id(), receive_id)
         msg.add_params(MyMessage.MSG_ARG_KEY_MODEL_PARAMS, weights)
         msg.add_params(MyMessage.MSG_ARG_KEY_NUM_SAMPLES, local_sample_num)
+        msg.add_params("round_idx", self.round_idx)
         self.send_message(msg)
 
     def _train(self):
         w, n = self.trainer.train()
+        drop = getattr(self.args, "fault_drop", None) or {}
+        if (self.rank - 1) in drop.get(self.round_idx, ()):   # fault injection: this worker's upload is lost
+            logging.warning("fault injection: dropping the upload of worker %d in round %d", self.rank - 1, self.round_idx)
+            return
         self.send_model_to_server(0, w, n)
 
 

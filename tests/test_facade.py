@@ -71,3 +71,43 @@ if int(os.environ["RANK"]) == 0:
     line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1]
     h = json.loads(line[len("RESULT "):])
     assert h["iteration"] == 1 and 0 <= h["test_acc"] <= 1
+
+
+def test_round_watchdog_closes_rounds_without_a_crashed_worker():
+    """Failure tolerance (the reference blocks forever on a missing upload): with ``round_timeout_s`` set, a worker whose
+    upload is lost (fault injection) does not stall the experiment — the round closes with the 9 uploads that arrived,
+    the straggler rejoins at the next broadcast, every round is still evaluated."""
+    sink = set_sink(MetricsSink())
+    a = _args("--concept_drift_algo", "softcluster", "--concept_drift_algo_arg", "H_A_C_1_10_0")
+    a.round_timeout_s, a.min_workers_per_round, a.fault_drop = 5.0, 5, {1: [3], 2: [0, 7]}
+    out = run_facade(a, sink)
+    assert len(out["history"]) == 3 and len(sink.series("Train/Acc")) == 9
+    assert a.watchdog_timeouts == 6            # rounds 1 and 2 of each of the 3 time steps
+    # without the watchdog the same fault leaves the round open: the event loop drains and the experiment stops early
+    sink2 = set_sink(MetricsSink())
+    b = _args("--concept_drift_algo", "softcluster", "--concept_drift_algo_arg", "H_A_C_1_10_0")
+    b.fault_drop = {1: [3]}
+    run_facade(b, sink2)
+    assert len(sink2.series("Train/Acc")) < 9
+
+
+def test_round_watchdog_timer_posts_a_local_timeout_message():
+    import time
+    from feddrift_b200.core.managers import RoundWatchdog
+
+    class FakeManager:
+        backend, rank, posted = "DIST", 0, []
+
+        def post_local(self, msg):
+            self.posted.append(msg)
+            return True
+
+    m = FakeManager()
+    wd = RoundWatchdog(m, timeout_s=0.05, min_workers=2)
+    wd.arm(4)
+    time.sleep(0.3)
+    assert len(m.posted) == 1 and m.posted[0].get("round_idx") == 4 and m.posted[0].get_type() == RoundWatchdog.MSG_TYPE_ROUND_TIMEOUT
+    wd.arm(5)
+    wd.cancel()
+    time.sleep(0.15)
+    assert len(m.posted) == 1

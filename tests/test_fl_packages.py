@@ -85,6 +85,16 @@ def test_distributed_fedavg_inproc(robust):
     assert torch.isfinite(srv.aggregator.bank.theta).all()
 
 
+def test_distributed_fedavg_survives_a_lost_upload_with_the_round_watchdog():
+    from feddrift_b200.fl.fedavg import FedML_FedAvg_distributed
+    sink = set_sink(MetricsSink())
+    ds, _ = _dataset()
+    a = _args(comm_round=3, epochs=2, round_timeout_s=5.0, min_workers_per_round=2, fault_drop={1: [2]})
+    comm, pid, size = FedML_init("INPROC", 5)
+    srv = FedML_FedAvg_distributed(pid, size, "cpu", comm, create_model("fnn", 2, 2), ds[0], ds[2], ds[3], ds[4], ds[5], ds[6], a)
+    assert srv.round_idx == 3 and srv.watchdog.timeouts == 1 and len(sink.series("Test/Acc")) == 3
+
+
 def test_weak_dp_noise_is_standard_normal_and_deterministic():
     from feddrift_b200.ops import reference as ref
     z = ref.gauss_hash(7, 4, 50000)

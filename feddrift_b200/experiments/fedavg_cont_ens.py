@@ -50,6 +50,10 @@ def add_args(parser: argparse.ArgumentParser) -> argparse.ArgumentParser:
     a("--resume", type=int, default=0); a("--metrics_file", type=str, default=None)
     a("--use_wandb", type=int, default=0); a("--strict_ref", type=int, default=0)
     a("--rounds_per_launch", type=int, default=0)
+    # façade extras: worker packing, zero-copy device payloads, straggler tolerance (core.managers.RoundWatchdog)
+    a("--pack_workers", type=int, default=0); a("--zero_copy", type=int, default=0)
+    a("--round_timeout_s", type=float, default=0.0, help="> 0: close a round without workers whose upload did not arrive in time")
+    a("--min_workers_per_round", type=int, default=1)
     return parser
 
 

@@ -22,6 +22,11 @@ static inline int persistent_grid(long long work_items, int threads) {
     return (int)max(1LL, min(need, cap));
 }
 
+// Dynamic shared memory for an n-float weight table, padded by one 16-byte vector: the compiler unrolls the weight loops
+// with LDS.64/96/128 whose tail lanes may read (never use) up to 3 floats past the table — compute-sanitizer memcheck
+// flags that as an out-of-bounds shared read when the allocation is exactly n floats.
+static inline size_t smem_floats(int n) { return ((size_t)n + 4) * sizeof(float); }
+
 // ------------------------------------------------------------------------------------------------ K1
 // theta[m, :] = Σ_c (n[c,m]/tot[m]) · cp[c, m, :]   for every m with tot[m] > 0.
 // server_opt != 0 fuses the FedOpt step: g = theta_old - avg, then sgd(+momentum)/adam/adagrad/yogi on theta.
@@ -153,7 +158,7 @@ int cluster_aggregate_launch(float* theta, int theta_stride, const float* cp, co
     const int gx = persistent_grid((P + 3) / 4, threads);
     dim3 grid(max(1, gx / max(1, min(M, 8))), min(M, 65535));
     if (M * (long long)gx <= 148 * 8) grid.x = gx;
-    cluster_aggregate_kernel<<<grid, threads, C * sizeof(float), stream>>>(theta, theta_stride, cp, n, C, M, P, tot_out, so);
+    cluster_aggregate_kernel<<<grid, threads, smem_floats(C), stream>>>(theta, theta_stride, cp, n, C, M, P, tot_out, so);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(256) weighted_average_kernel(const float* __re
 
 int weighted_average_launch(const float* rows, const float* w, int n, long long P, float* out, cudaStream_t stream) {
     const int threads = 256;
-    weighted_average_kernel<<<persistent_grid(P, threads), threads, n * sizeof(float), stream>>>(rows, w, n, P, out);
+    weighted_average_kernel<<<persistent_grid(P, threads), threads, smem_floats(n), stream>>>(rows, w, n, P, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(256) gossip_mix_kernel(const float* __restrict
 }
 int gossip_mix_launch(const float* X, const float* Wm, int n, long long P, float* out, cudaStream_t stream) {
     dim3 grid(max(1, persistent_grid(P, 256) / max(1, min(n, 16))), n);
-    gossip_mix_kernel<<<grid, 256, n * sizeof(float), stream>>>(X, Wm, n, P, out);
+    gossip_mix_kernel<<<grid, 256, smem_floats(n), stream>>>(X, Wm, n, P, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -19,6 +19,7 @@ failed capture falls back to eager execution of the same ops.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -136,9 +137,8 @@ def _peer_aggregate(sim, world, rank):
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
     """Opt-in (``FDB_NHWC=1``) channels_last activations for conv nets.  With NCHW activations 28 % of a ResNet-18 step's
     GPU time is cuDNN's nchwToNhwc / nhwcToNchw conversion kernels (tools/profile_generic.py), but NHWC kernels need
-    16-byte aligned weight pointers and the conv weights are 4-byte aligned views into the flat parameter row (a first
-    attempt faulted with "misaligned address"): the arena needs 16-byte aligned tensor offsets first."""
-    import os
+    16-byte aligned weight pointers (the arena now aligns every big tensor, models/utils.py::flat_spec); the first
+    end-to-end attempt with the aligned arena did not finish within its GPU time box, so this stays opt-in."""
     if os.environ.get("FDB_NHWC") == "1" and x.is_cuda and x.dim() == 4:
         return x.contiguous(memory_format=torch.channels_last)
     return x
@@ -251,7 +251,6 @@ def _stream_slots(sim):
     """Side streams for concurrent pair execution (CUDA + graphed module path only).  A federated local step is ~60
     small dependent kernels, i.e. latency-bound even inside a CUDA graph; replaying K pairs' graphs on K streams lets the
     SMs overlap them.  ``FDB_GRAPH_STREAMS`` (default 8; 1 disables) sets K."""
-    import os
     if sim.device.type != "cuda" or sim.bank.mlp is not None or os.environ.get("FDB_NO_GRAPHS") == "1":
         return []
     k = int(os.environ.get("FDB_GRAPH_STREAMS", "8"))
@@ -275,7 +274,6 @@ def _join_slots(sim, slots):
 
 def _graphed_step(sim, batch_shape, use_adam, lr, wd, slot: int = 0, steps: int = 1, indexed: bool = False):
     """Cached ``_GraphedStep`` for this (batch shape, optimizer, lr) or None when graphs are unavailable."""
-    import os
     if sim.device.type != "cuda" or sim.bank.mlp is not None or os.environ.get("FDB_NO_GRAPHS") == "1" \
             or getattr(sim, "_graphs_broken", False):
         return None
@@ -309,7 +307,6 @@ def _local_steps(sim, c, m, xy, sampler, seed, rnd, E, use_adam, lr, wd, feat_ma
         idxs.append(sampler(h1, mix32(h1 ^ 0x68E31DA4)))
     # one H2D + one gather for all E minibatches of this pair when they have equal length (the common case)
     same = all(i.numel() == idxs[0].numel() for i in idxs)
-    import os
     if same and feat_mask is None and mlp is None and sim.device.type == "cuda" and os.environ.get("FDB_NO_PAIR_GRAPH") != "1":
         # per-pair graph: the minibatch gathers are graph nodes reading the resident dataset through global sample ids
         S_, C_ = sim.data.X.shape[2], sim.C

@@ -97,7 +97,7 @@ def main(args) -> None:
                               "(pip install of /root/reference fails: no setup.py/pyproject.toml; see DESIGN.md)"}))
             return
     K, W = int(args.steps), max(int(args.warmup), 1)
-    budget_s = float(os.environ.get("FDB_REF_MAX_SECONDS", "420"))
+    budget_s = float(os.environ.get("FDB_REF_MAX_SECONDS", "240"))
     per_round_est = 0.3 * CLIENTS + 1.0  # ≥ 0.3 s sleep per ingested upload (com_manager.py:71-79)
     K_eff = K
     if (W + K) * per_round_est > budget_s:

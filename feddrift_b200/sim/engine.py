@@ -314,7 +314,11 @@ class DriftSim:
                   use_graph: bool = False) -> Dict:
         """ONE end-to-end FL round through the public API: (optional) host→device copy of the round's inputs
         from pinned memory, the fused round kernel, device→host copy of the per-client metrics, host reduction.
-        Synchronises (the caller gets real numbers back)."""
+        Synchronises (the caller gets real numbers back).
+
+        ``use_graph=True`` replays a captured graph that holds the ADDRESSES of ``host_inputs``' pinned tensors: write each
+        round's new data into the same ``host_inputs`` buffers (``make_host_round_inputs`` allocates them once per time
+        step); passing a different dict rebuilds the graph."""
         if use_graph and host_inputs is not None and self.device.type == "cuda":
             gr = getattr(self, "_graph", None)
             if gr is None or gr[1] is not host_inputs:

@@ -1,0 +1,187 @@
+"""Parity of the FedDrift brain against the ACTUAL reference implementation.
+
+The unmodified reference package (``baseline/_ref``, installed from ``/root/reference`` by ``baseline/install_reference.py``)
+is imported side by side with ``feddrift_b200`` and both ``SoftClusterState`` implementations are driven through the same
+scripted drifting federation: same data tensors, same model parameters, same "training" (the harness writes the ideal
+classifier of a cluster's majority concept into the cluster's model on both sides).  After every time step the complete
+weight history ``W[t', m, c]``, the isolation marks and every model's parameters must be identical — this checks drift
+detection, LRU slot allocation with parameter copy, the marking window, the A/B distances, complete/average linkage with
+the δ' cut, merges and the identical re-initialisation, through the reference's own ``cluster_hierarchical`` /
+``cluster`` code paths (``FedAvgEnsDataLoader.py:640-978``).
+
+Skipped when the reference tree is not available.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _reference_module():
+    if not os.path.isdir(os.path.join(REF, "fedml_api")):
+        if not os.path.isdir("/root/reference/fedml_api"):
+            pytest.skip("reference tree not available")
+        sys.path.insert(0, ROOT)
+        from baseline import install_reference
+        if install_reference.main() != 0 or not os.path.isdir(os.path.join(REF, "fedml_api")):
+            pytest.skip("reference could not be installed")
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    os.environ.setdefault("WANDB_SILENT", "true")
+    for p in (os.path.join(ROOT, "baseline", "shims"), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    try:
+        import wandb
+        if wandb.run is None:
+            wandb.init(mode="disabled")
+        from fedml_api.distributed.fedavg_ens import FedAvgEnsDataLoader as ref_mod
+    except Exception as exc:  # noqa: BLE001
+        pytest.skip(f"reference not importable here: {exc!r}")
+    return ref_mod
+
+
+C, T, S, M = 5, 5, 16, 8
+# concept k: label = [x0 > 0.5] XOR flip_k on half-plane pairs; 0/1 are opposites, 2/3 use the other axis
+CONCEPT_W = {0: ([8.0, 0.0], -4.0), 1: ([-8.0, 0.0], 4.0), 2: ([0.0, 8.0], -4.0), 3: ([0.0, -8.0], 4.0)}
+
+
+def _label(x, k):
+    w, b = CONCEPT_W[k]
+    return ((x @ torch.tensor(w)) + b > 0).long()
+
+
+def _ideal_state_dict(k):
+    w, b = CONCEPT_W[k]
+    # 2-class logistic regression: class-1 logit = w·x + b, class-0 logit = 0
+    return {"linear.weight": torch.tensor([[0.0, 0.0], w]), "linear.bias": torch.tensor([0.0, b])}
+
+
+class _LR(nn.Module):
+    """Plain linear 2-class model (no sigmoid) used on BOTH sides."""
+
+    def __init__(self):
+        super().__init__()
+        self.linear = nn.Linear(2, 2)
+
+    def forward(self, x):
+        return self.linear(x)
+
+
+def _schedule(seed):
+    """[T+1, C] concept ids with staggered drifts (some clients drift to the same new concept at different times)."""
+    rng = np.random.RandomState(seed)
+    cp = np.zeros((T + 1, C), dtype=np.int64)
+    for c in range(C):
+        k, t_change = 0, rng.randint(1, T)
+        for t in range(T + 1):
+            if t == t_change:
+                k = rng.choice([1, 2, 3])
+            cp[t, c] = k
+        if rng.rand() < 0.4:   # a second drift back or onwards
+            t2 = min(T, t_change + rng.randint(1, 3))
+            cp[t2:, c] = rng.choice([0, 1, 2, 3])
+    return cp
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", ["H_A_C", "H_B_D"])
+def test_hierarchical_feddrift_matches_reference_implementation(seed, variant):
+    ref_mod = _reference_module()
+    from feddrift_b200.data.drift import DriftData
+    from feddrift_b200.drift.evaluator import Evaluator
+    from feddrift_b200.drift.softcluster import SoftClusterState
+    from feddrift_b200.models import utils as mutils
+    from feddrift_b200.parallel.arena import ModelBank
+
+    dist_kind, link = variant.split("_")[1], variant.split("_")[2]
+    cp = _schedule(seed)
+    g = torch.Generator().manual_seed(100 + seed)
+    X = torch.rand(T + 1, C, S, 2, generator=g)
+    X = torch.where((X - 0.5).abs() < 0.06, X + 0.12 * torch.sign(X - 0.5 + 1e-9), X)   # keep a margin around the boundaries
+    Y = torch.stack([torch.stack([_label(X[t, c], int(cp[t, c])) for c in range(C)]) for t in range(T + 1)])
+    nsamp = torch.full((T + 1, C), S, dtype=torch.int32)
+    data = DriftData("parity", X, Y, nsamp, cp, 2)
+
+    # ---- ours
+    torch.manual_seed(7)
+    template = _LR()
+    bank = ModelBank(template, M, "cpu")
+    ev = Evaluator(bank, data, batch_size=S)
+    mine = SoftClusterState(C, M, "H", h_delta=0.15, h_deltap=0.15, h_w=1, h_distance=dist_kind, h_cluster=link)
+    mine.cluster_init()
+    # ---- reference
+    init_sd = {k: v.clone() for k, v in bank.state_dict(0).items()}
+    models = [_LR() for _ in range(M)]
+    for mod in models:
+        mod.load_state_dict(init_sd)
+    ref_mod.reinitialize = lambda model: model.load_state_dict(init_sd)      # "every re-init is identical" on both sides
+    all_data = [[[(X[t, c], Y[t, c])] for t in range(T + 1)] for c in range(C)]   # [client][iter] -> list of batches
+    theirs = ref_mod.SoftClusterState(C, M, "H", h_delta=0.15, h_deltap=0.15, h_w=1, h_distance=dist_kind, h_cluster=link)
+    theirs.cluster_init()
+
+    def train(t):
+        """Emulated local training + aggregation: every model used at t becomes the ideal classifier of the majority
+        concept of its clients (identical on both sides)."""
+        W_t = mine.W[t]
+        for m in range(M):
+            cs = np.nonzero(W_t[m] > 0)[0]
+            if len(cs) == 0:
+                continue
+            k = int(np.bincount(cp[t, cs]).argmax())
+            sd = _ideal_state_dict(k)
+            bank.load_state_dict(m, sd)
+            models[m].load_state_dict(sd)
+
+    def check(t):
+        for tt in range(t + 1):
+            assert np.array_equal(mine.W[tt], theirs.train_data_weights[tt]), (seed, variant, t, tt, mine.W[tt], theirs.train_data_weights[tt])
+        assert {c: tuple(v) for c, v in mine.h_marked.items()} == {c: tuple(v) for c, v in theirs.h_marked.items()}
+        for m in range(M):
+            a = bank.theta[m]
+            b = mutils.flatten_state_dict(models[m].state_dict())
+            assert torch.allclose(a, b, atol=1e-6), (seed, variant, t, m)
+
+    train(0)
+    acc0 = ev.acc_matrix([0], 0)[0]
+    for c in range(C):   # the aggregator records the t = 0 accuracies for the drift detector (SoftCluster.py:107-116)
+        mine.set_acc(c, float(acc0[c]))
+        theirs.set_acc(c, float(acc0[c]))
+    check(0)
+    for t in range(1, T + 1):
+        mine.cluster_hierarchical(t, bank, ev)
+        theirs.cluster_hierarchical(t, models, all_data, torch.device("cpu"))
+        check(t)
+        train(t)
+    # the scenario must actually exercise the algorithm: new models were spawned, and usually some were merged
+    assert max(int((mine.W[t].sum(1) > 0).sum()) for t in range(T + 1)) >= 2
+
+
+@pytest.mark.parametrize("alg", ["hard", "softmax_2", "mmacc_10"])
+def test_matrix_driven_clustering_matches_reference_implementation(alg):
+    """`cluster()` on scripted accuracy matrices: IFCA hard, softmax_α and FedDrift-Eager (mmacc_δ with LRU slots)."""
+    ref_mod = _reference_module()
+    from feddrift_b200.drift.softcluster import SoftClusterState
+    kw = dict(cluster_alg=alg.split("_")[0] if alg.startswith("mmacc") else alg)
+    if alg.startswith("softmax"):
+        kw = dict(cluster_alg=alg, softmax_alpha=2)
+    if alg.startswith("mmacc"):
+        kw = dict(cluster_alg=alg, mmacc_delta=0.10)
+    mine, theirs = SoftClusterState(6, 4, **kw), ref_mod.SoftClusterState(6, 4, **kw)
+    mine.cluster_init()
+    theirs.cluster_init()
+    rng = np.random.RandomState(3)
+    for c in range(6):
+        mine.set_acc(c, 0.9)
+        theirs.set_acc(c, 0.9)
+    for t in range(1, 5):
+        acc = rng.rand(4, 6) * 0.3 + 0.6
+        acc[:, rng.randint(0, 6)] -= 0.35      # one client's data drifted: every model is bad on it
+        mine.cluster(acc.copy(), t, 0)
+        theirs.cluster(acc.copy(), t, 0)
+        assert np.allclose(mine.W[t], theirs.train_data_weights[t]), (alg, t)

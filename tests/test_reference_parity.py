@@ -185,3 +185,150 @@ def test_matrix_driven_clustering_matches_reference_implementation(alg):
         mine.cluster(acc.copy(), t, 0)
         theirs.cluster(acc.copy(), t, 0)
         assert np.allclose(mine.W[t], theirs.train_data_weights[t]), (alg, t)
+
+
+def test_ada_state_matches_reference_implementation():
+    """Adaptive-FedAvg server learning-rate schedule (EMA mean / variance / ratio) on the same parameter trajectory."""
+    ref_mod = _reference_module()
+    from feddrift_b200.drift.states import AdaState
+    mine, theirs = AdaState(init_lr=0.05), ref_mod.AdaState(init_lr=0.05)
+    g = torch.Generator().manual_seed(0)
+    theta = torch.randn(5000, generator=g)
+    for t in range(12):
+        theta = theta + 0.3 * torch.randn(5000, generator=g) * (3.0 if t in (5, 9) else 1.0)   # two "drifts"
+        mine.update(theta.clone(), t)
+        theirs.update(theta.double().numpy(), t)
+        assert abs(mine.current_lr() - float(theirs.current_lr())) <= 1e-5 * float(theirs.current_lr()) + 1e-9, t
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_driftsurf_state_machine_matches_reference_implementation(seed):
+    """DriftSurf stable/reactive transitions, training windows, model switch — same scripted accuracy stream."""
+    ref_mod = _reference_module()
+    from feddrift_b200.drift.states import DriftSurfState
+    mine, theirs = DriftSurfState(delta=0.1, r=3, wl=4), ref_mod.DriftSurfState(delta=0.1, r=3, wl=4)
+    rng = np.random.RandomState(seed)
+    cur = {}
+    mine._score = lambda key, *a, **k: cur[key]
+    theirs._score = lambda key, *a, **k: cur[key]
+    for it in range(1, 16):
+        base = 0.9 - (0.3 if rng.rand() < 0.3 else 0.0)          # occasional accuracy collapse of the predictive model
+        cur.update(pred=base + 0.02 * rng.randn(), stab=0.88 + 0.05 * rng.randn(), reac=0.7 + 0.25 * rng.rand())
+        mine.run_ds_algo(None, None, it)
+        theirs.run_ds_algo(None, "cpu", it)
+        assert mine.state == theirs.state and mine.model_key == theirs.model_key, it
+        assert mine.get_train_keys() == theirs.get_train_keys(), it
+        for key in ("pred", "stab", "reac"):
+            assert (mine.train_data_dict[key] or []) == (theirs.train_data_dict[key] or []), (it, key)
+        assert abs(mine.acc_best - theirs.acc_best) < 1e-12
+        assert mine.reac_ctr == theirs.reac_ctr
+
+
+def test_change_point_matrices_equal_the_reference_data_files():
+    """Every named change-point matrix (A–F, W–Z, R0–R9) equals ``data/changepoints/<name>.cp`` of the reference."""
+    cp_dir = "/root/reference/data/changepoints"
+    if not os.path.isdir(cp_dir):
+        cp_dir = os.path.join(REF, "data", "changepoints")
+    if not os.path.isdir(cp_dir):
+        pytest.skip("reference data files not available")
+    from feddrift_b200.data import changepoints
+    names = sorted(f[:-3] for f in os.listdir(cp_dir) if f.endswith(".cp"))
+    assert len(names) >= 20
+    for name in names:
+        want = np.loadtxt(os.path.join(cp_dir, name + ".cp"), dtype=np.int64)
+        got = changepoints.named(name)
+        assert got.shape == want.shape and np.array_equal(got, want), name
+
+
+def test_retrain_window_selector_matches_reference_csv_loader(tmp_path):
+    """`select_iterations` (all / win-k / sel-… / clientsel-… / weight-linear|exp) vs the iterations the reference's
+    ``common/retrain.py`` actually reads, observed by giving every (client, iteration) CSV a unique marker row."""
+    _reference_module()
+    import pandas as pd
+    if not hasattr(pd.DataFrame, "append"):   # pandas ≥ 2 removed it; the reference arm restores it the same way
+        monkey = pytest.MonkeyPatch()
+        monkey.setattr(pd.DataFrame, "append", lambda self, other, ignore_index=False, **kw:
+                       pd.concat([self, other], ignore_index=ignore_index) if len(self) else other.reset_index(drop=True),
+                       raising=False)
+    else:
+        monkey = None
+    from fedml_api.data_preprocessing.common import retrain as ref_retrain
+    from feddrift_b200.data.drift import select_iterations
+    C_, T_ = 3, 5
+    for c in range(C_):
+        for it in range(T_ + 2):
+            pd.DataFrame({"f1": [float(it)], "label": [c]}).to_csv(tmp_path / f"client_{c}_iter_{it}.csv", index=False)
+    methods = ["all", "win-1", "win-3", "sel-0,2,4", "weight-linear", "weight-exp", 'clientsel-[[0,1],[2],[1,4]]']
+    for t_cur in (0, 2, 4):
+        for method in methods:
+            if method.startswith("clientsel") and t_cur < 4:
+                continue
+            train, _ = ref_retrain.load_retrain_table_data(str(tmp_path) + "/", C_, t_cur, "client_{}_iter_{}.csv", method)
+            for c in range(C_):
+                want = [int(v) for v in train[c]["f1"].tolist()]
+                got = list(select_iterations(method, t_cur, c))
+                assert sorted(got) == sorted(want), (method, t_cur, c, got, want)
+    if monkey is not None:
+        monkey.undo()
+
+
+def test_mpc_primitives_match_reference_implementation():
+    """TurboAggregate finite-field primitives vs ``turboaggregate/mpc_function.py`` (deterministic entry points)."""
+    _reference_module()
+    from fedml_api.distributed.turboaggregate import mpc_function as ref_mpc
+    from feddrift_b200.fl import turboaggregate as ours
+    p = 2 ** 15 - 19
+    rng = np.random.RandomState(0)
+    for a in (3, 17, 12345, p - 2):
+        assert ours.modular_inv(a, p) == ref_mpc.modular_inv(a, p)
+        assert ours.divmod(a, 7, p) == ref_mpc.divmod(a, 7, p)
+    vals = [int(v) for v in rng.randint(1, p, 6)]
+    assert ours.PI(vals, p) == ref_mpc.PI(vals, p)
+    alpha, beta = np.arange(1, 8), np.arange(8, 12)
+    assert np.array_equal(np.asarray(ours.gen_Lagrange_coeffs(alpha, beta, p), dtype=np.int64) % p,
+                          np.asarray(ref_mpc.gen_Lagrange_coeffs(alpha, beta, p), dtype=np.int64) % p)
+    assert np.array_equal(np.asarray(ours.gen_BGW_lambda_s(alpha, p), dtype=np.int64) % p,
+                          np.asarray(ref_mpc.gen_BGW_lambda_s(alpha, p), dtype=np.int64) % p)
+    N, K, T_ = 8, 2, 1
+    X = rng.randint(0, p, (4, 6)).astype(np.int64)
+    R_ = rng.randint(0, p, (T_, 2, 6)).astype(np.int64)
+    enc_o = np.asarray(ours.LCC_encoding_w_Random(X, R_, N, K, T_, p), dtype=np.int64) % p
+    enc_r = np.asarray(ref_mpc.LCC_encoding_w_Random(X, R_, N, K, T_, p), dtype=np.int64) % p
+    assert np.array_equal(enc_o, enc_r)
+    widx = np.arange(K + T_)
+    flat_o, flat_r = enc_o[widx].reshape(len(widx), -1), enc_r[widx].reshape(len(widx), -1)   # [workers, m/K · d]
+    dec_o = np.asarray(ours.LCC_decoding(flat_o, 1, N, K, T_, widx, p), dtype=np.int64) % p
+    dec_r = np.asarray(ref_mpc.LCC_decoding(flat_r, 1, N, K, T_, widx, p), dtype=np.int64) % p
+    assert np.array_equal(dec_o, dec_r)
+    assert np.array_equal(dec_o.reshape(K, 2, 6).reshape(4, 6), X % p)      # and the decode really recovers X
+    # small secrets: the reference computes g ** sk in numpy int64 (it overflows for real key sizes; ours uses pow(g, sk, p))
+    assert ours.my_pk_gen(11, p, 5) == int(ref_mpc.my_pk_gen(11, p, 5))
+    assert ours.my_key_agreement(7, 3, p, 5) == int(ref_mpc.my_key_agreement(7, 3, p, 5))
+
+
+def test_symmetric_topology_and_message_wire_format_match_reference():
+    _reference_module()
+    import networkx as nx
+    if not hasattr(nx, "to_numpy_matrix"):
+        nx.to_numpy_matrix = nx.to_numpy_array          # removed in networkx 3 (same shim as the reference arm)
+    from fedml_core.distributed.communication.message import Message as RefMessage
+    from fedml_core.distributed.topology.symmetric_topology_manager import SymmetricTopologyManager as RefTopo
+    from feddrift_b200.core.message import Message
+    from feddrift_b200.core.topology import SymmetricTopologyManager
+    for n, k in ((6, 2), (8, 4), (5, 2)):
+        a, b = SymmetricTopologyManager(n, k), RefTopo(n, k)
+        a.generate_topology()
+        b.generate_topology()
+        assert np.allclose(np.asarray(a.topology), np.asarray(b.topology))
+        for i in range(n):
+            assert list(a.get_in_neighbor_idx_list(i)) == list(b.get_in_neighbor_idx_list(i))
+            assert np.allclose(a.get_in_neighbor_weights(i), b.get_in_neighbor_weights(i))
+    m, r = Message(3, 1, 0), RefMessage(3, 1, 0)
+    for msg in (m, r):
+        msg.add_params("client_idx", "4")
+        msg.add_params("num_samples", 17)
+    import json
+    assert json.loads(m.to_json()) == json.loads(r.to_json())
+    back = RefMessage()
+    back.init_from_json_string(m.to_json())
+    assert back.get_type() == 3 and back.get_sender_id() == 1 and back.get("num_samples") == 17

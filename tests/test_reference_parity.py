@@ -332,3 +332,52 @@ def test_symmetric_topology_and_message_wire_format_match_reference():
     back = RefMessage()
     back.init_from_json_string(m.to_json())
     assert back.get_type() == 3 and back.get_sender_id() == 1 and back.get("num_samples") == 17
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_multi_model_acc_state_matches_reference_implementation(seed):
+    """Legacy FedDrift-Eager (mmacc) and oracle (mmgeni / mmgeniex) model selection on scripted accuracies."""
+    ref_mod = _reference_module()
+    from feddrift_b200.drift.states import MultiModelAccState
+    C_, M_ = 5, 3
+    rng = np.random.RandomState(seed)
+    table = {}
+
+    class FakeEvaluator:
+        def acc_matrix(self, models, t):
+            return np.array([[table[(m, c, t)] for c in range(C_)] for m in models])
+
+    mine, theirs = MultiModelAccState(C_, M_, 0.1), ref_mod.MultiModelAccState(C_, M_, 0.1)
+    theirs._score = lambda m, data, device: table[(m, data, cur_t[0])]      # `data` is the client id in this harness
+    cur_t = [0]
+    mine.run_model_select(None, 0)
+    theirs.run_model_select(None, "cpu", 0)
+    mine.set_model(0)
+    theirs.models[0] = object()
+    for c in range(C_):
+        mine.set_acc(c, 0.9)
+        theirs.acc_dict[c] = 0.9
+    for t in range(1, 6):
+        cur_t[0] = t
+        for m in range(M_):
+            for c in range(C_):
+                table[(m, c, t)] = float(np.clip(0.9 - (0.4 if rng.rand() < 0.25 else 0.0) + 0.03 * rng.randn(), 0, 1))
+        mine.run_model_select(FakeEvaluator(), t)
+        theirs.run_model_select({c: c for c in range(C_)}, "cpu", t)
+        assert mine.train_data_dict == theirs.train_data_dict, t
+        assert mine.train_model_idx == theirs.train_model_idx and mine.test_model_idx == theirs.test_model_idx
+        for m in {mine.train_model_idx[c] for c in range(C_)}:   # models that got data this step exist from now on
+            mine.set_model(m)
+            theirs.models[m] = object()
+        for c in range(C_):
+            a = table[(mine.train_model_idx[c], c, t)]
+            mine.set_acc(c, a)
+            theirs.acc_dict[c] = a
+    cp = (rng.rand(4, C_) < 0.5).astype(np.int64)
+    cp[0] = 0
+    g1, g2 = MultiModelAccState(C_, 2, 0.1), ref_mod.MultiModelAccState(C_, 2, 0.1)
+    for t in range(6):
+        g1.model_select_geniex(t, cp, 2)
+        g2.model_select_geniex(t, cp, 2)
+        assert g1.train_model_idx == g2.train_model_idx and g1.test_model_idx == g2.test_model_idx
+    assert g1.train_data_dict == g2.train_data_dict

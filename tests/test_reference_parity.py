@@ -381,3 +381,65 @@ def test_multi_model_acc_state_matches_reference_implementation(seed):
         g2.model_select_geniex(t, cp, 2)
         assert g1.train_model_idx == g2.train_model_idx and g1.test_model_idx == g2.test_model_idx
     assert g1.train_data_dict == g2.train_data_dict
+
+
+def test_kue_kappa_weights_match_reference_aggregator_code():
+    """KUE ensemble weights: the reference's ``FedAvgEnsAggregatorKue.update_ens_weights`` (masked confusion matrices →
+    Cohen's κ per model, worst-model index) executed on a stand-in ``self`` vs ops.confusion_matrix + cohen_kappa."""
+    _reference_module()
+    from types import SimpleNamespace
+    from fedml_api.distributed.fedavg_ens.FedAvgEnsAggregatorKue import FedAvgEnsAggregatorKue as RefKue
+    from feddrift_b200 import ops
+    from feddrift_b200.ops import reference as oref
+    torch.manual_seed(0)
+    C_, M_, classes, feat = 3, 3, 3, 6
+    models = [nn.Linear(feat, classes) for _ in range(M_)]
+    masks = [(torch.rand(feat) > 0.3).float().numpy() for _ in range(M_)]
+    data = {m: {c: [(torch.randn(10, feat), torch.randint(0, classes, (10,))) for _ in range(2)] for c in range(C_)}
+            for m in range(M_)}
+    state = SimpleNamespace(get_masks=lambda: masks, worst=None)
+    state.set_worst_idx = lambda i: setattr(state, "worst", int(i))
+    fake = SimpleNamespace(models=models, class_num=classes, device=torch.device("cpu"), kue_state=state,
+                           train_data_local_dicts=data, ens_weights=np.ones(M_),
+                           args=SimpleNamespace(client_num_in_total=C_, curr_train_iteration=1))
+    fake._confusion_matrix = lambda model, d, mask: RefKue._confusion_matrix(fake, model, d, mask)
+    RefKue.update_ens_weights(fake)
+    mine = []
+    for m in range(M_):
+        A = torch.zeros(classes, classes, dtype=torch.float64)
+        for c in range(C_):
+            for x, y in data[m][c]:
+                with torch.no_grad():
+                    pred = models[m](x * torch.from_numpy(masks[m])).argmax(-1)
+                A += ops.confusion_matrix(pred, y, classes).double()
+        mine.append(oref.cohen_kappa(A))
+    assert np.allclose(mine, fake.ens_weights, atol=1e-12)
+    assert int(np.argmin(mine)) == state.worst
+
+
+def test_aue_model_scores_match_reference_aggregator_code():
+    """AUE weights 1/(MSE_r + MSE_i + ε): the reference's ``update_ens_weights`` run on a stand-in ``self``.  The reference
+    stores the score of model k+1 at index k (``enumerate(self.models[1:])``) — we compare score by score."""
+    _reference_module()
+    from types import SimpleNamespace
+    from fedml_api.distributed.fedavg_ens.FedAvgEnsAggregatorAue import FedAvgEnsAggregatorAue as RefAue
+    from feddrift_b200 import ops
+    torch.manual_seed(1)
+    C_, K_, classes, feat = 4, 4, 3, 5
+    models = [nn.Linear(feat, classes) for _ in range(K_)]
+    newest = {c: [(torch.randn(12, feat), torch.randint(0, classes, (12,))) for _ in range(2)] for c in range(C_)}
+    fake = SimpleNamespace(models=models, class_num=classes, device=torch.device("cpu"), ens_weights=np.ones(K_),
+                           train_data_local_dicts={0: newest}, args=SimpleNamespace(client_num_in_total=C_))
+    fake._mse = lambda model, d: RefAue._mse(fake, model, d)
+    RefAue.update_ens_weights(fake)
+    mser = (1 - 1.0 / classes) ** 2
+    ours = np.zeros(K_)
+    ours[0] = 1.0 / (mser + 1e-20)
+    n = sum(y.shape[0] for c in range(C_) for _, y in newest[c])
+    for k in range(1, K_):
+        with torch.no_grad():
+            sq = sum(float(ops.aue_sqerr(models[k](x), y)) for c in range(C_) for x, y in newest[c])
+        ours[k] = 1.0 / (mser + sq / n + 1e-20)
+    ref_w = fake.ens_weights / fake.ens_weights[0]          # undo the normalisation: index 0 is the "perfect" score
+    for k in range(2, K_):                                  # reference index k-1 holds model k's score
+        assert abs(ref_w[k - 1] - ours[k] / ours[0]) < 1e-6, k

@@ -443,3 +443,72 @@ def test_aue_model_scores_match_reference_aggregator_code():
     ref_w = fake.ens_weights / fake.ens_weights[0]          # undo the normalisation: index 0 is the "perfect" score
     for k in range(2, K_):                                  # reference index k-1 holds model k's score
         assert abs(ref_w[k - 1] - ours[k] / ours[0]) < 1e-6, k
+
+
+@pytest.mark.parametrize("retrain", ["win-1", "all"])
+def test_cfl_split_logic_matches_reference_implementation(retrain):
+    """Clustered FL: adaptive ε₁/ε₂ from the observed update norms, cosine-similarity bipartition (complete linkage),
+    γ test, capped slot allocation, weight rewrite — the reference's ``cluster_cfl`` vs ours on the same client updates."""
+    ref_mod = _reference_module()
+    import sklearn.cluster as skc
+    from feddrift_b200.drift.softcluster import SoftClusterState
+    from feddrift_b200.models import utils as mutils
+    from feddrift_b200.parallel.arena import ModelBank
+
+    def agglo(affinity=None, linkage="ward", **kw):   # sklearn renamed `affinity` → `metric` (same shim as the reference arm)
+        return skc.AgglomerativeClustering(metric=affinity or "euclidean", linkage=linkage, **kw)
+    ref_mod.AgglomerativeClustering = agglo
+
+    C_, M_ = 6, 4
+    torch.manual_seed(3)
+    bank = ModelBank(_LR(), M_, "cpu")
+    init_sd = {k: v.clone() for k, v in bank.state_dict(0).items()}
+    models = [_LR() for _ in range(M_)]
+    for mod in models:
+        mod.load_state_dict(init_sd)
+    ref_mod.reinitialize = lambda model: model.load_state_dict(init_sd)
+    kw = dict(cluster_alg="cfl", cfl_gamma=0.1, cfl_retrain=retrain)
+    mine, theirs = SoftClusterState(C_, M_, **kw), ref_mod.SoftClusterState(C_, M_, **kw)
+    for s_ in (mine, theirs):
+        s_.cluster_init()
+        s_.cluster_cfl_init(1)
+    P = bank.P
+    g = torch.Generator().manual_seed(9)
+    direction = torch.randn(P, generator=g)
+
+    def round_updates(kind):
+        """kind 'warm': everybody moves the same way (large mean norm → sets ε); 'split': two opposed groups."""
+        ups = []
+        for c in range(C_):
+            if kind == "warm":
+                ups.append(direction * 1.0 + 0.01 * torch.randn(P, generator=g))
+            else:
+                sign = 1.0 if c < 3 else -1.0
+                ups.append(sign * direction * 0.9 + 0.01 * torch.randn(P, generator=g))
+        return ups
+
+    split_seen = False
+    for rnd, kind in enumerate(["warm", "split", "warm", "split"]):
+        ups = round_updates(kind)
+        client_params = torch.zeros(C_, M_, P)
+        n = torch.zeros(C_, M_)
+        weights_dict = {}
+        for c in range(C_):
+            weights_dict[c] = {}
+            for m in range(M_):
+                if mine.W[1][m][c] > 0:
+                    row = bank.theta[m] + ups[c]
+                    client_params[c, m], n[c, m] = row, 10
+                    weights_dict[c][m] = (mutils.unflatten_to_state_dict(row.clone(), bank.spec), 10)
+                else:
+                    weights_dict[c][m] = (None, 0)
+        a = mine.cluster_cfl(1, rnd, bank, client_params, n)
+        b = theirs.cluster_cfl(1, rnd, models, weights_dict)
+        assert a == b, (rnd, kind)
+        split_seen = split_seen or a
+        for tt in (0, 1):
+            assert np.array_equal(mine.W[tt], theirs.train_data_weights[tt]), (rnd, tt)
+        assert abs(mine.cfl_norm - theirs.cfl_norm) < 1e-5 and abs(mine.cfl_eps2 - theirs.cfl_eps2) < 1e-5
+        for m in range(M_):
+            assert torch.allclose(bank.theta[m], mutils.flatten_state_dict(models[m].state_dict()), atol=1e-6)
+    assert split_seen

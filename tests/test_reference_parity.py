@@ -512,3 +512,26 @@ def test_cfl_split_logic_matches_reference_implementation(retrain):
         for m in range(M_):
             assert torch.allclose(bank.theta[m], mutils.flatten_state_dict(models[m].state_dict()), atol=1e-6)
     assert split_seen
+
+
+def test_robust_aggregator_clipping_matches_reference_implementation():
+    _reference_module()
+    from types import SimpleNamespace
+    from fedml_core.robustness.robust_aggregation import RobustAggregator as RefRA
+    from feddrift_b200.core.robustness import RobustAggregator
+
+    class SD(dict):   # the reference calls both `.items()` and `.state_dict()` on the local model argument
+        def state_dict(self):
+            return self
+
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv2d(2, 3, 3), nn.BatchNorm2d(3), nn.Flatten(), nn.Linear(3, 2))
+    glob = {k: v.clone().float() for k, v in net.state_dict().items()}
+    local = SD({k: (v.float() + 0.7 * torch.randn_like(v.float())) if v.dtype.is_floating_point else v for k, v in glob.items()})
+    args = SimpleNamespace(defense_type="norm_diff_clipping", norm_bound=0.5, stddev=0.01)
+    ours, theirs = RobustAggregator(args).norm_diff_clipping(local, glob), RefRA(args).norm_diff_clipping(local, glob)
+    assert list(ours.keys()) == list(theirs.keys())
+    for k in ours:
+        assert torch.allclose(ours[k].float(), theirs[k].float(), atol=1e-6), k
+    diff = torch.cat([(ours[k] - glob[k]).reshape(-1) for k in ours if "running" not in k and "num_batches" not in k])
+    assert abs(diff.norm().item() - 0.5) < 1e-4

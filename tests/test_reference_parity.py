@@ -524,10 +524,12 @@ def test_robust_aggregator_clipping_matches_reference_implementation():
         def state_dict(self):
             return self
 
+    # the reference's vectorize_weight concatenates the tensors un-flattened (torch.cat fails on mixed ranks), so the
+    # comparison uses 1-D parameters; ours flattens and therefore also handles real conv / linear state_dicts
     torch.manual_seed(0)
-    net = nn.Sequential(nn.Conv2d(2, 3, 3), nn.BatchNorm2d(3), nn.Flatten(), nn.Linear(3, 2))
-    glob = {k: v.clone().float() for k, v in net.state_dict().items()}
-    local = SD({k: (v.float() + 0.7 * torch.randn_like(v.float())) if v.dtype.is_floating_point else v for k, v in glob.items()})
+    glob = {"l1.weight": torch.randn(12), "l1.bias": torch.randn(4), "bn.running_mean": torch.randn(4),
+            "bn.num_batches_tracked": torch.tensor([3.0]), "l2.weight": torch.randn(7)}
+    local = SD({k: v + 0.7 * torch.randn_like(v) for k, v in glob.items()})
     args = SimpleNamespace(defense_type="norm_diff_clipping", norm_bound=0.5, stddev=0.01)
     ours, theirs = RobustAggregator(args).norm_diff_clipping(local, glob), RefRA(args).norm_diff_clipping(local, glob)
     assert list(ours.keys()) == list(theirs.keys())

@@ -32,6 +32,35 @@ def main():
             return r
 
         cls.test_on_all_clients = timed
+    metrics_path = os.environ.get("FDB_REF_METRICS", "")
+    if rank == 0 and metrics_path:
+        # observation only: mirror what the reference sends to wandb.log (Train/Acc, Test/Acc, … keyed by round) into a
+        # JSON-lines file so that accuracy trajectories can be compared (tools/e2e_parity.py)
+        import wandb
+
+        def install():
+            orig_log = wandb.log
+
+            def log(data=None, *a, **k):
+                try:
+                    row = {str(kk): (float(v) if isinstance(v, (int, float)) else str(v)) for kk, v in dict(data or {}).items()}
+                    with open(metrics_path, "a") as fh:
+                        fh.write(json.dumps(row) + "\n")
+                except Exception:
+                    pass
+                return orig_log(data, *a, **k)
+
+            wandb.log = log
+
+        orig_init = wandb.init
+
+        def init(*a, **k):   # wandb.init rebinds wandb.log to the run's method: wrap again afterwards
+            run = orig_init(*a, **k)
+            install()
+            return run
+
+        wandb.init = init
+        install()
     script = os.environ.get("FDB_REF_SCRIPT", "main_fedavg.py")
     sys.argv = [script] + sys.argv[1:]
     runpy.run_path(os.path.join(exp_dir, script), run_name="__main__")

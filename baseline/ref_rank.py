@@ -16,22 +16,30 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     out_path = os.environ.get("FDB_REF_TIMING", "")
     if rank == 0 and out_path:
+        import importlib
         import torch
-        from fedml_api.distributed.fedavg_ens import FedAvgEnsAggregatorSoftCluster as mod
-        cls = mod.FedAvgEnsAggregatorSoftCluster
-        orig = cls.test_on_all_clients
         stamps = []
 
-        def timed(self, round_idx):
-            r = orig(self, round_idx)
-            if torch.cuda.is_available():
-                torch.cuda.synchronize()
-            stamps.append(time.perf_counter())
-            with open(out_path, "w") as fh:
-                json.dump({"round_end": stamps}, fh)
-            return r
+        def wrap(cls):
+            orig = cls.test_on_all_clients
 
-        cls.test_on_all_clients = timed
+            def timed(self, round_idx):
+                r = orig(self, round_idx)
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()
+                stamps.append(time.perf_counter())
+                with open(out_path, "w") as fh:
+                    json.dump({"round_end": stamps}, fh)
+                return r
+
+            cls.test_on_all_clients = timed
+
+        for name in ("SoftCluster", "Aue", "AuePc", "Kue", "DriftSurf", "MultiModelAcc", "ClusterFL", "Ada", "Vanilla"):
+            try:   # whichever aggregator the run's algorithm selects (FedAvgEnsAPI.py:95-141)
+                mod = importlib.import_module(f"fedml_api.distributed.fedavg_ens.FedAvgEnsAggregator{name}")
+                wrap(getattr(mod, f"FedAvgEnsAggregator{name}"))
+            except Exception:
+                pass
     metrics_path = os.environ.get("FDB_REF_METRICS", "")
     if rank == 0 and metrics_path:
         # observation only: mirror what the reference sends to wandb.log (Train/Acc, Test/Acc, … keyed by round) into a

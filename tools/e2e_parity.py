@@ -20,13 +20,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=3, help="time steps 0..steps-1 are trained")
     ap.add_argument("--rounds", type=int, default=10)
+    ap.add_argument("--algo", type=str, default="softcluster")
     ap.add_argument("--algo_arg", type=str, default="H_A_C_1_10_0")
+    ap.add_argument("--strict_ref", type=int, default=0, help="1: also reproduce the reference's known quirks (e.g. AUE weight shift)")
     a = ap.parse_args()
+    rr.ALGO = (a.algo, a.algo_arg)
     if not os.path.isdir(os.path.join(rr.REF, "fedml_api")):
         from baseline import install_reference
         assert install_reference.main() == 0
     total_iter = 10
-    for f in ("model_params.pt", "sc_state.pkl", "output.log"):
+    for f in ("model_params.pt", "sc_state.pkl", "output.log", "ds_state.pkl", "kue_state.pkl", "ada_state.pkl", "mm_state.pkl"):
         p = os.path.join(rr.EXP, f)
         if os.path.exists(p):
             os.remove(p)
@@ -69,7 +72,8 @@ def main():
     data = DriftData.from_csv_dir(cand[0], "sea", rr.CLIENTS, total_iter + 1, 2, cp)
     args = make_args(dataset="sea", model="fnn", client_num_in_total=rr.CLIENTS, client_num_per_round=rr.CLIENTS,
                      comm_round=a.rounds, epochs=5, batch_size=500, lr=0.01, total_train_iteration=total_iter, concept_num=4,
-                     concept_drift_algo="softcluster", concept_drift_algo_arg=a.algo_arg, change_points="A", sample_num=100)
+                     concept_drift_algo=a.algo, concept_drift_algo_arg=a.algo_arg, change_points="A", sample_num=100,
+                     strict_ref=a.strict_ref)
     sim = DriftSim(args, data=data, device="cuda" if torch.cuda.is_available() else "cpu", sink=MetricsSink())
     ours = []
     for it in range(a.steps):

@@ -338,7 +338,10 @@ Tensor gemm_tn_bias_act(Tensor A, Tensor B, c10::optional<Tensor> bias, bool rel
     const float* bp = nullptr;
     Tensor bias_f;
     if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
-    const int rc = fdb::gemm_tn_launch(A.data_ptr(), B.data_ptr(), D.data_ptr(), bp, M, N, K, relu ? 1 : 0, out_fp32 ? 1 : 0, cur_stream());
+    Tensor ws;   // fp32 split-K accumulator for bf16 outputs, from the caching allocator
+    if (!out_fp32 && fdb::gemm_split_count(M, N, K) > 1) ws = torch::empty({M, N}, A.options().dtype(torch::kFloat32));
+    const int rc = fdb::gemm_launch(A.data_ptr(), B.data_ptr(), D.data_ptr(), bp, M, N, K, 0, 0, relu ? 1 : 0, out_fp32 ? 1 : 0, cur_stream(),
+                                    ws.defined() ? ws.data_ptr<float>() : nullptr);
     CHECK_OK(rc, "gemm_tn (tcgen05)");
     return D;
 }
@@ -355,8 +358,10 @@ Tensor gemm_bias_act(Tensor A, Tensor B, bool a_mn, bool b_mn, c10::optional<Ten
     const float* bp = nullptr;
     Tensor bias_f;
     if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
+    Tensor ws;
+    if (!out_fp32 && fdb::gemm_split_count(M, N, K) > 1) ws = torch::empty({M, N}, A.options().dtype(torch::kFloat32));
     const int rc = fdb::gemm_launch(A.data_ptr(), B.data_ptr(), D.data_ptr(), bp, M, N, K, a_mn ? 1 : 0, b_mn ? 1 : 0, relu ? 1 : 0,
-                                    out_fp32 ? 1 : 0, cur_stream());
+                                    out_fp32 ? 1 : 0, cur_stream(), ws.defined() ? ws.data_ptr<float>() : nullptr);
     CHECK_OK(rc, "gemm (tcgen05)");
     return D;
 }
@@ -373,8 +378,10 @@ Tensor gemm_tn_bias_act_peer(Tensor A, int64_t b_ptr, int64_t N, c10::optional<T
     const float* bp = nullptr;
     Tensor bias_f;
     if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
-    const int rc = fdb::gemm_tn_launch(A.data_ptr(), reinterpret_cast<const void*>(b_ptr), D.data_ptr(), bp, M, (int)N, K, relu ? 1 : 0,
-                                       out_fp32 ? 1 : 0, cur_stream());
+    Tensor ws;
+    if (!out_fp32 && fdb::gemm_split_count(M, (int)N, K) > 1) ws = torch::empty({M, N}, A.options().dtype(torch::kFloat32));
+    const int rc = fdb::gemm_launch(A.data_ptr(), reinterpret_cast<const void*>(b_ptr), D.data_ptr(), bp, M, (int)N, K, 0, 0, relu ? 1 : 0,
+                                    out_fp32 ? 1 : 0, cur_stream(), ws.defined() ? ws.data_ptr<float>() : nullptr);
     CHECK_OK(rc, "gemm_tn_peer (tcgen05)");
     return D;
 }

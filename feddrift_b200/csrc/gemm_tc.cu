@@ -453,8 +453,25 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
+// number of K-splits gemm_launch will use for this problem (callers that want a bf16 output pre-allocate the fp32
+// accumulation workspace with their own allocator when this is > 1)
+int gemm_split_count(int M, int N, int K) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int bn = (N > 128) ? 256 : 128;
+    const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    const int kb_total = (K + BK - 1) / BK;
+    int splits = 1;
+    if (tiles * 4 <= sms && kb_total >= 16) {   // too few output tiles to fill the machine and a long K
+        splits = min(min(sms / tiles, kb_total / 4), 32);
+        if (splits < 2) splits = 1;
+    }
+    return splits;
+}
+
 int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int a_mn, int b_mn, int relu, int out_fp32,
-                cudaStream_t stream) {
+                cudaStream_t stream, float* splitk_ws) {
     // TMA global strides must be multiples of 16 B: the contiguous extent of each operand must be a multiple of 8 bf16
     if (M <= 0 || N <= 0 || K <= 0) return -5;
     if ((a_mn ? M : K) % 8 != 0 || (b_mn ? N : K) % 8 != 0) return -5;
@@ -468,17 +485,15 @@ int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M,
     if ((b_mn ? make_map_mn(&mb, B, N, K) : make_map(&mb, B, N, K, bn)) != 0) return -7;
     const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
     const int kb_total = (K + BK - 1) / BK;
-    // split-K when the output has too few tiles to fill the machine and K is long
-    int splits = 1;
-    if (tiles * 4 <= sms && kb_total >= 16) {
-        splits = min(min(sms / tiles, kb_total / 4), 32);
-        if (splits < 2) splits = 1;
-    }
+    (void)tiles; (void)kb_total;
+    const int splits = gemm_split_count(M, N, K);
     if (splits > 1) {
         float* acc = nullptr;
         const size_t bytes = (size_t)M * N * sizeof(float);
+        bool own = false;
         if (out_fp32) acc = reinterpret_cast<float*>(D);
-        else if (cudaMallocAsync(&acc, bytes, stream) != cudaSuccess) return -8;
+        else if (splitk_ws) acc = splitk_ws;     // caller's allocator (torch caching allocator: no driver call on the hot path)
+        else { if (cudaMallocAsync(&acc, bytes, stream) != cudaSuccess) return -8; own = true; }
         cudaMemsetAsync(acc, 0, bytes, stream);
         int rc = (bn == 256) ? launch_gemm<256>(ma, mb, acc, nullptr, M, N, K, 0, 1, splits, sms, a_mn, b_mn, stream)
                              : launch_gemm<128>(ma, mb, acc, nullptr, M, N, K, 0, 1, splits, sms, a_mn, b_mn, stream);
@@ -487,7 +502,7 @@ int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M,
             const long long MN = (long long)M * N;
             bias_act_kernel<<<(int)min((MN + 255) / 256, 148LL * 8), 256, 0, stream>>>(acc, D, bias, MN, N, relu, out_fp32);
         }
-        if (!out_fp32) cudaFreeAsync(acc, stream);
+        if (own) cudaFreeAsync(acc, stream);
         return cudaGetLastError() == cudaSuccess ? 0 : -4;
     }
     return (bn == 256) ? launch_gemm<256>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, a_mn, b_mn, stream)
@@ -496,7 +511,7 @@ int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M,
 
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
                    cudaStream_t stream) {
-    return gemm_launch(A, B, D, bias, M, N, K, 0, 0, relu, out_fp32, stream);
+    return gemm_launch(A, B, D, bias, M, N, K, 0, 0, relu, out_fp32, stream, nullptr);
 }
 
 }  // namespace fdb

@@ -46,8 +46,9 @@ int vfl_bce_launch(const float* parts, const float* y, int K, int B, float* loss
 int group_norm_fwd_launch(const float* x, float* y, const float* w, const float* b, int N, int C, int HW, int G, float eps,
                           cudaStream_t stream);
 // gemm_tc.cu : D[M,N] (fp32 or bf16) = act(A[M,K] · B[N,K]^T + bias[N]); A,B bf16 row-major (K contiguous)
+int gemm_split_count(int M, int N, int K);
 int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int a_mn, int b_mn, int relu, int out_fp32,
-                cudaStream_t stream);
+                cudaStream_t stream, float* splitk_ws = nullptr);
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
                    cudaStream_t stream);
 }  // namespace fdb

@@ -11,7 +11,7 @@ import time
 
 def main():
     ref_root = os.environ["FDB_REF_ROOT"]
-    exp_dir = os.path.join(ref_root, "fedml_experiments", "distributed", "fedavg_cont_ens")
+    exp_dir = os.path.join(ref_root, "fedml_experiments", "distributed", os.environ.get("FDB_REF_EXP", "fedavg_cont_ens"))
     os.chdir(exp_dir)
     rank = int(os.environ.get("RANK", "0"))
     out_path = os.environ.get("FDB_REF_TIMING", "")
@@ -40,6 +40,11 @@ def main():
                 wrap(getattr(mod, f"FedAvgEnsAggregator{name}"))
             except Exception:
                 pass
+        try:   # fedavg_cont_one (single-model window baselines) uses the plain FedAvg aggregator
+            mod = importlib.import_module("fedml_api.distributed.fedavg.FedAVGAggregator")
+            wrap(mod.FedAVGAggregator)
+        except Exception:
+            pass
     metrics_path = os.environ.get("FDB_REF_METRICS", "")
     if rank == 0 and metrics_path:
         # observation only: mirror what the reference sends to wandb.log (Train/Acc, Test/Acc, … keyed by round) into a

@@ -42,9 +42,17 @@ def _env(extra=None):
 
 
 ALGO = ("softcluster", "H_A_C_1_10_0")   # (concept_drift_algo, concept_drift_algo_arg); tools/e2e_parity.py overrides it
+CONT_ONE = None   # set to a --retrain_data value ("win-1", "all", …) to run fedavg_cont_one (single-model baselines) instead
 
 
 def _common_flags(gpus: int, rounds: int, it: int, total_iter: int):
+    if CONT_ONE is not None:   # fedavg_cont_one/main_fedavg.py: same driver, no drift-algorithm flags
+        return ["--gpu_server_num", "1", "--gpu_num_per_server", str(max(gpus, 1)), "--model", "fnn", "--dataset", "sea",
+                "--data_dir", "./../../../data/", "--noise_prob", "0", "--client_num_in_total", str(CLIENTS),
+                "--client_num_per_round", str(CLIENTS), "--comm_round", str(rounds), "--epochs", "5", "--batch_size", "500",
+                "--lr", "0.01", "--ci", "0", "--total_train_iteration", str(total_iter), "--curr_train_iteration", str(it),
+                "--reset_models", "0", "--drift_together", "0", "--report_client", "1", "--retrain_data", CONT_ONE,
+                "--time_stretch", "1", "--dummy_arg", "0", "--change_points", "A"]
     return ["--gpu_server_num", "1", "--gpu_num_per_server", str(max(gpus, 1)), "--model", "fnn", "--dataset", "sea",
             "--data_dir", "./../../../data/", "--noise_prob", "0", "--client_num_in_total", str(CLIENTS),
             "--client_num_per_round", str(CLIENTS), "--comm_round", str(rounds), "--epochs", "5", "--batch_size", "500",
@@ -63,9 +71,11 @@ def _run_time_step(gpus: int, rounds: int, it: int, total_iter: int, timing_path
         os.remove(timing_path)
     for rank in range(world):
         env = _env({"RANK": str(rank), "WORLD_SIZE": str(world), "MASTER_PORT": str(port),
-                    "FDB_REF_TIMING": timing_path if rank == 0 else ""})
+                    "FDB_REF_TIMING": timing_path if rank == 0 else "",
+                    "FDB_REF_EXP": "fedavg_cont_ens" if CONT_ONE is None else "fedavg_cont_one"})
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "ref_rank.py")] +
-                                      _common_flags(gpus, rounds, it, total_iter), env=env, cwd=EXP,
+                                      _common_flags(gpus, rounds, it, total_iter), env=env,
+                                      cwd=EXP if CONT_ONE is None else EXP.replace("fedavg_cont_ens", "fedavg_cont_one"),
                                       stdout=subprocess.DEVNULL, stderr=subprocess.PIPE if rank == 0 else subprocess.DEVNULL))
     t0 = time.time()
     err = b""

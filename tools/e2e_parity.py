@@ -23,16 +23,21 @@ def main():
     ap.add_argument("--algo", type=str, default="softcluster")
     ap.add_argument("--algo_arg", type=str, default="H_A_C_1_10_0")
     ap.add_argument("--strict_ref", type=int, default=0, help="1: also reproduce the reference's known quirks (e.g. AUE weight shift)")
+    ap.add_argument("--cont_one", type=str, default="", help="run fedavg_cont_one with this --retrain_data (win-1, win-2, all, …)")
     a = ap.parse_args()
     rr.ALGO = (a.algo, a.algo_arg)
+    if a.cont_one:
+        rr.CONT_ONE = a.cont_one
+        a.algo, a.algo_arg = a.cont_one, ""
     if not os.path.isdir(os.path.join(rr.REF, "fedml_api")):
         from baseline import install_reference
         assert install_reference.main() == 0
     total_iter = 10
     for f in ("model_params.pt", "sc_state.pkl", "output.log", "ds_state.pkl", "kue_state.pkl", "ada_state.pkl", "mm_state.pkl"):
-        p = os.path.join(rr.EXP, f)
-        if os.path.exists(p):
-            os.remove(p)
+        for d in (rr.EXP, rr.EXP.replace("fedavg_cont_ens", "fedavg_cont_one")):
+            p = os.path.join(d, f)
+            if os.path.exists(p):
+                os.remove(p)
     prep = subprocess.run([sys.executable, os.path.join(rr.HERE, "ref_rank.py"), "--dataset", "sea", "--data_dir", "./../../../data/",
                            "--sample_num", "100", "--noise_prob", "0", "--partition_method", "homo", "--client_num_in_total",
                            str(rr.CLIENTS), "--client_num_per_round", str(rr.CLIENTS), "--batch_size", "500", "--train_iteration",

@@ -42,6 +42,7 @@ def _env(extra=None):
 
 
 ALGO = ("softcluster", "H_A_C_1_10_0")   # (concept_drift_algo, concept_drift_algo_arg); tools/e2e_parity.py overrides it
+CHANGE_POINTS = "A"
 CONT_ONE = None   # set to a --retrain_data value ("win-1", "all", …) to run fedavg_cont_one (single-model baselines) instead
 
 
@@ -52,14 +53,14 @@ def _common_flags(gpus: int, rounds: int, it: int, total_iter: int):
                 "--client_num_per_round", str(CLIENTS), "--comm_round", str(rounds), "--epochs", "5", "--batch_size", "500",
                 "--lr", "0.01", "--ci", "0", "--total_train_iteration", str(total_iter), "--curr_train_iteration", str(it),
                 "--reset_models", "0", "--drift_together", "0", "--report_client", "1", "--retrain_data", CONT_ONE,
-                "--time_stretch", "1", "--dummy_arg", "0", "--change_points", "A"]
+                "--time_stretch", "1", "--dummy_arg", "0", "--change_points", CHANGE_POINTS]
     return ["--gpu_server_num", "1", "--gpu_num_per_server", str(max(gpus, 1)), "--model", "fnn", "--dataset", "sea",
             "--data_dir", "./../../../data/", "--noise_prob", "0", "--client_num_in_total", str(CLIENTS),
             "--client_num_per_round", str(CLIENTS), "--comm_round", str(rounds), "--epochs", "5", "--batch_size", "500",
             "--lr", "0.01", "--ci", "0", "--total_train_iteration", str(total_iter), "--curr_train_iteration", str(it),
             "--concept_num", "4", "--reset_models", "0", "--drift_together", "0", "--report_client", "1",
             "--retrain_data", "win-1", "--concept_drift_algo", ALGO[0], "--concept_drift_algo_arg", ALGO[1],
-            "--time_stretch", "1", "--dummy_arg", "0", "--change_points", "A"]
+            "--time_stretch", "1", "--dummy_arg", "0", "--change_points", CHANGE_POINTS]
 
 
 def _run_time_step(gpus: int, rounds: int, it: int, total_iter: int, timing_path: str, timeout_s: float):

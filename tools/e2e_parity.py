@@ -23,9 +23,11 @@ def main():
     ap.add_argument("--algo", type=str, default="softcluster")
     ap.add_argument("--algo_arg", type=str, default="H_A_C_1_10_0")
     ap.add_argument("--strict_ref", type=int, default=0, help="1: also reproduce the reference's known quirks (e.g. AUE weight shift)")
+    ap.add_argument("--change_points", type=str, default="A")
     ap.add_argument("--cont_one", type=str, default="", help="run fedavg_cont_one with this --retrain_data (win-1, win-2, all, …)")
     a = ap.parse_args()
     rr.ALGO = (a.algo, a.algo_arg)
+    rr.CHANGE_POINTS = a.change_points
     if a.cont_one:
         rr.CONT_ONE = a.cont_one
         a.algo, a.algo_arg = a.cont_one, ""
@@ -41,7 +43,7 @@ def main():
     prep = subprocess.run([sys.executable, os.path.join(rr.HERE, "ref_rank.py"), "--dataset", "sea", "--data_dir", "./../../../data/",
                            "--sample_num", "100", "--noise_prob", "0", "--partition_method", "homo", "--client_num_in_total",
                            str(rr.CLIENTS), "--client_num_per_round", str(rr.CLIENTS), "--batch_size", "500", "--train_iteration",
-                           str(total_iter), "--drift_together", "0", "--time_stretch", "1", "--change_points", "A"],
+                           str(total_iter), "--drift_together", "0", "--time_stretch", "1", "--change_points", a.change_points],
                           env=rr._env({"FDB_REF_SCRIPT": "prepare_data.py", "RANK": "0", "WORLD_SIZE": "1"}), cwd=rr.EXP,
                           capture_output=True, text=True)
     assert prep.returncode == 0, prep.stderr[-500:]
@@ -73,11 +75,11 @@ def main():
     data_dir = os.path.join(rr.REF, "data", "sea")
     cand = [d for d, _, fs in os.walk(data_dir) if any(f.startswith("client_0_iter_0") for f in fs)]
     assert cand, f"no generated CSVs under {data_dir}"
-    cp = changepoints.named("A")
+    cp = changepoints.named(a.change_points)
     data = DriftData.from_csv_dir(cand[0], "sea", rr.CLIENTS, total_iter + 1, 2, cp)
     args = make_args(dataset="sea", model="fnn", client_num_in_total=rr.CLIENTS, client_num_per_round=rr.CLIENTS,
                      comm_round=a.rounds, epochs=5, batch_size=500, lr=0.01, total_train_iteration=total_iter, concept_num=4,
-                     concept_drift_algo=a.algo, concept_drift_algo_arg=a.algo_arg, change_points="A", sample_num=100,
+                     concept_drift_algo=a.algo, concept_drift_algo_arg=a.algo_arg, change_points=a.change_points, sample_num=100,
                      strict_ref=a.strict_ref)
     sim = DriftSim(args, data=data, device="cuda" if torch.cuda.is_available() else "cpu", sink=MetricsSink())
     ours = []

@@ -9,8 +9,9 @@ A *step* is one complete FL round: broadcast of the cluster models, 5 local opti
 participating (client, model) pair, per-cluster weighted aggregation, train+test evaluation of every client
 (``frequency_of_the_test = 1`` like the reference's run script).  Timing: CUDA events around every round on the
 launching stream, L2 flushed (256 MiB write) between rounds outside the event brackets, max over ranks; the
-``e2e`` number drives the public ``DriftSim.run_round`` API with a pinned-host→device copy of the round's
-inputs and a device→host read of the round's metrics inside the timed region.
+``e2e`` number drives the public ``DriftSim.run_round`` API: every round the round's inputs travel from pinned host
+memory to the device and the round's metrics come back to pinned host memory inside the timed region (the round kernel
+performs both transfers itself — fused host I/O — so the whole round is one CUDA-graph node).
 """
 from __future__ import annotations
 

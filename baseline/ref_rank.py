@@ -74,6 +74,18 @@ def main():
 
         wandb.init = init
         install()
+    if os.environ.get("FDB_REF_NOSLEEP") == "1":
+        # "sleep-removed" variant of the baseline: the reference's event loop sleeps 0.3 s after every
+        # dispatched message (com_manager.py:71-79) and its send thread sleeps 0.3 s when idle (mpi_send_thread.py:28-29).
+        # Only those two modules get a `time` whose sleep() yields for 50 us instead; the sources stay untouched.
+        import importlib
+        import types
+        quick = types.SimpleNamespace(**{k: getattr(time, k) for k in dir(time) if not k.startswith("_")})
+        _real_sleep = time.sleep
+        quick.sleep = lambda s: _real_sleep(min(s, 5e-5))
+        for name in ("fedml_core.distributed.communication.mpi.com_manager",
+                     "fedml_core.distributed.communication.mpi.mpi_send_thread"):
+            importlib.import_module(name).time = quick
     script = os.environ.get("FDB_REF_SCRIPT", "main_fedavg.py")
     sys.argv = [script] + sys.argv[1:]
     runpy.run_path(os.path.join(exp_dir, script), run_name="__main__")

@@ -26,7 +26,7 @@ std::vector<int64_t> fed_round_small(
     c10::optional<Tensor> train_index, c10::optional<Tensor> train_count, c10::optional<Tensor> feat_mask,
     c10::optional<Tensor> eval_train_model, c10::optional<Tensor> eval_test_model, c10::optional<Tensor> ens_w,
     c10::optional<Tensor> client_out, c10::optional<Tensor> lr_dev, Tensor metrics, c10::optional<Tensor> timers,
-    std::vector<double> fcfg, std::vector<int64_t> icfg, std::vector<int64_t> peer_inbox, std::vector<int64_t> peer_flags,
+    std::vector<double> fcfg, std::vector<int64_t> icfg, std::vector<int64_t> peer_inbox,
     c10::optional<Tensor> error_flag, c10::optional<Tensor> counters, std::vector<int64_t> peer_metrics, std::vector<int64_t> host_io) {
     CHECK_CUDA_F32(X); CHECK_CUDA_I32(Y); CHECK_CUDA_I32(nsamp); CHECK_CUDA_F32(W); CHECK_CUDA_F32(theta); CHECK_CUDA_I32(opt_step);
     CHECK_CUDA_F32(metrics);
@@ -60,14 +60,11 @@ std::vector<int64_t> fed_round_small(
     const int cluster = (int)icfg[20];
     p.spin_timeout_ns = (long long)icfg[21] * 1000000LL;
     p.warps_per_pair = icfg.size() > 22 ? (int)icfg[22] : 1;
-    TORCH_CHECK(p.t_cur < 64, "fed_round_small supports t_cur < 64 time steps");
+    TORCH_CHECK(p.t_cur < 64, "fed_round_small supports t_cur < 64 time steps (use fed_round_small_fits to route)");
     TORCH_CHECK(p.world >= 1 && p.world <= fdb::kMaxPeers, "world must be in [1, 8]");
     if (p.world > 1) {
-        TORCH_CHECK((int)peer_inbox.size() == p.world && (int)peer_flags.size() == p.world, "need one inbox/flag pointer per rank");
-        for (int g = 0; g < p.world; ++g) {
-            p.inbox[g] = reinterpret_cast<float*>(peer_inbox[g]);
-            p.flags[g] = reinterpret_cast<unsigned*>(peer_flags[g]);
-        }
+        TORCH_CHECK((int)peer_inbox.size() == p.world, "need one inbox pointer per rank");
+        for (int g = 0; g < p.world; ++g) p.inbox[g] = reinterpret_cast<float*>(peer_inbox[g]);
         TORCH_CHECK(!p.recluster_hard, "per-round IFCA re-clustering is single-GPU only in this build");
     }
     p.error_flag = opt_ptr<int>(error_flag);
@@ -90,6 +87,10 @@ std::vector<int64_t> fed_round_small(
     TORCH_CHECK(rc != -2, "fed_round_small: shared-memory footprint exceeds 227 KB for this (clients, models) size");
     CHECK_OK(rc, "fed_round_small launch");
     return {info.cluster, info.threads, info.smem_bytes};
+}
+
+bool fed_round_small_fits(int64_t kind, int64_t din, int64_t hid, int64_t dout, int64_t C, int64_t M, int64_t t_cur) {
+    return fdb::fed_round_small_fits((int)kind, (int)din, (int)hid, (int)dout, (int)C, (int)M, (int)t_cur) != 0;
 }
 
 bool fed_round_small_supported(int64_t kind, int64_t din, int64_t hid, int64_t dout) {
@@ -429,6 +430,7 @@ void graph_launch_sync(int64_t exec, bool sync) {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("fed_round_small", &fed_round_small);
     m.def("fed_round_small_supported", &fed_round_small_supported);
+    m.def("fed_round_small_fits", &fed_round_small_fits);
     m.def("mlp_eval_matrix", &mlp_eval_matrix);
     m.def("cluster_aggregate", &cluster_aggregate);
     m.def("cluster_aggregate_opt", &cluster_aggregate_opt);

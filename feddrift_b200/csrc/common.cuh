@@ -70,6 +70,26 @@ FDB_DEVICE float ld_relaxed_sys_f32(const float* p) {
     asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
+// LL ("low latency") words: payload and epoch tag travel in ONE 8- or 16-byte store, so the receiver needs neither a
+// fence nor a separate flag — it polls the word until the tag matches.  (8-byte stores are single-copy atomic; the 16-byte
+// variant carries the tag twice and the reader checks both halves, as NCCL's LL lines do.)
+FDB_DEVICE void st_ll(uint2* p, float v, unsigned tag) {
+    asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+FDB_DEVICE uint2 ld_ll(const uint2* p) {
+    uint2 w;
+    asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p) : "memory");
+    return w;
+}
+FDB_DEVICE void st_ll2(uint4* p, float a, float b, unsigned tag) {
+    asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(tag),
+                 "r"(__float_as_uint(b)), "r"(tag) : "memory");
+}
+FDB_DEVICE uint4 ld_ll2(const uint4* p) {
+    uint4 w;
+    asm volatile("ld.relaxed.sys.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p) : "memory");
+    return w;
+}
 FDB_DEVICE long long globaltimer_ns() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -435,38 +435,50 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                         theta_s[e] = v;
                     }
                 }
-            } else {
-                // ---- cross-GPU: push the cluster partial to every peer inbox, publish epoch, sum in rank order
-                const unsigned epoch = flag_base + (unsigned)r + 1u;
-                const int xbuf = (int)((flag_base + (unsigned)r) & 1u);
-                if (crank == 0) {
-                    for (int e = tid; e < MP; e += blockDim.x) {
-                        float v = 0.f;
-                        for (int rk = 0; rk < G; ++rk) v += *(cluster.map_shared_rank(part_s + buf * MP + e, rk));
-                        for (int gq = 0; gq < p.world; ++gq)
-                            st_relaxed_sys_f32(p.inbox[gq] + ((size_t)(xbuf * p.world + p.rank)) * MP + e, v);
+            }
+            __syncthreads();
+        }
+        if (p.world > 1) {
+            // ---- cross-GPU exchange, LL protocol (flag-in-data, like NCCL's LL): every 8-byte inbox word is
+            //      {partial value, round epoch} written by ONE st.v2 — no fence, no separate flag, no round trip: the cost is
+            //      one one-way NVLink store latency.  CTA k of the cluster serves the destinations g ≡ k (mod G); every CTA
+            //      polls this rank's own inbox (local L2) and sums the senders in rank order (bit-identical on all ranks).
+            //      Slots are double-buffered by epoch parity: a sender can only reach epoch E+2 after it has received E+1
+            //      from every rank, i.e. after every rank finished reading E.  With skip_aggregate the exchange still runs
+            //      (zeros) so that ranks stay within one round of each other (the metrics staging below relies on it).
+            const unsigned epoch = flag_base + (unsigned)r + 1u;
+            const int xbuf = (int)((flag_base + (unsigned)r) & 1u);
+            const size_t slot = (size_t)(xbuf * p.world + p.rank) * MP;
+            for (int e = tid; e < MP; e += blockDim.x) {
+                float v = 0.f;
+                if (!p.skip_aggregate)
+                    for (int rk = 0; rk < G; ++rk) v += *(cluster.map_shared_rank(part_s + buf * MP + e, rk));
+                for (int gq = crank; gq < p.world; gq += G)
+                    st_ll(reinterpret_cast<uint2*>(p.inbox[gq]) + slot + e, v, epoch);
+            }
+            const uint2* inb = reinterpret_cast<const uint2*>(p.inbox[p.rank]) + (size_t)(xbuf * p.world) * MP;
+            const long long t0 = globaltimer_ns();
+            for (int e = tid; e < MP; e += blockDim.x) {
+                uint2 w[kMaxPeers];
+#pragma unroll
+                for (int gq = 0; gq < kMaxPeers; ++gq)   // all senders' words in flight at once (one L2 latency, not W)
+                    if (gq < p.world) w[gq] = ld_ll(inb + (size_t)gq * MP + e);
+                float v = 0.f;
+                bool ok = true;
+#pragma unroll
+                for (int gq = 0; gq < kMaxPeers; ++gq) {
+                    if (gq < p.world) {
+                        while (ok && w[gq].y != epoch) {
+                            if (globaltimer_ns() - t0 > p.spin_timeout_ns) { ok = false; break; }
+                            w[gq] = ld_ll(inb + (size_t)gq * MP + e);
+                        }
+                        v += __uint_as_float(w[gq].x);
                     }
-                    __threadfence_system();
-                    __syncthreads();
-                    if (tid < p.world) st_release_sys(p.flags[tid] + xbuf * p.world + p.rank, epoch);
                 }
-                if (tid < p.world) {
-                    const unsigned* f = p.flags[p.rank] + xbuf * p.world + tid;
-                    const long long t0 = globaltimer_ns();
-                    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-                        if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 1); break; }
-                    }
-                }
-                __syncthreads();
-                const float* inb = p.inbox[p.rank] + (size_t)(xbuf * p.world) * MP;
-                for (int e = tid; e < MP; e += blockDim.x) {
-                    const int m = e / P;
-                    if (tot_s[m] > 0.f) {
-                        float v = 0.f;
-                        for (int gq = 0; gq < p.world; ++gq) v += ld_relaxed_sys_f32(inb + (size_t)gq * MP + e);
-                        theta_s[e] = v;
-                    }
-                }
+                // a peer that never arrives: raise the (host-visible) error flag and KEEP the old model — never consume a
+                // stale or partial inbox; the host raises at its next metrics read (DriftSim._check_peer_error)
+                if (!ok) { if (p.error_flag) atomicExch(p.error_flag, 1); }
+                else if (!p.skip_aggregate && tot_s[e / P] > 0.f) theta_s[e] = v;
             }
             __syncthreads();
         }
@@ -563,11 +575,12 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
             corr = warp_sum(corr); loss = warp_sum(loss);
             if (lane == 0) {
                 const size_t moff = ((size_t)r * C + c) * 4 + which * 2;
-                if (p.world > 1 && p.metrics_peer[0]) {  // the owner writes this client's row into EVERY rank's buffer
-                    for (int gq = 0; gq < p.world; ++gq) {
-                        st_relaxed_sys_f32(p.metrics_peer[gq] + moff, corr);
-                        st_relaxed_sys_f32(p.metrics_peer[gq] + moff + 1, loss);
-                    }
+                if (p.world > 1 && p.metrics_peer[0]) {
+                    // the owner pushes this client's (correct, loss) pair into EVERY rank's LL staging area as one 16-byte
+                    // store {corr, epoch, loss, epoch}; the tail of the launch compacts the staging area into p.metrics
+                    const unsigned epoch = flag_base + (unsigned)r + 1u;
+                    for (int gq = 0; gq < p.world; ++gq)
+                        st_ll2(reinterpret_cast<uint4*>(p.metrics_peer[gq]) + (moff >> 1), corr, loss, epoch);
                 } else {
                     *reinterpret_cast<float2*>(p.metrics + moff) = make_float2(corr, loss);
                 }
@@ -581,29 +594,31 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
         // (no barrier needed here: θ_s is next written after the __syncthreads that follows local training)
     }
 
-    // ---- multi-GPU: make every rank's metric rows visible everywhere before the host (or the next graph node) reads
-    if (p.world > 1 && p.metrics_peer[0]) {
-        __threadfence_system();
-        if (G > 1) cluster.sync(); else __syncthreads();
-        if (crank == 0) {
-            const unsigned done = flag_base + (unsigned)p.rounds;
-            if (tid < p.world) st_release_sys(p.flags[tid] + 2 * p.world + p.rank, done);
-            if (tid < p.world) {
-                const unsigned* f = p.flags[p.rank] + 2 * p.world + tid;
-                const long long t0 = globaltimer_ns();
-                while ((int)(ld_acquire_sys(f) - done) < 0) {
-                    if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 2); break; }
-                }
+    // ---- multi-GPU: gather the launch's metric rows.  Every (round, client, split) pair arrives as one self-validating
+    //      16-byte LL word from its owner; cluster rank 0 polls this rank's staging area (one-way NVLink latency after the
+    //      slowest peer's evaluation — no fence / flag handshake) and writes the plain [rounds, C, 4] metrics tensor and,
+    //      for the end-to-end graph, the pinned host mirror (posted PCIe writes).
+    if (p.world > 1 && p.metrics_peer[0] && crank == 0) {
+        const uint4* stg = reinterpret_cast<const uint4*>(p.metrics_peer[p.rank]);
+        const long long t0 = globaltimer_ns();
+        for (int e = tid; e < p.rounds * C * 2; e += blockDim.x) {
+            const int c = (e >> 1) % C, which = e & 1;
+            if (t + which >= p.T1) continue;   // nobody evaluates a test split beyond the last time step
+            const unsigned epoch = flag_base + (unsigned)(e / (2 * C)) + 1u;
+            (void)c;
+            uint4 w = ld_ll2(stg + e);
+            bool ok = true;
+            while (w.y != epoch || w.w != epoch) {
+                if (globaltimer_ns() - t0 > p.spin_timeout_ns) { ok = false; break; }
+                w = ld_ll2(stg + e);
             }
-        }
-    }
-    // ---- multi-GPU fused D2H: after the handshake every rank's symmetric metrics buffer holds ALL clients' rows; mirror
-    //      this launch's rows into the pinned host buffer (a few hundred bytes of posted PCIe writes)
-    if (p.world > 1 && p.metrics_peer[0] && p.host_metrics) {
-        __syncthreads();
-        if (crank == 0) {
-            const float* src = p.metrics_peer[p.rank];
-            for (int e = tid; e < p.rounds * C * 4; e += blockDim.x) st_relaxed_sys_f32(p.host_metrics + e, ld_relaxed_sys_f32(src + e));
+            if (!ok) { if (p.error_flag) atomicExch(p.error_flag, 2); continue; }
+            const float2 v = make_float2(__uint_as_float(w.x), __uint_as_float(w.z));
+            *reinterpret_cast<float2*>(p.metrics + 2 * (size_t)e) = v;
+            if (p.host_metrics) {
+                st_relaxed_sys_f32(p.host_metrics + 2 * (size_t)e, v.x);
+                st_relaxed_sys_f32(p.host_metrics + 2 * (size_t)e + 1, v.y);
+            }
         }
     }
     if (p.counters && crank == 0 && tid == 0) { p.counters[0] = round0 + p.rounds; p.counters[1] = (int)(flag_base + (unsigned)p.rounds); }
@@ -696,6 +711,23 @@ int fed_round_small_launch(int kind, int din, int hid, int dout, const RoundPara
     FDB_MLP_SHAPES(FDB_CASE)
 #undef FDB_CASE
     return -1;
+}
+
+template <class Net>
+static int fits_round(int C, int M) {
+    const int CM = C * M, G = 8;   // the launcher may use up to the portable cluster size
+    const SmemLayout L = make_layout<Net>(M, C, (CM + G - 1) / G);
+    return L.total * (int)sizeof(float) <= 227 * 1024;
+}
+
+// 1 when the fused kernel can run this federation: instantiated shape, t_cur < kTmax, shared-memory layout within 227 KB
+int fed_round_small_fits(int kind, int din, int hid, int dout, int C, int M, int t_cur) {
+    if (t_cur >= kTmax) return 0;
+#define FDB_CASE(K, I, H, O) \
+    if (kind == K && din == I && (K == 0 || hid == H) && dout == O) return fits_round<Mlp<K, I, H, O>>(C, M);
+    FDB_MLP_SHAPES(FDB_CASE)
+#undef FDB_CASE
+    return 0;
 }
 
 int fed_round_small_supported(int kind, int din, int hid, int dout) {

@@ -45,9 +45,8 @@ struct RoundParams {
     int warps_per_pair; // 1, 2 or 4 warps cooperate on one (client, model) pair
     // multi-GPU (clients sharded c % world == rank); world == 1 → everything local
     int world, rank;
-    float* inbox[kMaxPeers];     // inbox[g]: this rank's view of peer g's symmetric inbox  [2, world, M*(P)+M]
-    unsigned* flags[kMaxPeers];  // flags[g]:  peer g's flag words [3, world] (2 aggregation parities + metrics epoch)
-    float* metrics_peer[kMaxPeers];  // every rank's (symmetric) metrics buffer, or nullptrs
+    float* inbox[kMaxPeers];     // inbox[g]: this rank's view of peer g's symmetric inbox: LL words {value, epoch} [2, world, M*P] x 8 B
+    float* metrics_peer[kMaxPeers];  // every rank's (symmetric) metrics STAGING area: LL words {corr, epoch, loss, epoch} [rounds, C, 2] x 16 B
     unsigned flag_base;          // monotonically increasing epoch base (per launch)
     long long spin_timeout_ns;   // bail out instead of hanging the GPU if a peer never arrives
     int* error_flag;             // set to nonzero on timeout
@@ -68,6 +67,7 @@ struct SmallLaunchInfo {
 int fed_round_small_launch(int kind, int din, int hid, int dout, const RoundParams& p, int cluster, cudaStream_t stream,
                            SmallLaunchInfo* info);
 int fed_round_small_supported(int kind, int din, int hid, int dout);
+int fed_round_small_fits(int kind, int din, int hid, int dout, int C, int M, int t_cur);
 int mlp_eval_matrix_launch(int kind, int din, int hid, int dout, const float* theta, int theta_stride, int M, const float* X,
                            const int* Y, const int* nsamp, int C, int S, float* correct, float* loss, float* sqerr,
                            cudaStream_t stream);

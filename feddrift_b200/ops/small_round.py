@@ -19,6 +19,22 @@ def supported(kind: str, din: int, hid: int, dout: int) -> bool:
     return ext is not None and bool(ext.fed_round_small_supported(KIND_ID[kind], din, hid, dout))
 
 
+def fits(kind: str, din: int, hid: int, dout: int, C: int, M: int, t_cur: int) -> bool:
+    """True when the fused kernel can run this federation at time step ``t_cur`` (instantiated MLP shape, ``t_cur`` below
+    the kernel's plan-table limit, shared-memory layout within 227 KB); otherwise route to the generic executor."""
+    ext = _ext.load()
+    if ext is None:
+        return True   # CPU reference has no such limits
+    return bool(ext.fed_round_small_fits(KIND_ID[kind], din, hid, dout, int(C), int(M), int(t_cur)))
+
+
+def spin_timeout_ms(st: Dict) -> int:
+    """Cross-GPU spin bound: generous by default (a peer may legitimately be busy for seconds in host-side clustering or
+    a CUDA-graph build); ``FDB_SPIN_TIMEOUT_MS`` / ``st['spin_timeout_ms']`` override it."""
+    import os
+    return int(st.get("spin_timeout_ms") or os.environ.get("FDB_SPIN_TIMEOUT_MS", 60000))
+
+
 def _i32(t: Optional[torch.Tensor], dev) -> Optional[torch.Tensor]:
     if t is None:
         return None
@@ -88,35 +104,31 @@ def run_native(st: Dict, rounds: int, metrics_out: Optional[torch.Tensor] = None
         st["W"] = W = W.to(device=dev, dtype=torch.float32).contiguous()
     ens_w = _f32(st.get("ens_w"), dev)
     use_adam = st.get("optimizer", "adam") != "sgd"
-    mg0 = st.get("multi_gpu")
     if metrics_out is None:
-        if mg0 and mg0.get("metrics_buf") is not None:
-            metrics_out = mg0["metrics_buf"][: rounds * C * 4].view(rounds, C, 4)
-        else:
-            metrics_out = torch.zeros(rounds, C, 4, dtype=torch.float32, device=dev)
+        metrics_out = torch.zeros(rounds, C, 4, dtype=torch.float32, device=dev)
     lr = st["lr"]
     lr_dev = lr if isinstance(lr, torch.Tensor) else None
     Lmax = int(cache["train_index"].shape[2]) if cache["train_index"] is not None else 0
-    mg = st.get("multi_gpu")  # dict(world, rank, inbox_ptrs, flag_ptrs, flag_base, error_flag)
+    mg = st.get("multi_gpu")  # dict(world, rank, inbox_ptrs, metrics_ptrs, flag_base, error_flag)
     world = int(mg["world"]) if mg else 1
     icfg = [T1, C, S, M, Lmax, int(st["batch_size"]), int(st["epochs"]), int(st["t_cur"]), int(rounds), int(st["round0"]),
             int(st["seed"]) & 0xFFFFFFFF, int(use_adam), MODE_ID[st.get("sample_mode", "pool")],
             1 if st.get("n_mode", "batches") == "samples" else 0, int(bool(st.get("recluster_hard", False))),
             int(st.get("ens_mode", 0) or 0), int(bool(st.get("skip_aggregate", False))), world,
             int(mg["rank"]) if mg else 0, int(mg["flag_base"]) if mg else 0, int(st.get("cluster", 0) or cache["cluster"]),
-            int(st.get("spin_timeout_ms", 2000)), int(st.get("warps_per_pair", 0) or cache["wpp"])]
+            spin_timeout_ms(st), int(st.get("warps_per_pair", 0) or cache["wpp"])]
     fcfg = [float(lr) if lr_dev is None else 0.0, float(st["wd"]), 0.9, 0.999, 1e-8]
     peer_metrics = []
     if mg and mg.get("metrics_ptrs") is not None:
-        # the caller's metrics_out must be (a view at offset 0 of) this rank's symmetric metrics buffer
-        assert metrics_out.data_ptr() == mg["metrics_buf"].data_ptr(), "multi-GPU metrics must live in the symmetric buffer"
+        # every rank's LL staging area (symmetric); the kernel compacts this launch's rows into the plain metrics_out
+        assert rounds <= int(mg["metrics_rounds"]), "block larger than the symmetric metrics staging area"
         peer_metrics = list(mg["metrics_ptrs"])
     info = ext.fed_round_small(
         KIND_ID[st["kind"]], int(st["din"]), int(st["hid"]), int(st["dout"]), cache["X"], cache["Y"], cache["nsamp"], W, theta,
         int(st.get("theta_stride", theta.stride(0))), st.get("opt_m"), st.get("opt_v"), st.get("opt_vmax"), st["opt_step"],
         cache["train_index"], cache["train_count"], cache["feat_mask"], cache["eval_train_model"], cache["eval_test_model"],
         ens_w, st.get("client_out"), lr_dev, metrics_out, st.get("timers"), fcfg, icfg,
-        list(mg["inbox_ptrs"]) if mg else [], list(mg["flag_ptrs"]) if mg else [], mg.get("error_flag") if mg else None,
+        list(mg["inbox_ptrs"]) if mg else [], mg.get("error_flag") if mg else None,
         st.get("counters"), peer_metrics, [int(v) for v in st["host_io"]] if st.get("host_io") else [])
     if mg:
         mg["flag_base"] = int(mg["flag_base"]) + rounds

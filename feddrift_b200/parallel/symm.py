@@ -2,10 +2,12 @@
 
 Every rank allocates one identically-shaped buffer through ``torch.distributed._symmetric_memory`` (CUDA VMM +
 fabric handles under the hood); after the rendezvous each rank holds a device pointer to EVERY peer's buffer, so
-the kernel can ``st.global`` partial sums straight into the peers' inboxes over NVLink and publish
-``st.release.sys`` epoch flags — no NCCL call on the aggregate/broadcast path (BASELINE.json north star).
+the kernel can store partial sums straight into the peers' inboxes over NVLink — no NCCL call on the
+aggregate/broadcast path (BASELINE.json north star).  Both areas use the LL ("low latency") format: payload and round
+epoch travel in the same 8- / 16-byte store, so there are no fences, no flag words and no round trips.
 
-Layout of the per-rank buffer (floats):   inbox [2 (parity)] [world] [M·P]   |   flags (u32) [2] [world]
+Layout of the per-rank buffer:   inbox  uint2 {value, epoch}             [2 (parity)] [world] [M·P]
+                                 staging uint4 {corr, epoch, loss, epoch} [max_rounds] [C] [2 (train | test)]
 """
 from __future__ import annotations
 
@@ -24,23 +26,20 @@ def _rendezvous(numel: int, device) -> Dict:
 
 
 def attach_multi_gpu(sim, world: int, rank: int) -> None:
-    """Give ``sim`` the symmetric inbox/flag pointers; clients are then sharded ``c % world == rank``."""
+    """Give ``sim`` the symmetric inbox / metrics-staging pointers; clients are then sharded ``c % world == rank``."""
     MP = sim.M * sim.bank.P
-    inbox_floats = 2 * world * MP
-    inbox_floats = (inbox_floats + 31) // 32 * 32  # keep the flag words on their own 128-byte line
-    flag_words = 3 * world
-    flag_floats = max((flag_words + 31) // 32 * 32, 32)
+    inbox_floats = 2 * (2 * world * MP)                      # 8-byte LL words
+    inbox_floats = (inbox_floats + 31) // 32 * 32            # staging area starts on its own 128-byte line
     max_rounds = int(getattr(sim.args, "max_rounds_per_launch", 0) or max(sim.args.comm_round, 256))
-    metric_floats = max_rounds * sim.C * 4
-    r = _rendezvous(inbox_floats + flag_floats + metric_floats, sim.device)
+    staging_floats = 4 * (max_rounds * sim.C * 2)            # 16-byte LL words
+    r = _rendezvous(inbox_floats + staging_floats, sim.device)
     base = r["ptrs"]
-    moff = inbox_floats + flag_floats
     sim.multi = {
         "world": world, "rank": rank, "flag_base": 0,
-        "inbox_ptrs": base, "flag_ptrs": [p + 4 * inbox_floats for p in base],
-        "metrics_ptrs": [p + 4 * moff for p in base], "metrics_buf": r["buf"][moff:moff + metric_floats],
-        "metrics_rounds": max_rounds,
-        "error_flag": torch.zeros(1, dtype=torch.int32, device=sim.device),
+        "inbox_ptrs": base, "metrics_ptrs": [p + 4 * inbox_floats for p in base], "metrics_rounds": max_rounds,
+        # pinned + device-mapped: the kernel raises it with a system-scope atomic on a spin timeout and the host can test
+        # it after any stream sync without another device round trip
+        "error_flag": torch.zeros(1, dtype=torch.int32).pin_memory(),
         "_keepalive": r,
     }
     torch.cuda.synchronize()
@@ -48,6 +47,10 @@ def attach_multi_gpu(sim, world: int, rank: int) -> None:
 
 
 def check_error(sim) -> None:
+    """Raise if the fused kernel gave up waiting for a peer (call after a stream sync; reads pinned host memory)."""
     m = getattr(sim, "multi", None)
-    if m is not None and int(m["error_flag"].item()) != 0:
-        raise RuntimeError("fed_round_small: a peer rank never published its round flag (spin timeout)")
+    if m is not None and int(m["error_flag"][0]) != 0:
+        code = int(m["error_flag"][0])
+        raise RuntimeError(f"fed_round_small: rank {m['rank']} gave up waiting for a peer ("
+                           f"{'aggregation inbox' if code == 1 else 'metrics rows'} never arrived within the spin timeout); "
+                           "the cluster models were NOT updated from the incomplete inbox")

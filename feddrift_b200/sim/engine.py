@@ -190,7 +190,7 @@ class DriftSim:
                 block = min(block, rpl)
             if self.multi is not None:
                 block = min(block, int(self.multi["metrics_rounds"]))
-            if self.spec is not None and self.algo.fused_ok() and not getattr(self, "shard_clients", False):
+            if self._use_fused():
                 st = self._small_state()
                 st["round0"] = self.round_in_step
                 out = ops.fed_round_small(st, block)
@@ -207,6 +207,22 @@ class DriftSim:
         self.timings["rounds_s"] += time.perf_counter() - t0
         return last
 
+    def _use_fused(self) -> bool:
+        """Route a block of rounds: the fused persistent kernel when the federation is a small MLP it can hold (shape
+        instantiated, ``t < 64`` plan-table limit, shared-memory layout within 227 KB), the generic executor otherwise."""
+        if self.spec is None or not self.algo.fused_ok() or getattr(self, "shard_clients", False):
+            return False
+        if self.device.type != "cuda":
+            return True
+        from ..ops import small_round
+        s = self.spec
+        return small_round.fits(s["kind"], s["in"], s["hidden"], s["out"], self.C, self.M, self.t)
+
+    def _check_peer_error(self) -> None:
+        if self.multi is not None:
+            from ..parallel.symm import check_error
+            check_error(self)
+
     # ------------------------------------------------------------------ device-only / end-to-end single rounds
     def run_rounds_device(self, n: int) -> torch.Tensor:
         """Launch ``n`` fused rounds and leave the per-round metrics ON DEVICE (no host sync, no logging).
@@ -215,14 +231,11 @@ class DriftSim:
         st["round0"] = self.round_in_step
         if self.device.type == "cuda":
             from ..ops import small_round
-            if self.multi is not None:
-                assert n <= int(self.multi["metrics_rounds"]), "block larger than the symmetric metrics buffer"
-                out = small_round.run_native(st, n, None)  # rows of every rank land in the symmetric buffer
-            else:
-                buf = getattr(self, "_metrics_buf", None)
-                if buf is None or buf.shape[0] < n:
-                    buf = self._metrics_buf = torch.zeros(max(n, 64), self.C, 4, dtype=torch.float32, device=self.device)
-                out = small_round.run_native(st, n, buf[:n])
+            buf = getattr(self, "_metrics_buf", None)
+            if buf is None or buf.shape[0] < n:
+                buf = self._metrics_buf = torch.zeros(max(n, 64), self.C, 4, dtype=torch.float32, device=self.device)
+            # multi-GPU: the owners push their rows into every rank's LL staging area; the kernel compacts them into buf
+            out = small_round.run_native(st, n, buf[:n])
         else:
             out = ops.fed_round_small(st, n)
         self.round_in_step += n
@@ -369,6 +382,7 @@ class DriftSim:
         return self._round_result(hm.numpy(), log)
 
     def _round_result(self, m, log: bool) -> Dict:
+        self._check_peer_error()
         t = self.t
         nn_ = getattr(self, "_counts_tot", None)
         if nn_ is None or nn_[0] != t:
@@ -387,6 +401,7 @@ class DriftSim:
     def _flush_metrics(self, out: Dict[str, torch.Tensor], r0: int, n: int) -> Dict:
         """One D2H copy per block; emits the reference's wandb keys for every tested round."""
         met = out["metrics"].detach().to("cpu", torch.float64).numpy()  # [n, C, 4]
+        self._check_peer_error()
         cnt = out["counts"].detach().to("cpu", torch.float64).numpy()   # [C, 2]
         a = self.args
         ntr, nte = max(cnt[:, 0].sum(), 1.0), max(cnt[:, 1].sum(), 1.0)

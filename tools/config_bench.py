@@ -13,23 +13,8 @@ sys.path.insert(0, ".")
 from feddrift_b200.sim import DriftSim, make_args  # noqa: E402
 from feddrift_b200.utils.metrics import MetricsSink  # noqa: E402
 
-CONFIGS = {
-    "cfg2_sea_fnn_100clients_feddrift": dict(model="fnn", dataset="sea", client_num_in_total=100, client_num_per_round=100,
-                                             concept_drift_algo="softcluster", concept_drift_algo_arg="H_A_C_1_10_0", concept_num=4,
-                                             change_points="A", sample_num=100, batch_size=500, comm_round=40),
-    "cfg3_mnist_cnn_64clients_ifca": dict(model="cnn", dataset="MNIST", client_num_in_total=64, client_num_per_round=64,
-                                          concept_drift_algo="softclusterwin-1", concept_drift_algo_arg="hard-r", concept_num=4,
-                                          change_points="B", sample_num=64, batch_size=32, comm_round=3),
-    "cfg4_cifar_resnet18_32clients_aue": dict(model="resnet18", dataset="cifar10", client_num_in_total=32, client_num_per_round=32,
-                                              concept_drift_algo="aue", concept_drift_algo_arg="", concept_num=2, ensemble_window=2,
-                                              change_points="A", sample_num=32, batch_size=32, comm_round=2),
-    "cfg5_shakespeare_lstm_128clients_win1": dict(model="rnn", dataset="shakespeare", client_num_in_total=128, client_num_per_round=128,
-                                                  concept_drift_algo="win-1", concept_drift_algo_arg="", concept_num=2,
-                                                  change_points="A", sample_num=32, batch_size=16, comm_round=2),
-    "cfg5_shakespeare_lstm_128clients_feddrift": dict(model="rnn", dataset="shakespeare", client_num_in_total=128, client_num_per_round=128,
-                                                      concept_drift_algo="softcluster", concept_drift_algo_arg="H_A_C_1_10_0", concept_num=2,
-                                                      change_points="A", sample_num=32, batch_size=16, comm_round=2),
-}
+from feddrift_b200.experiments.configs import CONFIGS  # noqa: E402
+
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 dev = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
 torch.cuda.set_device(dev)

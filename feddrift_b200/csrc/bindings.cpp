@@ -425,6 +425,57 @@ void graph_launch_sync(int64_t exec, bool sync) {
     }
 }
 
+// ---------------------------------------------------------------------------------- persistent LSTM (lstm_tc.cu)
+// offs = {emb, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2, w_hh2, b_ih2, b_hh2} element offsets inside a parameter row.
+static fdb::LstmArgs lstm_args(const Tensor& params, const Tensor& row_off, const std::vector<int64_t>& offs, const Tensor& tokens,
+                               const Tensor& gates, const Tensor& cst, const Tensor& hhist, const Tensor& hlast, int64_t E) {
+    CHECK_CUDA_F32(params); CHECK_CUDA_I32(tokens); CHECK_CUDA_F32(gates); CHECK_CUDA_F32(cst); CHECK_CUDA_F32(hlast);
+    TORCH_CHECK(row_off.is_cuda() && row_off.scalar_type() == torch::kInt64, "row_off must be a CUDA int64 tensor");
+    TORCH_CHECK(hhist.is_cuda() && hhist.scalar_type() == torch::kBFloat16, "hhist must be CUDA bf16");
+    TORCH_CHECK(offs.size() == 9, "need 9 parameter offsets");
+    TORCH_CHECK(tokens.dim() == 3 && tokens.size(1) == 16 && tokens.is_contiguous(), "tokens must be [npairs, 16, T] contiguous");
+    const int64_t np = tokens.size(0), T = tokens.size(2);
+    TORCH_CHECK(row_off.numel() == np && E >= 1 && E <= 16 && T >= 1, "lstm2: bad sizes");
+    TORCH_CHECK(gates.numel() == np * 2 * T * 16 * 1024 && cst.numel() == np * 2 * T * 16 * 256 &&
+                hhist.numel() == np * 2 * (T + 1) * 16 * 256 && hlast.numel() == np * 16 * 256, "lstm2: workspace sizes");
+    fdb::LstmArgs a{};
+    a.params = params.data_ptr<float>();
+    a.row_off = reinterpret_cast<const long long*>(row_off.data_ptr<int64_t>());
+    a.off_emb = offs[0]; a.off_wih1 = offs[1]; a.off_whh1 = offs[2]; a.off_bih1 = offs[3]; a.off_bhh1 = offs[4];
+    a.off_wih2 = offs[5]; a.off_whh2 = offs[6]; a.off_bih2 = offs[7]; a.off_bhh2 = offs[8];
+    a.tokens = tokens.data_ptr<int>();
+    a.gates = gates.data_ptr<float>(); a.cst = cst.data_ptr<float>(); a.hhist = hhist.data_ptr(); a.hlast = hlast.data_ptr<float>();
+    a.T = (int)T; a.E = (int)E;
+    return a;
+}
+
+void lstm2_forward(Tensor params, Tensor row_off, std::vector<int64_t> offs, Tensor tokens, Tensor gates, Tensor cst, Tensor hhist,
+                   Tensor hlast, int64_t E) {
+    c10::cuda::CUDAGuard guard(params.device());
+    fdb::LstmArgs a = lstm_args(params, row_off, offs, tokens, gates, cst, hhist, hlast, E);
+    CHECK_OK(fdb::lstm2_fwd_launch(a, (int)tokens.size(0), cur_stream()), "lstm2_fwd (tcgen05 cluster kernel)");
+}
+
+void lstm2_backward(Tensor params, Tensor row_off, std::vector<int64_t> offs, Tensor tokens, Tensor gates, Tensor cst, Tensor hhist,
+                    Tensor hlast, int64_t E, c10::optional<Tensor> dh2_last, c10::optional<Tensor> dh2_all, Tensor dgates) {
+    c10::cuda::CUDAGuard guard(params.device());
+    fdb::LstmArgs a = lstm_args(params, row_off, offs, tokens, gates, cst, hhist, hlast, E);
+    const int64_t np = tokens.size(0), T = tokens.size(2);
+    TORCH_CHECK(dgates.is_cuda() && dgates.scalar_type() == torch::kBFloat16 && dgates.numel() == np * 2 * T * 16 * 1024, "dgates workspace");
+    if (dh2_all.has_value() && dh2_all->defined()) {
+        CHECK_CUDA_F32(*dh2_all);
+        TORCH_CHECK(dh2_all->numel() == np * T * 16 * 256 && dh2_all->is_contiguous(), "dh2_all must be [npairs, T, 16, 256]");
+        a.dh2_all = dh2_all->data_ptr<float>();
+    } else {
+        TORCH_CHECK(dh2_last.has_value() && dh2_last->defined(), "lstm2_backward needs dh2_last or dh2_all");
+        CHECK_CUDA_F32(*dh2_last);
+        TORCH_CHECK(dh2_last->numel() == np * 16 * 256 && dh2_last->is_contiguous(), "dh2_last must be [npairs, 16, 256]");
+        a.dh2_last = dh2_last->data_ptr<float>();
+    }
+    a.dgates = dgates.data_ptr();
+    CHECK_OK(fdb::lstm2_bwd_launch(a, (int)np, cur_stream()), "lstm2_bwd (tcgen05 cluster kernel)");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -458,4 +509,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("graph_launch_sync", &graph_launch_sync);
     m.def("im2col_bf16", &im2col_bf16);
     m.def("col2im", &col2im);
+    m.def("lstm2_forward", &lstm2_forward);
+    m.def("lstm2_backward", &lstm2_backward);
 }

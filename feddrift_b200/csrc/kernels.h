@@ -51,4 +51,22 @@ int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M,
                 cudaStream_t stream, float* splitk_ws = nullptr);
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
                    cudaStream_t stream);
+// lstm_tc.cu : persistent cluster-resident 2-layer LSTM(256) forward / BPTT over many (client, model) pairs per launch
+struct LstmArgs {
+    const float* params;          // parameter arena base
+    const long long* row_off;     // [npairs] element offset of each pair's flat parameter row
+    long long off_emb, off_wih1, off_whh1, off_bih1, off_bhh1, off_wih2, off_whh2, off_bih2, off_bhh2;   // offsets inside a row
+    const int* tokens;            // [npairs, 16, T] int32 token ids (rows beyond the real batch are padding)
+    float* gates;                 // [npairs, 2, T, 16, 4, 256] activated gates (i, f, g, o)
+    float* cst;                   // [npairs, 2, T, 16, 256]    cell states
+    void* hhist;                  // [npairs, 2, T+1, 16, 256]  bf16 hidden states, index 0 = h_{-1} = 0
+    float* hlast;                 // [npairs, 16, 256]          fp32 h2_{T-1}
+    // backward only
+    const float* dh2_last;        // [npairs, 16, 256] gradient wrt h2_{T-1}            (used when dh2_all == nullptr)
+    const float* dh2_all;         // [npairs, T, 16, 256] gradient wrt every h2_t, or nullptr
+    void* dgates;                 // [npairs, 2, T, 16, 1024] bf16 pre-activation gate gradients (PyTorch row order)
+    int T, E;
+};
+int lstm2_fwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream);
+int lstm2_bwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream);
 }  // namespace fdb

@@ -1,0 +1,570 @@
+// lstm_tc — persistent, cluster-resident 2-layer LSTM (hidden 256) forward + BPTT for RNN_OriginalFedAvg
+// (reference: fedml_api/model/nlp/rnn.py:18-33 — Embedding(90,8) → 2×LSTM(256, batch_first) → Linear on the last step;
+// the reference runs it through cuDNN's per-timestep kernels: ~10 launches per timestep per layer per direction).
+//
+// ONE launch runs the whole sequence for MANY (client, model) pairs: grid = npairs × 8 CTAs, one thread-block CLUSTER of 8
+// CTAs per pair (and per 16-row batch chunk).  CTA j of a cluster owns hidden units [32j, 32j+32) of BOTH layers, i.e. 128
+// gate rows (i, f, g, o × 32 units) per layer.
+//
+// Forward (lstm2_fwd_kernel):
+//   * the CTA's weight slices live in TENSOR MEMORY for the whole sequence: A1 = [W_hh1 | W_ih1] (128 × 272, 136 TMEM
+//     columns) and A2 = [W_ih2 | W_hh2] (128 × 512, 256 columns), written once with tcgen05.st as packed bf16 pairs; shared
+//     memory only holds the activations;
+//   * every timestep is one tcgen05.mma chain per layer in the TS form (A from TMEM, B = activations [16 × K] from
+//     shared memory in the no-swizzle K-major core-matrix layout, D = 128 gate rows × 16 batch columns fp32 in TMEM):
+//     gatesᵀ = W_slice · [x_t | h_{t-1}]ᵀ — the recurrent GEMM runs "swapped" so that the 128-row MMA is full even at batch 16;
+//   * layers are WAVEFRONT-pipelined: phase p computes layer 1 at time p and layer 2 at time p-1 (both only need h1_{p-1}),
+//     so there is one cluster exchange per timestep instead of two;
+//   * the epilogue (tcgen05.ld → bias → σ/tanh → cell update, c kept in registers) produces the CTA's 32 new hidden units
+//     for 16 batch rows, stages them as bf16 in the operand layout and BROADCASTS the 1-KB slice into all 8 CTAs' next-step
+//     operand buffers with cp.async.bulk shared::cta → shared::cluster (DSMEM); arrival is tracked by an mbarrier
+//     transaction count in each destination — no cluster barrier in the time loop;
+//   * gate activations, cell states and hidden states are written to a history workspace for BPTT.
+//
+// Backward (lstm2_bwd_kernel): same ownership, reversed wavefront.  TMEM holds the TRANSPOSED slices (W_hh2ᵀ, W_ih2ᵀ,
+// W_hh1ᵀ: 256 hidden rows × 128 own gate rows each, two 128-lane tiles per matrix).  Per phase: sum the 8 partial dh blocks
+// that arrived in the inbox (fixed order → deterministic), elementwise LSTM backward for the own units (dc carried in
+// registers), dG (bf16) → smem operand + global history, partial dhᵀ[256 × 16] = W_sliceᵀ · dGᵀ on tcgen05, tcgen05.ld and
+// a DSMEM bulk REDUCE-SCATTER of the 2-KB blocks to the owners of those hidden units.  Weight gradients are GEMMs over the
+// saved histories (dW = dGᵀ · H with the MN-major tcgen05 GEMM of gemm_tc.cu), outside this file.
+//
+// All waits are bounded (trap after 4 s).  bf16 operands, fp32 accumulation, fp32 cell state / gates / gradients.
+#include <cooperative_groups.h>
+
+#include "kernels.h"
+#include "tc05.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fdb {
+
+namespace lstm {
+constexpr int H = 256, CL = 8, U = 32, NB = 16, KX = 16;
+constexpr int kThreads = 128;
+// forward TMEM map (columns)
+constexpr uint32_t A1_COL = 0, A1_XCOL = 128, A2_COL = 136, D1_COL = 392, D2_COL = 424, F_TMEM = 512;
+// backward TMEM map: three transposed matrices × 2 tiles × 64 columns, then 6 accumulators × 16 columns
+constexpr uint32_t BT_HH2 = 0, BT_IH2 = 128, BT_HH1 = 256, BD_REC2 = 384, BD_IN1 = 416, BD_REC1 = 448, B_TMEM = 512;
+// instruction descriptor: D fp32, A/B bf16, both K-major, N = 16, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t kLBO = (NB / 8) * 128, kSBO = 128;   // no-swizzle K-major: [k_core][n_core][8 rows][16 B]
+}  // namespace lstm
+
+// element offset of (batch row b, reduction index k) in a no-swizzle K-major operand tile of 16 rows
+FDB_DEVICE int op_off(int b, int k) { return (((k >> 3) * (lstm::NB / 8) + (b >> 3)) << 6) + ((b & 7) << 3) + (k & 7); }
+
+FDB_DEVICE uint64_t make_desc_nosw(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lstm::kLBO >> 4) << 16;
+    d |= (uint64_t)(lstm::kSBO >> 4) << 32;
+    d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
+    return d;                          // layout type 0 = SWIZZLE_NONE
+}
+// D[tmem] (+)= A[tmem] · B[smem]   (TS form: the A operand is read from tensor memory)
+FDB_DEVICE void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+FDB_DEVICE void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31]) : "memory");
+}
+FDB_DEVICE void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+FDB_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+FDB_DEVICE void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+FDB_DEVICE uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+// DSMEM bulk copy: this CTA's shared memory → a cluster peer's shared memory; completion = tx bytes on the PEER's mbarrier
+FDB_DEVICE void bulk_copy_s2c(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes, uint32_t mbar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
+FDB_DEVICE void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (globaltimer_ns() - t0 > 4000000000LL) __trap();
+    }
+}
+FDB_DEVICE uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x (low half) = lo
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+FDB_DEVICE float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+FDB_DEVICE float tanh_f(float x) { return 2.f / (1.f + __expf(-2.f * x)) - 1.f; }
+
+// 64 consecutive fp32 weights of one row → 32 packed bf16 pairs → 32 TMEM columns of this thread's lane
+FDB_DEVICE void load_row_chunk_to_tmem(const float* __restrict__ src, uint32_t taddr) {
+    uint32_t v[32];
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(src) + j);
+            v[2 * j] = pack_bf16(f.x, f.y);
+            v[2 * j + 1] = pack_bf16(f.z, f.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = pack_bf16(__ldg(src + 2 * j), __ldg(src + 2 * j + 1));
+    }
+    tmem_st_x32(taddr, v);
+}
+
+// ======================================================================================================= forward
+__global__ void __cluster_dims__(lstm::CL, 1, 1) __launch_bounds__(lstm::kThreads, 1)
+lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
+    using namespace lstm;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int pair = blockIdx.x / CL;
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int T = a.T, E = a.E;
+
+    // ---- shared memory carve-up
+    __nv_bfloat16* H1s = reinterpret_cast<__nv_bfloat16*>(smem_raw);            // [2][NB*256]
+    __nv_bfloat16* H2s = H1s + 2 * NB * H;                                       // [2][NB*256]
+    __nv_bfloat16* Xs = H2s + 2 * NB * H;                                        // [2][NB*16]
+    __nv_bfloat16* stage = Xs + 2 * NB * KX;                                     // [2 parities][2 layers][NB*32]
+    float* act_s = reinterpret_cast<float*>(stage + 2 * 2 * NB * U);             // [2 layers][4 gates][NB][32]
+    uint64_t* hbar = reinterpret_cast<uint64_t*>(act_s + 2 * 4 * NB * U);        // [2]
+    uint64_t* mma_bar = hbar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+    const float* prow = a.params + a.row_off[pair];
+    const float* w_ih1 = prow + a.off_wih1;
+    const float* w_hh1 = prow + a.off_whh1;
+    const float* w_ih2 = prow + a.off_wih2;
+    const float* w_hh2 = prow + a.off_whh2;
+    const float* emb = prow + a.off_emb;
+    const int* tok = a.tokens + (size_t)pair * NB * T;
+
+    if (tid == 0) {
+        mbar_init(hbar + 0, 1); mbar_init(hbar + 1, 1); mbar_init(mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(F_TMEM));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // zero the operand buffers (h_{-1} = 0, padded x columns = 0) and write x_0
+    for (int i = tid; i < (2 * NB * H * 2 + 2 * NB * KX) / 2; i += kThreads) reinterpret_cast<uint32_t*>(H1s)[i] = 0u;
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+    const uint32_t lane_addr = tmem + ((uint32_t)(w * 32) << 16);
+
+    // ---- weights → TMEM (this thread owns gate row r = tid: gate w, local unit l)
+    const int R = w * H + crank * U + l;              // row of the PyTorch [4H, K] weight matrices
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_hh1 + (size_t)R * H + 64 * c, lane_addr + A1_COL + 32 * c);
+    {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float lo = (2 * j < E) ? __ldg(w_ih1 + (size_t)R * E + 2 * j) : 0.f;
+            const float hi = (2 * j + 1 < E) ? __ldg(w_ih1 + (size_t)R * E + 2 * j + 1) : 0.f;
+            v[j] = pack_bf16(lo, hi);
+        }
+        tmem_st_x8(lane_addr + A1_XCOL, v);
+    }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_ih2 + (size_t)R * H + 64 * c, lane_addr + A2_COL + 32 * c);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_hh2 + (size_t)R * H + 64 * c, lane_addr + A2_COL + 128 + 32 * c);
+    tmem_st_wait();
+    const float bias1 = __ldg(prow + a.off_bih1 + R) + __ldg(prow + a.off_bhh1 + R);
+    const float bias2 = __ldg(prow + a.off_bih2 + R) + __ldg(prow + a.off_bhh2 + R);
+
+    // x_0 → Xs[0]
+    for (int i = tid; i < NB * KX; i += kThreads) {
+        const int b = i / KX, k = i % KX;
+        const float v = (k < E) ? __ldg(emb + (size_t)tok[b * T + 0] * E + k) : 0.f;
+        Xs[op_off(b, k)] = __float2bfloat16(v);
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    cluster.sync();            // every CTA's barriers / buffers are initialised before any peer writes into them
+    tcgen05_fence_after();
+
+    // cell-phase ownership: unit ul = l, batch rows b = w + 4 i
+    float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int unit = crank * U + l;
+    float* gates_p = a.gates + (size_t)pair * 2 * T * NB * 4 * H;
+    float* cst_p = a.cst + (size_t)pair * 2 * T * NB * H;
+    __nv_bfloat16* hh_p = reinterpret_cast<__nv_bfloat16*>(a.hhist) + (size_t)pair * 2 * (T + 1) * NB * H;
+    // history row 0 (h_{-1} = 0) is zeroed by the host once; rows t+1 are written below
+
+    for (int p = 0; p <= T; ++p) {
+        const bool doL1 = p < T, doL2 = p >= 1;
+        if (p >= 1) mbar_wait_long(hbar + ((p - 1) & 1), ((p - 1) >> 1) & 1);   // h1_{p-1} (and h2_{p-2}) from all 8 CTAs
+        if (tid == 0) {
+            tcgen05_fence_after();
+            const uint32_t h1prev = smem_u32(H1s + ((p + 1) & 1) * NB * H);     // h1_{p-1}
+            if (doL1) {
+#pragma unroll
+                for (int s = 0; s < 16; ++s)
+                    umma_ts_f16(tmem + D1_COL, tmem + A1_COL + 8 * s, make_desc_nosw(h1prev + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                umma_ts_f16(tmem + D1_COL, tmem + A1_XCOL, make_desc_nosw(smem_u32(Xs + (p & 1) * NB * KX)), kIdesc, 1u);
+            }
+            if (doL2) {
+                const uint32_t h2prev = smem_u32(H2s + (p & 1) * NB * H);       // h2_{p-2}
+#pragma unroll
+                for (int s = 0; s < 16; ++s)
+                    umma_ts_f16(tmem + D2_COL, tmem + A2_COL + 8 * s, make_desc_nosw(h1prev + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+#pragma unroll
+                for (int s = 0; s < 16; ++s)
+                    umma_ts_f16(tmem + D2_COL, tmem + A2_COL + 128 + 8 * s, make_desc_nosw(h2prev + s * 2 * kLBO), kIdesc, 1u);
+            }
+            tcgen05_commit(mma_bar);
+        }
+        mbar_wait_long(mma_bar, p & 1);
+        tcgen05_fence_after();
+
+        // ---- epilogue: this thread = gate row (gate w, unit l); 16 batch columns
+        if (doL1) {
+            float z[16];
+            tmem_ld_x16(lane_addr + D1_COL, z);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float x = z[b] + bias1;
+                act_s[((0 * 4 + w) * NB + b) * U + l] = (w == 2) ? tanh_f(x) : sigmoid_f(x);
+            }
+        }
+        if (doL2) {
+            float z[16];
+            tmem_ld_x16(lane_addr + D2_COL, z);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const float x = z[b] + bias2;
+                act_s[((1 * 4 + w) * NB + b) * U + l] = (w == 2) ? tanh_f(x) : sigmoid_f(x);
+            }
+        }
+        tcgen05_fence_before();
+        __syncthreads();
+
+        // ---- cell update for the own 32 units × 16 rows; stage the bf16 slice in operand layout
+        __nv_bfloat16* st1 = stage + ((p & 1) * 2 + 0) * NB * U;
+        __nv_bfloat16* st2 = stage + ((p & 1) * 2 + 1) * NB * U;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = w + 4 * i;
+            if (doL1) {
+                const float gi = act_s[((0 * 4 + 0) * NB + b) * U + l], gf = act_s[((0 * 4 + 1) * NB + b) * U + l];
+                const float gg = act_s[((0 * 4 + 2) * NB + b) * U + l], go = act_s[((0 * 4 + 3) * NB + b) * U + l];
+                c1[i] = gf * c1[i] + gi * gg;
+                const float h = go * tanh_f(c1[i]);
+                const size_t row = ((size_t)(0 * T + p) * NB + b);
+                float* g = gates_p + row * 4 * H + unit;
+                g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
+                cst_p[row * H + unit] = c1[i];
+                const __nv_bfloat16 hb = __float2bfloat16(h);
+                hh_p[((size_t)(0 * (T + 1) + p + 1) * NB + b) * H + unit] = hb;
+                st1[op_off(b, l)] = hb;     // k_core = l/8 local to the slice
+            }
+            if (doL2) {
+                const int t2 = p - 1;
+                const float gi = act_s[((1 * 4 + 0) * NB + b) * U + l], gf = act_s[((1 * 4 + 1) * NB + b) * U + l];
+                const float gg = act_s[((1 * 4 + 2) * NB + b) * U + l], go = act_s[((1 * 4 + 3) * NB + b) * U + l];
+                c2[i] = gf * c2[i] + gi * gg;
+                const float h = go * tanh_f(c2[i]);
+                const size_t row = ((size_t)(1 * T + t2) * NB + b);
+                float* g = gates_p + row * 4 * H + unit;
+                g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
+                cst_p[row * H + unit] = c2[i];
+                const __nv_bfloat16 hb = __float2bfloat16(h);
+                hh_p[((size_t)(1 * (T + 1) + t2 + 1) * NB + b) * H + unit] = hb;
+                st2[op_off(b, l)] = hb;
+                if (t2 == T - 1) a.hlast[((size_t)pair * NB + b) * H + unit] = h;
+            }
+        }
+        if (p + 1 < T) {   // x_{p+1} → Xs[(p+1)&1]
+            __nv_bfloat16* xd = Xs + ((p + 1) & 1) * NB * KX;
+            for (int i = tid; i < NB * KX; i += kThreads) {
+                const int b = i / KX, k = i % KX;
+                const float v = (k < E) ? __ldg(emb + (size_t)tok[b * T + p + 1] * E + k) : 0.f;
+                xd[op_off(b, k)] = __float2bfloat16(v);
+            }
+        }
+        fence_proxy_async_smem();   // generic-proxy writes (stage, Xs) → visible to the async proxy (bulk copy, tcgen05)
+        __syncthreads();
+        if (p < T && tid == 0) {
+            // ---- all-gather: my 1-KB slices → every CTA's next-step operand buffers (incl. my own)
+            const uint32_t bytes_each = NB * U * 2;
+            mbar_expect_tx(hbar + (p & 1), CL * bytes_each * ((doL1 ? 1u : 0u) + (doL2 ? 1u : 0u)));
+            const uint32_t bar = smem_u32(hbar + (p & 1));
+            const uint32_t d1 = smem_u32(H1s + (p & 1) * NB * H) + crank * bytes_each;         // h1_p slot of my units
+            const uint32_t d2 = smem_u32(H2s + ((p + 1) & 1) * NB * H) + crank * bytes_each;   // h2_{p-1}
+#pragma unroll 1
+            for (int d = 0; d < CL; ++d) {
+                const uint32_t rbar = mapa_u32(bar, d);
+                if (doL1) bulk_copy_s2c(mapa_u32(d1, d), smem_u32(st1), bytes_each, rbar);
+                if (doL2) bulk_copy_s2c(mapa_u32(d2, d), smem_u32(st2), bytes_each, rbar);
+            }
+        }
+    }
+    // ---- teardown: nobody may exit while peers still copy into its shared memory
+    tcgen05_fence_before();
+    cluster.sync();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(F_TMEM));
+}
+
+// ======================================================================================================= backward
+// 64 own gate rows (r0 .. r0+63) of column `k` of W → 32 packed pairs → 32 TMEM columns (transposed slice)
+FDB_DEVICE void load_col_chunk_to_tmem(const float* __restrict__ W, int ldw, int k, int crank, int r0, uint32_t taddr) {
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int ra = r0 + 2 * j, rb = ra + 1;
+        const int Ra = (ra >> 5) * lstm::H + crank * lstm::U + (ra & 31), Rb = (rb >> 5) * lstm::H + crank * lstm::U + (rb & 31);
+        v[j] = pack_bf16(__ldg(W + (size_t)Ra * ldw + k), __ldg(W + (size_t)Rb * ldw + k));
+    }
+    tmem_st_x32(taddr, v);
+}
+
+__global__ void __cluster_dims__(lstm::CL, 1, 1) __launch_bounds__(lstm::kThreads, 1)
+lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
+    using namespace lstm;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int pair = blockIdx.x / CL;
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int T = a.T;
+
+    // ---- shared memory: inbox [2 bufs][8 src][3 kinds][NB][32] fp32, out staging [3 kinds][8 dst][NB][32] fp32 (double-buffered),
+    //      dG operands [2 layers][NB × 128] bf16
+    constexpr int BLK = NB * U;   // 512 floats = 2 KB
+    float* inbox = reinterpret_cast<float*>(smem_raw);                  // 2*8*3*BLK
+    float* outst = inbox + 2 * CL * 3 * BLK;                            // 2*3*8*BLK
+    __nv_bfloat16* dGs = reinterpret_cast<__nv_bfloat16*>(outst + 2 * 3 * CL * BLK);   // [2][NB*128]
+    uint64_t* ibar = reinterpret_cast<uint64_t*>(dGs + 2 * NB * 128);  // [2]
+    uint64_t* mma_bar = ibar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+    const float* prow = a.params + a.row_off[pair];
+    const float* w_hh1 = prow + a.off_whh1;
+    const float* w_ih2 = prow + a.off_wih2;
+    const float* w_hh2 = prow + a.off_whh2;
+
+    if (tid == 0) {
+        mbar_init(ibar + 0, 1); mbar_init(ibar + 1, 1); mbar_init(mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(B_TMEM));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_ptr_smem;
+    const uint32_t lane_addr = tmem + ((uint32_t)(w * 32) << 16);
+
+    // ---- transposed weight slices → TMEM: tile h, lane = hidden column k = 128 h + tid; K = own 128 gate rows
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int k = 128 * h + tid;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            load_col_chunk_to_tmem(w_hh2, H, k, crank, 64 * c, lane_addr + BT_HH2 + 64 * h + 32 * c);
+            load_col_chunk_to_tmem(w_ih2, H, k, crank, 64 * c, lane_addr + BT_IH2 + 64 * h + 32 * c);
+            load_col_chunk_to_tmem(w_hh1, H, k, crank, 64 * c, lane_addr + BT_HH1 + 64 * h + 32 * c);
+        }
+    }
+    tmem_st_wait();
+    tcgen05_fence_before();
+    cluster.sync();
+    tcgen05_fence_after();
+
+    const int unit = crank * U + l;
+    const float* gates_p = a.gates + (size_t)pair * 2 * T * NB * 4 * H;
+    const float* cst_p = a.cst + (size_t)pair * 2 * T * NB * H;
+    __nv_bfloat16* dG_p = reinterpret_cast<__nv_bfloat16*>(a.dgates) + (size_t)pair * 2 * T * NB * 4 * H;
+    float dc1[4] = {0.f, 0.f, 0.f, 0.f}, dc2[4] = {0.f, 0.f, 0.f, 0.f};
+
+    // phase p = T-1 … -1: layer 2 at time p, layer 1 at time p+1
+    for (int p = T - 1, it = 0; p >= -1; --p, ++it) {
+        const bool doL2 = p >= 0, doL1 = p + 1 <= T - 1;
+        const bool have_in = it > 0;                 // partial blocks of the previous phase
+        const int ibuf = (it + 1) & 1;               // inbox buffer written during phase it-1
+        if (have_in) mbar_wait_long(ibar + ibuf, ((it - 1) >> 1) & 1);
+        const float* in = inbox + (size_t)ibuf * CL * 3 * BLK;
+        // what the previous phase produced: kind 0 = rec2 (for layer 2 at time p), kind 1 = dh1in (layer 1 at time p+1),
+        // kind 2 = rec1 (layer 1 at time p+1)
+        const bool prev_had_L2 = have_in;                       // phase it-1 ran layer 2 at time p+1 (always, for it ≥ 1)
+        const bool prev_had_L1 = have_in && (p + 2 <= T - 1);   // … and layer 1 at time p+2
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = w + 4 * i;
+            if (doL2) {
+                float dh = 0.f;
+                if (a.dh2_all) dh = a.dh2_all[(((size_t)pair * T + p) * NB + b) * H + unit];
+                else if (p == T - 1) dh = a.dh2_last[((size_t)pair * NB + b) * H + unit];
+                if (prev_had_L2) {
+#pragma unroll
+                    for (int s = 0; s < CL; ++s) dh += in[(s * 3 + 0) * BLK + b * U + l];
+                }
+                const size_t row = ((size_t)(1 * T + p) * NB + b);
+                const float* g = gates_p + row * 4 * H + unit;
+                const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
+                const float c = cst_p[row * H + unit];
+                const float cprev = (p > 0) ? cst_p[((size_t)(1 * T + p - 1) * NB + b) * H + unit] : 0.f;
+                const float tc = tanh_f(c);
+                const float dcv = dc2[i] + dh * go * (1.f - tc * tc);
+                const float dzi = dcv * gg * gi * (1.f - gi), dzf = dcv * cprev * gf * (1.f - gf);
+                const float dzg = dcv * gi * (1.f - gg * gg), dzo = dh * tc * go * (1.f - go);
+                dc2[i] = dcv * gf;
+                __nv_bfloat16* o = dG_p + row * 4 * H + unit;
+                const __nv_bfloat16 bi = __float2bfloat16(dzi), bf = __float2bfloat16(dzf), bg = __float2bfloat16(dzg), bo = __float2bfloat16(dzo);
+                o[0] = bi; o[H] = bf; o[2 * H] = bg; o[3 * H] = bo;
+                __nv_bfloat16* s2 = dGs + 1 * NB * 128;
+                s2[op_off(b, 0 * 32 + l)] = bi; s2[op_off(b, 1 * 32 + l)] = bf; s2[op_off(b, 2 * 32 + l)] = bg; s2[op_off(b, 3 * 32 + l)] = bo;
+            }
+            if (doL1) {
+                const int t1 = p + 1;
+                float dh = 0.f;
+                if (prev_had_L2) {
+#pragma unroll
+                    for (int s = 0; s < CL; ++s) dh += in[(s * 3 + 1) * BLK + b * U + l];
+                }
+                if (prev_had_L1) {
+#pragma unroll
+                    for (int s = 0; s < CL; ++s) dh += in[(s * 3 + 2) * BLK + b * U + l];
+                }
+                const size_t row = ((size_t)(0 * T + t1) * NB + b);
+                const float* g = gates_p + row * 4 * H + unit;
+                const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
+                const float c = cst_p[row * H + unit];
+                const float cprev = (t1 > 0) ? cst_p[((size_t)(0 * T + t1 - 1) * NB + b) * H + unit] : 0.f;
+                const float tc = tanh_f(c);
+                const float dcv = dc1[i] + dh * go * (1.f - tc * tc);
+                const float dzi = dcv * gg * gi * (1.f - gi), dzf = dcv * cprev * gf * (1.f - gf);
+                const float dzg = dcv * gi * (1.f - gg * gg), dzo = dh * tc * go * (1.f - go);
+                dc1[i] = dcv * gf;
+                __nv_bfloat16* o = dG_p + row * 4 * H + unit;
+                const __nv_bfloat16 bi = __float2bfloat16(dzi), bf = __float2bfloat16(dzf), bg = __float2bfloat16(dzg), bo = __float2bfloat16(dzo);
+                o[0] = bi; o[H] = bf; o[2 * H] = bg; o[3 * H] = bo;
+                __nv_bfloat16* s1 = dGs;
+                s1[op_off(b, 0 * 32 + l)] = bi; s1[op_off(b, 1 * 32 + l)] = bf; s1[op_off(b, 2 * 32 + l)] = bg; s1[op_off(b, 3 * 32 + l)] = bo;
+            }
+        }
+        if (p == -1) break;            // time 0 of layer 1 has no consumer for its dh_{-1}
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tcgen05_fence_after();
+            const uint32_t g2 = smem_u32(dGs + NB * 128), g1 = smem_u32(dGs);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // doL2 is always true here (p ≥ 0)
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    umma_ts_f16(tmem + BD_REC2 + 16 * h, tmem + BT_HH2 + 64 * h + 8 * s, make_desc_nosw(g2 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    umma_ts_f16(tmem + BD_IN1 + 16 * h, tmem + BT_IH2 + 64 * h + 8 * s, make_desc_nosw(g2 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                if (doL1) {
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)
+                        umma_ts_f16(tmem + BD_REC1 + 16 * h, tmem + BT_HH1 + 64 * h + 8 * s, make_desc_nosw(g1 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                }
+            }
+            tcgen05_commit(mma_bar);
+        }
+        mbar_wait_long(mma_bar, it & 1);
+        tcgen05_fence_after();
+        // ---- partial dhᵀ tiles → staging blocks [b][unit-in-owner] (this warp's 32 lanes = 32 hidden units of owner 4h + w)
+        float* ob = outst + (size_t)(it & 1) * 3 * CL * BLK;
+        const int nk = doL1 ? 3 : 2;
+        for (int kind = 0; kind < nk; ++kind) {
+            const uint32_t col = (kind == 0) ? BD_REC2 : (kind == 1 ? BD_IN1 : BD_REC1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float z[16];
+                tmem_ld_x16(lane_addr + col + 16 * h, z);
+                float* dst = ob + (size_t)(kind * CL + (4 * h + w)) * BLK;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) dst[b * U + l] = z[b];
+            }
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            // ---- reduce-scatter: block (kind, owner d) → owner d's inbox slot [src = me][kind]
+            const int obuf = it & 1;
+            mbar_expect_tx(ibar + obuf, (uint32_t)(CL * nk * BLK * 4));
+            const uint32_t bar = smem_u32(ibar + obuf);
+#pragma unroll 1
+            for (int d = 0; d < CL; ++d) {
+                const uint32_t rbar = mapa_u32(bar, d);
+                for (int kind = 0; kind < nk; ++kind) {
+                    const uint32_t dst = smem_u32(inbox + ((size_t)obuf * CL + crank) * 3 * BLK + kind * BLK);
+                    bulk_copy_s2c(mapa_u32(dst, d), smem_u32(ob + (size_t)(kind * CL + d) * BLK), BLK * 4, rbar);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster.sync();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(B_TMEM));
+}
+
+// ======================================================================================================= launchers
+static size_t fwd_smem_bytes() {
+    using namespace lstm;
+    size_t b = (size_t)(2 * NB * H + 2 * NB * H + 2 * NB * KX + 2 * 2 * NB * U) * 2 + (size_t)2 * 4 * NB * U * 4 + 64;
+    return b < 120 * 1024 ? 120 * 1024 : b;   // > half an SM's shared memory: exactly one CTA (one 512-column TMEM owner) per SM
+}
+static size_t bwd_smem_bytes() {
+    using namespace lstm;
+    return (size_t)(2 * CL * 3 + 2 * 3 * CL) * NB * U * 4 + (size_t)2 * NB * 128 * 2 + 64;
+}
+
+int lstm2_fwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream) {
+    const size_t smem = fwd_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(lstm2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -3;
+    lstm2_fwd_kernel<<<npairs * lstm::CL, lstm::kThreads, smem, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+int lstm2_bwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream) {
+    const size_t smem = bwd_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(lstm2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -3;
+    lstm2_bwd_kernel<<<npairs * lstm::CL, lstm::kThreads, smem, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+}  // namespace fdb

@@ -2,7 +2,8 @@
 
 Parity: ``fedml_api/model/nlp/rnn.py:4-33`` (RNN_OriginalFedAvg: Embedding(90,8)
 → 2-layer LSTM(256, batch_first) → Linear(256,90) on the LAST step; 822 570
-params) and ``:36-66`` (RNN_StackOverFlow: Embedding(10004,96) → LSTM(670) →
+params; on CUDA the embedding + 2-layer LSTM run in the fused persistent kernel ``csrc/lstm_tc.cu`` — state-dict
+keys stay those of ``nn.Embedding`` / ``nn.LSTM``) and ``:36-66`` (RNN_StackOverFlow: Embedding(10004,96) → LSTM(670) →
 fc 96 → fc 10004; 4 053 428 params).  ``per_position=True`` is the optional
 TFF-style per-position head.
 """
@@ -23,6 +24,14 @@ class RNN_OriginalFedAvg(nn.Module):
         self.fc = TcLinear(hidden_size, vocab_size)
 
     def forward(self, input_seq):
+        from ..ops import lstm as fused
+        if fused.eligible(input_seq, self.embeddings.weight, self.lstm):
+            # persistent cluster-resident tcgen05 kernel: the whole sequence, both layers, ONE launch (csrc/lstm_tc.cu)
+            if self.per_position:
+                out = fused.lstm2_embed_forward(input_seq, self.embeddings, self.lstm, need_all=True)
+                b, t, h = out.shape
+                return self.fc(out.reshape(b * t, h)).reshape(b, t, -1).transpose(1, 2)
+            return self.fc(fused.lstm2_embed_forward(input_seq, self.embeddings, self.lstm))
         out, _ = self.lstm(self.embeddings(input_seq))
         if self.per_position:
             b, t, h = out.shape

@@ -42,6 +42,7 @@ def attach_multi_gpu(sim, world: int, rank: int) -> None:
         "error_flag": torch.zeros(1, dtype=torch.int32).pin_memory(),
         "_keepalive": r,
     }
+    sim.multi["error_np"] = sim.multi["error_flag"].numpy()   # zero-overhead host view for the per-round check
     torch.cuda.synchronize()
     dist.barrier()
 
@@ -49,8 +50,8 @@ def attach_multi_gpu(sim, world: int, rank: int) -> None:
 def check_error(sim) -> None:
     """Raise if the fused kernel gave up waiting for a peer (call after a stream sync; reads pinned host memory)."""
     m = getattr(sim, "multi", None)
-    if m is not None and int(m["error_flag"][0]) != 0:
-        code = int(m["error_flag"][0])
+    if m is not None and m["error_np"][0] != 0:
+        code = int(m["error_np"][0])
         raise RuntimeError(f"fed_round_small: rank {m['rank']} gave up waiting for a peer ("
                            f"{'aggregation inbox' if code == 1 else 'metrics rows'} never arrived within the spin timeout); "
                            "the cluster models were NOT updated from the incomplete inbox")

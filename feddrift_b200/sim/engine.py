@@ -219,7 +219,7 @@ class DriftSim:
         return small_round.fits(s["kind"], s["in"], s["hidden"], s["out"], self.C, self.M, self.t)
 
     def _check_peer_error(self) -> None:
-        if self.multi is not None:
+        if self.multi is not None and self.multi["error_np"][0] != 0:
             from ..parallel.symm import check_error
             check_error(self)
 

@@ -367,6 +367,20 @@ Tensor gemm_bias_act(Tensor A, Tensor B, bool a_mn, bool b_mn, c10::optional<Ten
     return D;
 }
 
+// Batched weight-gradient GEMM (one launch for every pair): D[bt] [M, N] fp32 = A'[rows a_k0 + bt·a_kstride …+K, M]ᵀ · B'[rows b_k0 + bt·b_kstride …+K, N]
+Tensor gemm_batched_mn(Tensor A, Tensor B, int64_t K, int64_t batch, int64_t a_k0, int64_t a_kstride, int64_t b_k0, int64_t b_kstride) {
+    TORCH_CHECK(A.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm_batched_mn needs CUDA bf16 operands");
+    TORCH_CHECK(A.is_contiguous() && B.is_contiguous() && A.dim() == 2 && B.dim() == 2, "gemm_batched_mn: contiguous 2-D operands");
+    TORCH_CHECK(a_k0 + (batch - 1) * a_kstride + K <= A.size(0) && b_k0 + (batch - 1) * b_kstride + K <= B.size(0), "gemm_batched_mn: K range");
+    c10::cuda::CUDAGuard guard(A.device());
+    const int M = (int)A.size(1), N = (int)B.size(1);
+    auto D = torch::empty({batch, M, N}, A.options().dtype(torch::kFloat32));
+    const int rc = fdb::gemm_batched_mn_launch(A.data_ptr(), B.data_ptr(), D.data_ptr<float>(), M, N, (int)K, (int)batch, (int)A.size(0),
+                                               (int)B.size(0), (int)a_k0, (int)a_kstride, (int)b_k0, (int)b_kstride, cur_stream());
+    CHECK_OK(rc, "gemm_batched_mn (tcgen05)");
+    return D;
+}
+
 // K2 (consumer-pull broadcast): the weight matrix B[N,K] stays in the OWNER GPU's symmetric-memory arena; `b_ptr` is
 // the peer-mapped device pointer.  The TMA producer of the GEMM pulls B tiles straight over NVLink inside the tile loop,
 // so "broadcast the model, then run the first layer" is one kernel and no local copy of the weights ever exists.
@@ -428,29 +442,39 @@ void graph_launch_sync(int64_t exec, bool sync) {
 // ---------------------------------------------------------------------------------- persistent LSTM (lstm_tc.cu)
 // offs = {emb, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2, w_hh2, b_ih2, b_hh2} element offsets inside a parameter row.
 static fdb::LstmArgs lstm_args(const Tensor& params, const Tensor& row_off, const std::vector<int64_t>& offs, const Tensor& tokens,
-                               const Tensor& gates, const Tensor& cst, const Tensor& hhist, const Tensor& hlast, int64_t E) {
-    CHECK_CUDA_F32(params); CHECK_CUDA_I32(tokens); CHECK_CUDA_F32(gates); CHECK_CUDA_F32(cst); CHECK_CUDA_F32(hlast);
+                               const c10::optional<Tensor>& gates, const c10::optional<Tensor>& cst, const c10::optional<Tensor>& hhist,
+                               const Tensor& hlast, int64_t E) {
+    CHECK_CUDA_F32(params); CHECK_CUDA_I32(tokens); CHECK_CUDA_F32(hlast);
     TORCH_CHECK(row_off.is_cuda() && row_off.scalar_type() == torch::kInt64, "row_off must be a CUDA int64 tensor");
-    TORCH_CHECK(hhist.is_cuda() && hhist.scalar_type() == torch::kBFloat16, "hhist must be CUDA bf16");
     TORCH_CHECK(offs.size() == 9, "need 9 parameter offsets");
     TORCH_CHECK(tokens.dim() == 3 && tokens.size(1) == 16 && tokens.is_contiguous(), "tokens must be [npairs, 16, T] contiguous");
     const int64_t np = tokens.size(0), T = tokens.size(2);
     TORCH_CHECK(row_off.numel() == np && E >= 1 && E <= 16 && T >= 1, "lstm2: bad sizes");
-    TORCH_CHECK(gates.numel() == np * 2 * T * 16 * 1024 && cst.numel() == np * 2 * T * 16 * 256 &&
-                hhist.numel() == np * 2 * (T + 1) * 16 * 256 && hlast.numel() == np * 16 * 256, "lstm2: workspace sizes");
+    TORCH_CHECK(hlast.numel() == np * 16 * 256, "lstm2: hlast size");
     fdb::LstmArgs a{};
     a.params = params.data_ptr<float>();
     a.row_off = reinterpret_cast<const long long*>(row_off.data_ptr<int64_t>());
     a.off_emb = offs[0]; a.off_wih1 = offs[1]; a.off_whh1 = offs[2]; a.off_bih1 = offs[3]; a.off_bhh1 = offs[4];
     a.off_wih2 = offs[5]; a.off_whh2 = offs[6]; a.off_bih2 = offs[7]; a.off_bhh2 = offs[8];
     a.tokens = tokens.data_ptr<int>();
-    a.gates = gates.data_ptr<float>(); a.cst = cst.data_ptr<float>(); a.hhist = hhist.data_ptr(); a.hlast = hlast.data_ptr<float>();
+    if (gates.has_value() && gates->defined()) {
+        TORCH_CHECK(cst.has_value() && cst->defined(), "lstm2: gates and cst come together");
+        CHECK_CUDA_F32(*gates); CHECK_CUDA_F32(*cst);
+        TORCH_CHECK(gates->numel() == np * 2 * T * 16 * 1024 && cst->numel() == np * 2 * T * 16 * 256, "lstm2: workspace sizes");
+        a.gates = gates->data_ptr<float>(); a.cst = cst->data_ptr<float>();
+    }
+    if (hhist.has_value() && hhist->defined()) {
+        TORCH_CHECK(hhist->is_cuda() && hhist->scalar_type() == torch::kBFloat16 && hhist->numel() == np * 2 * (T + 1) * 16 * 256,
+                    "hhist must be CUDA bf16 [2, npairs, T+1, 16, 256]");
+        a.hhist = hhist->data_ptr();
+    }
+    a.hlast = hlast.data_ptr<float>();
     a.T = (int)T; a.E = (int)E;
     return a;
 }
 
-void lstm2_forward(Tensor params, Tensor row_off, std::vector<int64_t> offs, Tensor tokens, Tensor gates, Tensor cst, Tensor hhist,
-                   Tensor hlast, int64_t E) {
+void lstm2_forward(Tensor params, Tensor row_off, std::vector<int64_t> offs, Tensor tokens, c10::optional<Tensor> gates,
+                   c10::optional<Tensor> cst, c10::optional<Tensor> hhist, Tensor hlast, int64_t E) {
     c10::cuda::CUDAGuard guard(params.device());
     fdb::LstmArgs a = lstm_args(params, row_off, offs, tokens, gates, cst, hhist, hlast, E);
     CHECK_OK(fdb::lstm2_fwd_launch(a, (int)tokens.size(0), cur_stream()), "lstm2_fwd (tcgen05 cluster kernel)");
@@ -460,6 +484,7 @@ void lstm2_backward(Tensor params, Tensor row_off, std::vector<int64_t> offs, Te
                     Tensor hlast, int64_t E, c10::optional<Tensor> dh2_last, c10::optional<Tensor> dh2_all, Tensor dgates) {
     c10::cuda::CUDAGuard guard(params.device());
     fdb::LstmArgs a = lstm_args(params, row_off, offs, tokens, gates, cst, hhist, hlast, E);
+    TORCH_CHECK(a.gates != nullptr, "lstm2_backward needs the forward history");
     const int64_t np = tokens.size(0), T = tokens.size(2);
     TORCH_CHECK(dgates.is_cuda() && dgates.scalar_type() == torch::kBFloat16 && dgates.numel() == np * 2 * T * 16 * 1024, "dgates workspace");
     if (dh2_all.has_value() && dh2_all->defined()) {
@@ -474,6 +499,27 @@ void lstm2_backward(Tensor params, Tensor row_off, std::vector<int64_t> offs, Te
     }
     a.dgates = dgates.data_ptr();
     CHECK_OK(fdb::lstm2_bwd_launch(a, (int)np, cur_stream()), "lstm2_bwd (tcgen05 cluster kernel)");
+}
+
+// fc + softmax-CE + all head gradients for `nchunks` 16-row chunks (lstm_tc.cu::lstm_head_kernel)
+void lstm_head(Tensor params, Tensor row_off, int64_t off_fcw, int64_t off_fcb, Tensor hlast, Tensor labels, Tensor scale, Tensor dh,
+               Tensor dW, Tensor db, c10::optional<Tensor> loss, int64_t V) {
+    CHECK_CUDA_F32(params); CHECK_CUDA_F32(hlast); CHECK_CUDA_I32(labels); CHECK_CUDA_F32(scale); CHECK_CUDA_F32(dh); CHECK_CUDA_F32(dW);
+    CHECK_CUDA_F32(db);
+    TORCH_CHECK(row_off.is_cuda() && row_off.scalar_type() == torch::kInt64, "row_off must be a CUDA int64 tensor");
+    c10::cuda::CUDAGuard guard(params.device());
+    const int64_t n = row_off.numel();
+    TORCH_CHECK(hlast.numel() == n * 16 * 256 && labels.numel() == n * 16 && scale.numel() == n && dh.numel() == n * 16 * 256 &&
+                dW.numel() == n * V * 256 && db.numel() == n * V, "lstm_head: tensor sizes");
+    fdb::LstmHeadArgs a{};
+    a.params = params.data_ptr<float>();
+    a.row_off = reinterpret_cast<const long long*>(row_off.data_ptr<int64_t>());
+    a.off_fcw = off_fcw; a.off_fcb = off_fcb;
+    a.hlast = hlast.data_ptr<float>(); a.labels = labels.data_ptr<int>(); a.scale = scale.data_ptr<float>();
+    a.dh = dh.data_ptr<float>(); a.dW = dW.data_ptr<float>(); a.db = db.data_ptr<float>();
+    a.loss = opt_ptr<float>(loss);
+    a.V = (int)V;
+    CHECK_OK(fdb::lstm_head_launch(a, (int)n, cur_stream()), "lstm_head");
 }
 
 }  // namespace
@@ -505,10 +551,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("gemm_tn_bias_act", &gemm_tn_bias_act);
     m.def("gemm_tn_bias_act_peer", &gemm_tn_bias_act_peer);
     m.def("gemm_bias_act", &gemm_bias_act);
+    m.def("gemm_batched_mn", &gemm_batched_mn);
     m.def("gossip_mix_peer", &gossip_mix_peer);
     m.def("graph_launch_sync", &graph_launch_sync);
     m.def("im2col_bf16", &im2col_bf16);
     m.def("col2im", &col2im);
     m.def("lstm2_forward", &lstm2_forward);
     m.def("lstm2_backward", &lstm2_backward);
+    m.def("lstm_head", &lstm_head);
 }

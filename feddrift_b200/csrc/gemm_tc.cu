@@ -33,6 +33,7 @@ namespace fdb {
 constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 4;
 constexpr int kGemmThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 epilogue
 constexpr uint32_t kStageBytesA = BM * BK * 2;
+struct GemmBatch { int batch, a_k0, a_kstride, b_k0, b_kstride; };
 
 template <int BN> struct GemmCfg {
     static constexpr uint32_t kStageBytesB = BN * BK * 2;
@@ -47,7 +48,7 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, void* __restrict__ D, const float* __restrict__ bias, int M, int N, int K,
-               int relu, int out_fp32, int splits, int tma_out, int a_mn, int b_mn) {
+               int relu, int out_fp32, int splits, int tma_out, int a_mn, int b_mn, GemmBatch gb) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,7 +63,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
-    const int num_tiles = m_tiles * n_tiles;
+    // batched mode (gb.batch > 1; both operands MN-major, M % 128 == 0, K % 64 == 0): batch bt multiplies the reduction rows
+    // [a_k0 + bt·a_kstride, +K) of A' with [b_k0 + bt·b_kstride, +K) of B' into rows [bt·M, bt·M + M) of D — one launch for
+    // the weight gradients dW_p = dG_pᵀ·H_p of every (client, model) pair
+    const int tiles_per_batch = m_tiles * n_tiles;
+    const int num_tiles = tiles_per_batch * gb.batch;
     const int kb_total = (K + BK - 1) / BK;
     const int kb_per = (kb_total + splits - 1) / splits;
     const int kb_lo = blockIdx.z * kb_per, kb_hi = min(kb_total, kb_lo + kb_per);
@@ -91,7 +96,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0 && nkb > 0) {  // ===== TMA producer
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+                const int bt = tile / tiles_per_batch, rem = tile - bt * tiles_per_batch;
+                const int m_blk = rem % m_tiles, n_blk = rem / m_tiles;
+                const int ak = gb.a_k0 + bt * gb.a_kstride, bk = gb.b_k0 + bt * gb.b_kstride;   // 0 unless batched
                 for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -101,13 +108,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     uint8_t* sb = smem_b + s * Cfg::kStageBytesB;
                     if (a_mn) {   // [K, M] tensor: two 64(M)×64(K) boxes
 #pragma unroll
-                        for (int h = 0; h < BM / 64; ++h) tma_load_2d(&map_a, full_bar + s, sa + h * 8192, m_blk * BM + h * 64, kb * BK);
+                        for (int h = 0; h < BM / 64; ++h) tma_load_2d(&map_a, full_bar + s, sa + h * 8192, m_blk * BM + h * 64, ak + kb * BK);
                     } else {
                         tma_load_2d(&map_a, full_bar + s, sa, kb * BK, m_blk * BM);
                     }
                     if (b_mn) {
 #pragma unroll
-                        for (int h = 0; h < BN / 64; ++h) tma_load_2d(&map_b, full_bar + s, sb + h * 8192, n_blk * BN + h * 64, kb * BK);
+                        for (int h = 0; h < BN / 64; ++h) tma_load_2d(&map_b, full_bar + s, sb + h * 8192, n_blk * BN + h * 64, bk + kb * BK);
                     } else {
                         tma_load_2d(&map_b, full_bar + s, sb, kb * BK, n_blk * BN);
                     }
@@ -148,7 +155,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int q = warp - 4;
         uint32_t tl = 0, chunk_it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-            const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+            const int bt = tile / tiles_per_batch, rem = tile - bt * tiles_per_batch;
+            const int m_blk = rem % m_tiles, n_blk = rem / m_tiles;
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
             mbar_wait(tmem_full + acc, aph);
             tcgen05_fence_after();
@@ -158,7 +166,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // staging (conflict-free 16-byte stores) → ONE TMA tile store (or fp32 reduce-add for split-K) per
                 // 128-byte column chunk.  Staging is double-buffered per warp; TMA clips the M/N edges.
                 const int cols_per_chunk = out_fp32 ? 32 : 64;
-                const int row0 = m_blk * BM + q * 32;
+                const int row0 = bt * M + m_blk * BM + q * 32;   // batched outputs are stacked along the rows of D
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += cols_per_chunk, ++chunk_it) {
                     const int col0 = n_blk * BN + c0;
@@ -346,19 +354,20 @@ static int make_map_mn(CUtensorMap* map, const void* base, int rows, int K) {
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
-                       int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream) {
+                       int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream, GemmBatch gb = GemmBatch{1, 0, 0, 0, 0}) {
     CUtensorMap md;
     int tma_out = 0;
-    if (make_out_map(&md, D, M, N, out_fp32, &tma_out) != 0) return -7;
+    if (make_out_map(&md, D, M * gb.batch, N, out_fp32, &tma_out) != 0) return -7;
+    if (gb.batch > 1 && !tma_out) return -9;
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess) return -3;
         attr_set = true;
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * gb.batch;
     dim3 grid(min(tiles, max(1, sms / splits)), 1, splits);
-    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out, a_mn, b_mn);
+    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out, a_mn, b_mn, gb);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -416,6 +425,25 @@ int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M,
     }
     return (bn == 256) ? launch_gemm<256>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, a_mn, b_mn, stream)
                        : launch_gemm<128>(ma, mb, D, bias, M, N, K, relu, out_fp32, 1, sms, a_mn, b_mn, stream);
+}
+
+// Batched dW-style GEMM: D[bt·M + m, n] = Σ_k A'[a_k0 + bt·a_kstride + k, m] · B'[b_k0 + bt·b_kstride + k, n]   (k < K), fp32 out.
+// A' is [a_rows_total, M] and B' is [b_rows_total, N] (bf16, row-major = MN-major operands).
+int gemm_batched_mn_launch(const void* A, const void* B, float* D, int M, int N, int K, int batch, int a_rows_total, int b_rows_total,
+                           int a_k0, int a_kstride, int b_k0, int b_kstride, cudaStream_t stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return -5;
+    if (M % BM != 0 || K % BK != 0 || M % 8 != 0 || N % 8 != 0) return -5;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return -6;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int bn = (N > 128) ? 256 : 128;
+    CUtensorMap ma, mb;
+    if (make_map_mn(&ma, A, M, a_rows_total) != 0) return -7;
+    if (make_map_mn(&mb, B, N, b_rows_total) != 0) return -7;
+    GemmBatch gb{batch, a_k0, a_kstride, b_k0, b_kstride};
+    return (bn == 256) ? launch_gemm<256>(ma, mb, D, nullptr, M, N, K, 0, 1, 1, sms, 1, 1, stream, gb)
+                       : launch_gemm<128>(ma, mb, D, nullptr, M, N, K, 0, 1, 1, sms, 1, 1, stream, gb);
 }
 
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,

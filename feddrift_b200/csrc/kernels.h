@@ -49,6 +49,8 @@ int group_norm_fwd_launch(const float* x, float* y, const float* w, const float*
 int gemm_split_count(int M, int N, int K);
 int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int a_mn, int b_mn, int relu, int out_fp32,
                 cudaStream_t stream, float* splitk_ws = nullptr);
+int gemm_batched_mn_launch(const void* A, const void* B, float* D, int M, int N, int K, int batch, int a_rows_total, int b_rows_total,
+                           int a_k0, int a_kstride, int b_k0, int b_kstride, cudaStream_t stream);
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
                    cudaStream_t stream);
 // lstm_tc.cu : persistent cluster-resident 2-layer LSTM(256) forward / BPTT over many (client, model) pairs per launch
@@ -57,16 +59,30 @@ struct LstmArgs {
     const long long* row_off;     // [npairs] element offset of each pair's flat parameter row
     long long off_emb, off_wih1, off_whh1, off_bih1, off_bhh1, off_wih2, off_whh2, off_bih2, off_bhh2;   // offsets inside a row
     const int* tokens;            // [npairs, 16, T] int32 token ids (rows beyond the real batch are padding)
-    float* gates;                 // [npairs, 2, T, 16, 4, 256] activated gates (i, f, g, o)
-    float* cst;                   // [npairs, 2, T, 16, 256]    cell states
-    void* hhist;                  // [npairs, 2, T+1, 16, 256]  bf16 hidden states, index 0 = h_{-1} = 0
+    float* gates;                 // [2, npairs, T, 16, 4, 256] activated gates (i, f, g, o); nullptr = inference (no history)
+    float* cst;                   // [2, npairs, T, 16, 256]    cell states
+    void* hhist;                  // [2, npairs, T+1, 16, 256]  bf16 hidden states, index 0 = h_{-1} = 0; nullptr = not kept
     float* hlast;                 // [npairs, 16, 256]          fp32 h2_{T-1}
     // backward only
     const float* dh2_last;        // [npairs, 16, 256] gradient wrt h2_{T-1}            (used when dh2_all == nullptr)
     const float* dh2_all;         // [npairs, T, 16, 256] gradient wrt every h2_t, or nullptr
-    void* dgates;                 // [npairs, 2, T, 16, 1024] bf16 pre-activation gate gradients (PyTorch row order)
+    void* dgates;                 // [2, npairs, T, 16, 1024] bf16 pre-activation gate gradients (PyTorch row order)
     int T, E;
 };
+struct LstmHeadArgs {
+    const float* params;          // parameter arena base
+    const long long* row_off;     // [nchunks] element offset of each chunk's parameter row
+    long long off_fcw, off_fcb;   // fc.weight [V, 256] / fc.bias [V] offsets inside a row
+    const float* hlast;           // [nchunks, 16, 256]
+    const int* labels;            // [nchunks, 16]  (-1 = padding row)
+    const float* scale;           // [nchunks] 1 / (#real rows of the chunk's pair)
+    float* dh;                    // [nchunks, 16, 256]  d loss / d h2_{T-1}
+    float* dW;                    // [nchunks, V, 256]
+    float* db;                    // [nchunks, V]
+    float* loss;                  // [nchunks] or nullptr
+    int V;
+};
+int lstm_head_launch(const LstmHeadArgs& a, int nchunks, cudaStream_t stream);
 int lstm2_fwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream);
 int lstm2_bwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream);
 }  // namespace fdb

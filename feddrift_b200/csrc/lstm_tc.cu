@@ -218,9 +218,15 @@ lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
     // cell-phase ownership: unit ul = l, batch rows b = w + 4 i
     float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
     const int unit = crank * U + l;
-    float* gates_p = a.gates + (size_t)pair * 2 * T * NB * 4 * H;
-    float* cst_p = a.cst + (size_t)pair * 2 * T * NB * H;
-    __nv_bfloat16* hh_p = reinterpret_cast<__nv_bfloat16*>(a.hhist) + (size_t)pair * 2 * (T + 1) * NB * H;
+    // history layout is LAYER-outermost: [2][npairs][T (+1)][16][...] so that one layer's rows of consecutive pairs form one
+    // [npairs·T·16, 1024] matrix for the batched weight-gradient GEMMs
+    const int NP = (int)gridDim.x / CL;
+    const bool keep = a.gates != nullptr;            // training: save gates / cell states for BPTT
+    const bool keep_h = a.hhist != nullptr;
+    float* gates_l[2] = {a.gates + (size_t)(0 * NP + pair) * T * NB * 4 * H, a.gates + (size_t)(1 * NP + pair) * T * NB * 4 * H};
+    float* cst_l[2] = {a.cst + (size_t)(0 * NP + pair) * T * NB * H, a.cst + (size_t)(1 * NP + pair) * T * NB * H};
+    __nv_bfloat16* hh_l[2] = {reinterpret_cast<__nv_bfloat16*>(a.hhist) + (size_t)(0 * NP + pair) * (T + 1) * NB * H,
+                              reinterpret_cast<__nv_bfloat16*>(a.hhist) + (size_t)(1 * NP + pair) * (T + 1) * NB * H};
     // history row 0 (h_{-1} = 0) is zeroed by the host once; rows t+1 are written below
 
     for (int p = 0; p <= T; ++p) {
@@ -282,12 +288,14 @@ lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
                 const float gg = act_s[((0 * 4 + 2) * NB + b) * U + l], go = act_s[((0 * 4 + 3) * NB + b) * U + l];
                 c1[i] = gf * c1[i] + gi * gg;
                 const float h = go * tanh_f(c1[i]);
-                const size_t row = ((size_t)(0 * T + p) * NB + b);
-                float* g = gates_p + row * 4 * H + unit;
-                g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
-                cst_p[row * H + unit] = c1[i];
+                const size_t row = (size_t)p * NB + b;
+                if (keep) {
+                    float* g = gates_l[0] + row * 4 * H + unit;
+                    g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
+                    cst_l[0][row * H + unit] = c1[i];
+                }
                 const __nv_bfloat16 hb = __float2bfloat16(h);
-                hh_p[((size_t)(0 * (T + 1) + p + 1) * NB + b) * H + unit] = hb;
+                if (keep_h) hh_l[0][((size_t)(p + 1) * NB + b) * H + unit] = hb;
                 st1[op_off(b, l)] = hb;     // k_core = l/8 local to the slice
             }
             if (doL2) {
@@ -296,12 +304,14 @@ lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
                 const float gg = act_s[((1 * 4 + 2) * NB + b) * U + l], go = act_s[((1 * 4 + 3) * NB + b) * U + l];
                 c2[i] = gf * c2[i] + gi * gg;
                 const float h = go * tanh_f(c2[i]);
-                const size_t row = ((size_t)(1 * T + t2) * NB + b);
-                float* g = gates_p + row * 4 * H + unit;
-                g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
-                cst_p[row * H + unit] = c2[i];
+                const size_t row = (size_t)t2 * NB + b;
+                if (keep) {
+                    float* g = gates_l[1] + row * 4 * H + unit;
+                    g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
+                    cst_l[1][row * H + unit] = c2[i];
+                }
                 const __nv_bfloat16 hb = __float2bfloat16(h);
-                hh_p[((size_t)(1 * (T + 1) + t2 + 1) * NB + b) * H + unit] = hb;
+                if (keep_h) hh_l[1][((size_t)(t2 + 1) * NB + b) * H + unit] = hb;
                 st2[op_off(b, l)] = hb;
                 if (t2 == T - 1) a.hlast[((size_t)pair * NB + b) * H + unit] = h;
             }
@@ -406,9 +416,11 @@ lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
     tcgen05_fence_after();
 
     const int unit = crank * U + l;
-    const float* gates_p = a.gates + (size_t)pair * 2 * T * NB * 4 * H;
-    const float* cst_p = a.cst + (size_t)pair * 2 * T * NB * H;
-    __nv_bfloat16* dG_p = reinterpret_cast<__nv_bfloat16*>(a.dgates) + (size_t)pair * 2 * T * NB * 4 * H;
+    const int NP = (int)gridDim.x / CL;
+    const float* gates_l[2] = {a.gates + (size_t)(0 * NP + pair) * T * NB * 4 * H, a.gates + (size_t)(1 * NP + pair) * T * NB * 4 * H};
+    const float* cst_l[2] = {a.cst + (size_t)(0 * NP + pair) * T * NB * H, a.cst + (size_t)(1 * NP + pair) * T * NB * H};
+    __nv_bfloat16* dG_l[2] = {reinterpret_cast<__nv_bfloat16*>(a.dgates) + (size_t)(0 * NP + pair) * T * NB * 4 * H,
+                              reinterpret_cast<__nv_bfloat16*>(a.dgates) + (size_t)(1 * NP + pair) * T * NB * 4 * H};
     float dc1[4] = {0.f, 0.f, 0.f, 0.f}, dc2[4] = {0.f, 0.f, 0.f, 0.f};
 
     // phase p = T-1 … -1: layer 2 at time p, layer 1 at time p+1
@@ -433,17 +445,17 @@ lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
 #pragma unroll
                     for (int s = 0; s < CL; ++s) dh += in[(s * 3 + 0) * BLK + b * U + l];
                 }
-                const size_t row = ((size_t)(1 * T + p) * NB + b);
-                const float* g = gates_p + row * 4 * H + unit;
+                const size_t row = (size_t)p * NB + b;
+                const float* g = gates_l[1] + row * 4 * H + unit;
                 const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
-                const float c = cst_p[row * H + unit];
-                const float cprev = (p > 0) ? cst_p[((size_t)(1 * T + p - 1) * NB + b) * H + unit] : 0.f;
+                const float c = cst_l[1][row * H + unit];
+                const float cprev = (p > 0) ? cst_l[1][((size_t)(p - 1) * NB + b) * H + unit] : 0.f;
                 const float tc = tanh_f(c);
                 const float dcv = dc2[i] + dh * go * (1.f - tc * tc);
                 const float dzi = dcv * gg * gi * (1.f - gi), dzf = dcv * cprev * gf * (1.f - gf);
                 const float dzg = dcv * gi * (1.f - gg * gg), dzo = dh * tc * go * (1.f - go);
                 dc2[i] = dcv * gf;
-                __nv_bfloat16* o = dG_p + row * 4 * H + unit;
+                __nv_bfloat16* o = dG_l[1] + row * 4 * H + unit;
                 const __nv_bfloat16 bi = __float2bfloat16(dzi), bf = __float2bfloat16(dzf), bg = __float2bfloat16(dzg), bo = __float2bfloat16(dzo);
                 o[0] = bi; o[H] = bf; o[2 * H] = bg; o[3 * H] = bo;
                 __nv_bfloat16* s2 = dGs + 1 * NB * 128;
@@ -460,17 +472,17 @@ lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
 #pragma unroll
                     for (int s = 0; s < CL; ++s) dh += in[(s * 3 + 2) * BLK + b * U + l];
                 }
-                const size_t row = ((size_t)(0 * T + t1) * NB + b);
-                const float* g = gates_p + row * 4 * H + unit;
+                const size_t row = (size_t)t1 * NB + b;
+                const float* g = gates_l[0] + row * 4 * H + unit;
                 const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
-                const float c = cst_p[row * H + unit];
-                const float cprev = (t1 > 0) ? cst_p[((size_t)(0 * T + t1 - 1) * NB + b) * H + unit] : 0.f;
+                const float c = cst_l[0][row * H + unit];
+                const float cprev = (t1 > 0) ? cst_l[0][((size_t)(t1 - 1) * NB + b) * H + unit] : 0.f;
                 const float tc = tanh_f(c);
                 const float dcv = dc1[i] + dh * go * (1.f - tc * tc);
                 const float dzi = dcv * gg * gi * (1.f - gi), dzf = dcv * cprev * gf * (1.f - gf);
                 const float dzg = dcv * gi * (1.f - gg * gg), dzo = dh * tc * go * (1.f - go);
                 dc1[i] = dcv * gf;
-                __nv_bfloat16* o = dG_p + row * 4 * H + unit;
+                __nv_bfloat16* o = dG_l[0] + row * 4 * H + unit;
                 const __nv_bfloat16 bi = __float2bfloat16(dzi), bf = __float2bfloat16(dzf), bg = __float2bfloat16(dzg), bo = __float2bfloat16(dzo);
                 o[0] = bi; o[H] = bf; o[2 * H] = bg; o[3 * H] = bo;
                 __nv_bfloat16* s1 = dGs;
@@ -538,6 +550,93 @@ lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
     tcgen05_fence_before();
     cluster.sync();
     if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(B_TMEM));
+}
+
+// ======================================================================================================= classifier head
+// Linear(256 → V) on the last hidden state + softmax cross-entropy + every gradient of the head, one CTA per 16-row chunk:
+// logits, CE (mean over the pair's real rows via `scale`), dlogits, dW_fc, db_fc and dh2_{T-1} (the BPTT kernel's input).
+// Replaces fc GEMM + log_softmax + nll + three backward GEMMs + bias reduction (~9 launches) per pair and step.
+__global__ void __launch_bounds__(256) lstm_head_kernel(const __grid_constant__ LstmHeadArgs a) {
+    constexpr int H = lstm::H, NB = lstm::NB, VP = 96;
+    __shared__ float h_s[NB][H];
+    __shared__ float dl_s[NB][VP];
+    __shared__ float red_s[8];
+    const int ch = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31, V = a.V;
+    const float* prow = a.params + a.row_off[ch];
+    const float* Wfc = prow + a.off_fcw;
+    const float* bfc = prow + a.off_fcb;
+    const float* hl = a.hlast + (size_t)ch * NB * H;
+    for (int i = tid; i < NB * H; i += 256) h_s[i / H][i % H] = hl[i];
+    __syncthreads();
+    // logits[b][v] = h[b]·W[v] + bias[v]: one warp per output neuron, lanes split K, 16 rows at once
+    for (int v = w; v < V; v += 8) {
+        float wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = __ldg(Wfc + (size_t)v * H + l + 32 * j);
+        const float bv = __ldg(bfc + v);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(wv[j], h_s[b][l + 32 * j], acc);
+            acc = warp_sum(acc);
+            if (l == 0) dl_s[b][v] = acc + bv;
+        }
+    }
+    __syncthreads();
+    // softmax-CE per row; dlogits = (p − onehot)·scale   (scale = 1 / #real rows of the pair; padding rows: label < 0 → 0)
+    const float scale = a.scale[ch];
+    float lsum = 0.f;
+    for (int b = w; b < NB; b += 8) {
+        const int y = a.labels[ch * NB + b];
+        float mx = -INFINITY;
+        for (int v = l; v < V; v += 32) mx = fmaxf(mx, dl_s[b][v]);
+        mx = warp_max(mx);
+        float se = 0.f;
+        for (int v = l; v < V; v += 32) se += __expf(dl_s[b][v] - mx);
+        se = warp_sum(se);
+        const float inv = 1.f / se;
+        for (int v = l; v < V; v += 32) {
+            const float z = dl_s[b][v];
+            const float pr = __expf(z - mx) * inv;
+            if (y >= 0 && v == y) lsum += (mx + __logf(se) - z) * scale;
+            dl_s[b][v] = (y >= 0) ? (pr - (v == y ? 1.f : 0.f)) * scale : 0.f;
+        }
+    }
+    lsum = warp_sum(lsum);
+    if (l == 0) red_s[w] = lsum;
+    __syncthreads();
+    if (tid == 0 && a.loss) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red_s[i]; a.loss[ch] = t; }
+    // thread k: dW[v][k] = Σ_b dl[b][v] h[b][k],  dh[b][k] = Σ_v dl[b][v] W[v][k]
+    {
+        const int k = tid;
+        float hr[NB], dh[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { hr[b] = h_s[b][k]; dh[b] = 0.f; }
+        float* dW = a.dW + (size_t)ch * V * H;
+        for (int v = 0; v < V; ++v) {
+            const float wv = __ldg(Wfc + (size_t)v * H + k);
+            float acc = 0.f;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) { const float d = dl_s[b][v]; acc = fmaf(d, hr[b], acc); dh[b] = fmaf(d, wv, dh[b]); }
+            dW[(size_t)v * H + k] = acc;
+        }
+        float* dho = a.dh + (size_t)ch * NB * H;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) dho[b * H + k] = dh[b];
+    }
+    if (tid < V) {
+        float acc = 0.f;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) acc += dl_s[b][tid];
+        a.db[(size_t)ch * V + tid] = acc;
+    }
+}
+
+int lstm_head_launch(const LstmHeadArgs& a, int nchunks, cudaStream_t stream) {
+    if (a.V > 96 || a.V < 1) return -5;
+    lstm_head_kernel<<<nchunks, 256, 0, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
 // ======================================================================================================= launchers

@@ -63,7 +63,10 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
         active = (st["train_count"] > 0).any(dim=1) if st["sample_mode"] == "index" else (Wt != 0).any(dim=1)
         cl.n.zero_()
         world, rank = _world_rank(sim)
-        slots = _stream_slots(sim)          # K side streams: independent (client, model) pairs replay concurrently
+        from . import lstm_exec
+        batched = lstm_exec.applicable(sim, feat_mask)   # LSTM federations: all pairs advance in the same few launches
+        bpairs, n_host = [], np.zeros((C, M), dtype=np.float32)
+        slots = [] if batched else _stream_slots(sim)    # K side streams: independent (client, model) pairs replay concurrently
         pair_i = 0
         for c in range(C):
             if world > 1 and c % world != rank:   # clients are sharded over the ranks (one process per GPU)
@@ -75,6 +78,10 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
                 n_cm, sampler = _pair_sampler(st, c, m, t, nb, B)
                 if n_cm <= 0:
                     continue
+                if batched:
+                    bpairs.append((c, m, sampler))
+                    n_host[c, m] = n_cm
+                    continue
                 if slots:
                     with torch.cuda.stream(slots[pair_i % len(slots)]):
                         cl.params[c, m].copy_(bank.theta[m])
@@ -85,6 +92,9 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
                 pair_i += 1
                 cl.n[c, m] = n_cm
         _join_slots(sim, slots)
+        if batched:
+            lstm_exec.train_pairs(sim, bpairs, seed, rnd, E, use_adam, lr, a.wd)
+            cl.n.copy_(torch.from_numpy(n_host), non_blocking=True)
         # raw-update hooks (CFL family) may veto the aggregation of this round
         skip = False
         if hasattr(sim.algo, "state") and "cfl" in getattr(sim.algo, "arg", ""):

@@ -60,3 +60,41 @@ def test_rnn_model_uses_fused_kernel_and_trains():
         losses.append(loss.item())
     assert fused.CALLS["fwd"] == n0 + 8
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+def _run_rnn_federation(env):
+    import os
+    from feddrift_b200.sim import DriftSim, make_args
+    from feddrift_b200.utils.metrics import MetricsSink
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        kw = dict(model="rnn", dataset="shakespeare", client_num_in_total=6, client_num_per_round=6, concept_drift_algo="win-1",
+                  concept_drift_algo_arg="", concept_num=2, change_points="A", sample_num=32, batch_size=16, comm_round=2,
+                  total_train_iteration=2, epochs=2, lr=0.05, client_optimizer="sgd", report_client=0)
+        sim = DriftSim(make_args(**kw), device="cuda:0", sink=MetricsSink())
+        init = sim.bank.theta.clone()
+        out = sim.run_time_step(0, rounds=2)
+        torch.cuda.synchronize()
+        return init, sim.bank.theta.clone(), out
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_batched_lstm_executor_matches_per_pair_cudnn_path():
+    """All pairs in one launch (sim/lstm_exec.py) vs the per-pair nn.LSTM (cuDNN, fp32) executor: same federated update."""
+    from feddrift_b200.ops import lstm as fused
+    n0 = fused.CALLS["bwd"]
+    init, th_b, out_b = _run_rnn_federation({"FDB_LSTM_BATCHED": "1"})
+    assert fused.CALLS["bwd"] > n0, "batched executor did not run the fused BPTT kernel"
+    _, th_r, out_r = _run_rnn_federation({"FDB_LSTM_BATCHED": "0", "FDB_NO_FUSED_LSTM": "1"})
+    upd_b, upd_r = th_b - init, th_r - init
+    scale = upd_r.abs().max().item()
+    assert scale > 1e-4
+    err = (upd_b - upd_r).abs().max().item() / scale
+    assert err < 6e-2, f"federated update differs: rel {err}"
+    assert abs(out_b["train_loss"] - out_r["train_loss"]) < 5e-2 * max(1.0, abs(out_r["train_loss"]))

@@ -132,12 +132,12 @@ def train_pairs(sim, pairs: List, seed: int, rnd: int, E: int, use_adam: bool, l
         dG2f = ws.dgates[1].reshape(nch, TB, 4 * L.H).float()
         b1, b2 = dG1f.sum(1), dG2f.sum(1)
         tokl = tok.long().permute(0, 2, 1).reshape(nch, TB)
-        prow = params2.index_select(0, chunk_rows)                       # current local parameters of every chunk's pair
-        embw = prow[:, o_emb:o_emb + n_emb].reshape(nch, -1, Eemb)
+        # current local embedding / W_ih1 of every chunk's pair (column slices of the arena rows: a few KB per chunk)
+        embw = params2[:, o_emb:o_emb + n_emb].index_select(0, chunk_rows).reshape(nch, -1, Eemb)
         gi = tokl.unsqueeze(-1).expand(-1, -1, Eemb)
         Xe = embw.gather(1, gi).to(torch.bfloat16).float()               # the kernel fed bf16 embeddings to the tensor core
         dWih1 = torch.bmm(dG1f.transpose(1, 2), Xe)                      # [nch, 1024, E]
-        wih1 = prow[:, o_wih1:o_wih1 + n_wih1].reshape(nch, 4 * L.H, Eemb).to(torch.bfloat16).float()
+        wih1 = params2[:, o_wih1:o_wih1 + n_wih1].index_select(0, chunk_rows).reshape(nch, 4 * L.H, Eemb).to(torch.bfloat16).float()
         dX = torch.bmm(dG1f, wih1)                                       # [nch, T·16, E]
         demb = torch.zeros(nch, embw.shape[1], Eemb, dtype=torch.float32, device=dev).scatter_add_(1, gi, dX)
         demb[:, 0] = 0                                                   # nn.Embedding(padding_idx=0)

@@ -12,6 +12,7 @@ Replaces the reference's mpi4py pickle p2p (``mpi_send_thread.py:20-29``,
 """
 from __future__ import annotations
 
+import logging
 import pickle
 import queue
 import threading
@@ -92,6 +93,15 @@ class _Endpoint:
     _instances: Dict[int, "_Endpoint"] = {}
 
     def __init__(self, rank: int, size: int, group, device):
+        # The control plane relies on any-source ``dist.recv`` and message tags — ProcessGroupNCCL supports neither (the
+        # receive thread would raise and the manager would block forever).  On an NCCL default group the endpoint opens a
+        # gloo SIDE group for control messages; tensors travel as ``DeviceRef`` handles / peer memory, not through here.
+        backend = dist.get_backend(group) if group is not None else dist.get_backend()
+        if "gloo" not in str(backend).lower():
+            if group is not None:
+                raise RuntimeError(f"DistCommunicationManager needs a gloo process group for its control messages, got '{backend}'")
+            group = dist.new_group(backend="gloo")
+            device = torch.device("cpu")
         self.rank, self.size, self.group, self.device = rank, size, group, device
         self.q_send: "queue.Queue" = queue.Queue()
         self.q_recv: "queue.Queue" = queue.Queue()
@@ -124,7 +134,9 @@ class _Endpoint:
                 if item is None:
                     return
                 self._send_one(*item)
-            except Exception:  # group torn down
+            except Exception as exc:  # group torn down (or a transport error: say so instead of dying silently)
+                if dist.is_initialized():
+                    logging.error("feddrift_b200 send thread of rank %d stopped: %r", self.rank, exc)
                 return
             finally:
                 self.q_send.task_done()
@@ -142,7 +154,10 @@ class _Endpoint:
                 flat = torch.empty(dlen, dtype=torch.uint8, device=self.device)
                 if dlen:
                     dist.recv(flat, src=src, group=self.group, tag=_TAG_DATA)
-            except Exception:  # process group torn down while blocked
+            except Exception as exc:  # process group torn down while blocked (or a transport error)
+                if dist.is_initialized():
+                    logging.error("feddrift_b200 receive thread of rank %d stopped: %r", self.rank, exc)
+                    self.q_recv.put(None)   # unblock the dispatch loop instead of hanging forever
                 return
             self.q_recv.put(Message().init(unpack_payload(hdr.cpu().numpy().tobytes(), flat.cpu())))
 

@@ -164,7 +164,7 @@ class _Lstm2Fn(torch.autograd.Function):
         tok[:B] = tokens.to(torch.int32)
         tok = tok.reshape(n, NB, T)
         row_off = torch.zeros(n, dtype=torch.int64, device=dev)
-        train = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        train = any(ctx.needs_input_grad[3:])   # (grad mode is always off inside Function.forward)
         ws = Lstm2Workspace(n, T, dev, train=train, keep_h=train or bool(need_all))
         lstm2_pairs_forward(arena, row_off, offs, tok, E, ws)
         ctx.ws, ctx.tok, ctx.offs, ctx.arena, ctx.row_off = ws, tok, offs, arena, row_off

@@ -386,10 +386,14 @@ class KueAlgo(DriftAlgo):
             sim._small["ens_w"] = self._ens().to(sim.device)
 
     def state_dict(self):
-        return {"kue": {"masks": self.state.masks.copy(), "worst": self.state.worst_idx, "kappa": self.kappa.copy()}}
+        # the mask RNG is part of the state: a resumed run must draw the same feature subspaces as an uninterrupted one
+        return {"kue": {"masks": self.state.masks.copy(), "worst": self.state.worst_idx, "kappa": self.kappa.copy(),
+                        "rng": self.state.rng.get_state()}}
 
     def load_state_dict(self, d):
         self.state.masks, self.state.worst_idx, self.kappa = d["kue"]["masks"], d["kue"]["worst"], d["kue"]["kappa"]
+        if d["kue"].get("rng") is not None:
+            self.state.rng.set_state(d["kue"]["rng"])
 
 
 def sim_classes(sim) -> int:
@@ -532,6 +536,14 @@ class ClusterFLAlgo(DriftAlgo):
         iters = [(lambda c, m=m: select_iterations(retrain, t, c) if self.assign[c] == m else [])
                  for m in range(self.args.concept_num)]
         return self._index_plan(t, iters)
+
+    def state_dict(self):
+        return {"clusterfl": {"assign": self.assign.copy(), "split_done": bool(self.split_done)}}
+
+    def load_state_dict(self, d):
+        if "clusterfl" in d:
+            self.assign = np.asarray(d["clusterfl"]["assign"], dtype=np.int64).copy()
+            self.split_done = bool(d["clusterfl"]["split_done"])
 
     def on_client_updates(self, t: int, client_params: torch.Tensor, n: torch.Tensor) -> bool:
         """Called by the generic path at the split round with raw local models; returns True if split."""

@@ -37,8 +37,35 @@ def save(sim, path: str) -> str:
     return path
 
 
+def _safe_globals():
+    """Checkpoints hold tensors, numpy arrays and plain containers only — load them with the restricted unpickler
+    (``weights_only=True``) plus an allow-list of the numpy reconstruction helpers, never arbitrary objects."""
+    import numpy as np
+    allow = [np.ndarray, np.dtype, np.random.RandomState]
+    for mod, name in (("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+                      ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar")):
+        try:
+            allow.append(getattr(__import__(mod, fromlist=[name]), name))
+        except Exception:  # noqa: BLE001 — module layout differs between numpy 1.x / 2.x
+            pass
+    for t in ("bool_", "int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "float16", "float32", "float64"):
+        allow.append(getattr(np, t))
+    try:
+        allow += [type(np.dtype(t)) for t in ("bool", "int32", "int64", "uint32", "float32", "float64")]
+    except Exception:  # noqa: BLE001
+        pass
+    return allow
+
+
 def load(path: str) -> Dict:
-    return torch.load(path, map_location="cpu", weights_only=False)
+    try:
+        with torch.serialization.safe_globals(_safe_globals()):
+            return torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as exc:  # noqa: BLE001
+        if os.environ.get("FDB_TRUSTED_CHECKPOINTS") == "1":   # legacy blobs with arbitrary pickled objects: opt-in only
+            return torch.load(path, map_location="cpu", weights_only=False)
+        raise RuntimeError(f"checkpoint {path} is not loadable with the restricted unpickler ({exc}); set "
+                           "FDB_TRUSTED_CHECKPOINTS=1 to unpickle a checkpoint you trust") from exc
 
 
 def resume(sim, path: str) -> int:
@@ -71,6 +98,6 @@ def export_model_params(sim, path: str = "model_params.pt") -> str:
 
 
 def import_model_params(sim, path: str = "model_params.pt") -> None:
-    params = torch.load(path, map_location="cpu", weights_only=False)
+    params = torch.load(path, map_location="cpu", weights_only=True)   # {m: state_dict} of plain tensors
     for m, sd in params.items():
         sim.bank.load_state_dict(int(m), sd)

@@ -97,6 +97,18 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
             cl.n.copy_(torch.from_numpy(n_host), non_blocking=True)
         # raw-update hooks (CFL family) may veto the aggregation of this round
         skip = False
+        wants_raw = (hasattr(sim.algo, "state") and "cfl" in getattr(sim.algo, "arg", "")) or \
+            (hasattr(sim.algo, "on_client_updates") and not sim.algo.split_done and rnd == sim.algo.split_round)
+        if world > 1 and wants_raw:
+            # every rank trained only its own clients, but the split decision (norms, cosine bipartition, slot allocation)
+            # must be taken on ALL updates and identically everywhere: complete the arena first (cold path, NCCL)
+            import torch.distributed as dist
+            others = [c for c in range(C) if c % world != rank]
+            if others:
+                cl.params[others] = 0
+                cl.n[others] = 0
+            dist.all_reduce(cl.params)
+            dist.all_reduce(cl.n)
         if hasattr(sim.algo, "state") and "cfl" in getattr(sim.algo, "arg", ""):
             skip = sim.algo.state.cluster_cfl(t, rnd + 1, bank, cl.params, cl.n)
             if skip:

@@ -330,6 +330,36 @@ Tensor group_norm_fwd(Tensor x, int64_t groups, c10::optional<Tensor> w, c10::op
     return y;
 }
 
+// training forward: also returns the per-(sample, group) mean / rstd the backward kernel needs
+std::vector<Tensor> group_norm_fwd_train(Tensor x, int64_t groups, c10::optional<Tensor> w, c10::optional<Tensor> b, double eps) {
+    CHECK_CUDA_F32(x);
+    TORCH_CHECK(x.is_contiguous(), "group_norm: x must be contiguous NCHW");
+    c10::cuda::CUDAGuard guard(x.device());
+    auto y = torch::empty_like(x);
+    const int N = (int)x.size(0), C = (int)x.size(1);
+    const int HW = (int)(x.numel() / ((int64_t)N * C));
+    auto mean = torch::empty({N * groups}, x.options());
+    auto rstd = torch::empty({N * groups}, x.options());
+    CHECK_OK(fdb::group_norm_fwd_launch(x.data_ptr<float>(), y.data_ptr<float>(), opt_ptr<float>(w), opt_ptr<float>(b), N, C, HW, (int)groups,
+                                        (float)eps, cur_stream(), mean.data_ptr<float>(), rstd.data_ptr<float>()), "group_norm_fwd");
+    return {y, mean, rstd};
+}
+// -> (dx, dgamma [C], dbeta [C])
+std::vector<Tensor> group_norm_bwd(Tensor x, Tensor dy, c10::optional<Tensor> w, Tensor mean, Tensor rstd, int64_t groups) {
+    CHECK_CUDA_F32(x); CHECK_CUDA_F32(dy); CHECK_CUDA_F32(mean); CHECK_CUDA_F32(rstd);
+    TORCH_CHECK(x.is_contiguous() && dy.is_contiguous() && x.sizes() == dy.sizes(), "group_norm_bwd: contiguous x / dy of equal shape");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int N = (int)x.size(0), C = (int)x.size(1);
+    const int HW = (int)(x.numel() / ((int64_t)N * C));
+    auto dx = torch::empty_like(x);
+    auto dg = torch::empty({N, C}, x.options());
+    auto db = torch::empty({N, C}, x.options());
+    CHECK_OK(fdb::group_norm_bwd_launch(x.data_ptr<float>(), dy.data_ptr<float>(), opt_ptr<float>(w), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                                        dx.data_ptr<float>(), dg.data_ptr<float>(), db.data_ptr<float>(), N, C, HW, (int)groups, cur_stream()),
+             "group_norm_bwd");
+    return {dx, dg.sum(0), db.sum(0)};
+}
+
 Tensor gemm_tn_bias_act(Tensor A, Tensor B, c10::optional<Tensor> bias, bool relu, bool out_fp32) {
     TORCH_CHECK(A.is_cuda() && A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm_tn needs CUDA bf16 operands");
     TORCH_CHECK(A.is_contiguous() && B.is_contiguous() && A.size(1) == B.size(1), "gemm_tn: A [M,K], B [N,K] contiguous");
@@ -548,6 +578,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("kd_kl_fwd_bwd", &kd_kl_fwd_bwd);
     m.def("vfl_bce_grad", &vfl_bce_grad);
     m.def("group_norm_fwd", &group_norm_fwd);
+    m.def("group_norm_fwd_train", &group_norm_fwd_train);
+    m.def("group_norm_bwd", &group_norm_bwd);
     m.def("gemm_tn_bias_act", &gemm_tn_bias_act);
     m.def("gemm_tn_bias_act_peer", &gemm_tn_bias_act_peer);
     m.def("gemm_bias_act", &gemm_bias_act);

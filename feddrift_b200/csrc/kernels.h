@@ -44,7 +44,9 @@ int modp_matmul_launch(const long long* A, const long long* B, long long* C, int
 int kd_kl_launch(const float* s, const float* t, int B, int K, float T, float* loss1, float* grad_s, cudaStream_t stream);
 int vfl_bce_launch(const float* parts, const float* y, int K, int B, float* loss1, float* grad, cudaStream_t stream);
 int group_norm_fwd_launch(const float* x, float* y, const float* w, const float* b, int N, int C, int HW, int G, float eps,
-                          cudaStream_t stream);
+                          cudaStream_t stream, float* mean_out = nullptr, float* rstd_out = nullptr);
+int group_norm_bwd_launch(const float* x, const float* dy, const float* w, const float* mean, const float* rstd, float* dx, float* dg_part,
+                          float* db_part, int N, int C, int HW, int G, cudaStream_t stream);
 // gemm_tc.cu : D[M,N] (fp32 or bf16) = act(A[M,K] · B[N,K]^T + bias[N]); A,B bf16 row-major (K contiguous)
 int gemm_split_count(int M, int N, int K);
 int gemm_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int a_mn, int b_mn, int relu, int out_fp32,

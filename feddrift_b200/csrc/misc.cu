@@ -72,7 +72,8 @@ int vfl_bce_launch(const float* parts, const float* y, int K, int B, float* loss
 // (mean/var with fp32 Welford-free two-moment sum, then normalise + affine).  The reference reshapes into
 // F.batch_norm (model/cv/group_normalization.py:35-40) — 4 eager kernels + 2 reshapes.
 __global__ void __launch_bounds__(256) group_norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
-                                                             const float* __restrict__ b, int C, int HW, int G, float eps) {
+                                                             const float* __restrict__ b, int C, int HW, int G, float eps,
+                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     __shared__ float red[32];
     const int n = blockIdx.x / G, g = blockIdx.x % G;
     const int cpg = C / G;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) group_norm_fwd_kernel(const float* __rest
     const float mean = s / (float)len;
     const float var = fmaxf(s2 / (float)len - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
+    if (mean_out && threadIdx.x == 0) { mean_out[blockIdx.x] = mean; rstd_out[blockIdx.x] = rstd; }   // saved for the backward kernel
     for (int i = threadIdx.x; i < len; i += blockDim.x) {
         const int c = g * cpg + i / HW;
         const float gamma = w ? w[c] : 1.f, beta = b ? b[c] : 0.f;
@@ -91,8 +93,50 @@ __global__ void __launch_bounds__(256) group_norm_fwd_kernel(const float* __rest
     }
 }
 int group_norm_fwd_launch(const float* x, float* y, const float* w, const float* b, int N, int C, int HW, int G, float eps,
-                          cudaStream_t stream) {
-    group_norm_fwd_kernel<<<N * G, 256, 0, stream>>>(x, y, w, b, C, HW, G, eps);
+                          cudaStream_t stream, float* mean_out, float* rstd_out) {
+    group_norm_fwd_kernel<<<N * G, 256, 0, stream>>>(x, y, w, b, C, HW, G, eps, mean_out, rstd_out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// GroupNorm backward, NCHW: one CTA per (n, group).  Pass 1 walks the group's channels: per-channel Σdy and Σdy·x̂ (written
+// as [N, C] partials for dγ/dβ — summed over N by the caller, deterministic) and the group sums Σγ·dy, Σγ·dy·x̂; pass 2 writes
+// dx = rstd·(γ·dy − mean_g(γ·dy) − x̂·mean_g(γ·dy·x̂)).  (Reference: autograd through the F.batch_norm reshaping trick,
+// model/cv/group_normalization.py:35-40 — ~10 eager kernels.)
+__global__ void __launch_bounds__(256) group_norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ w,
+                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                             float* __restrict__ dx, float* __restrict__ dg_part, float* __restrict__ db_part,
+                                                             int C, int HW, int G) {
+    __shared__ float red[32];
+    const int n = blockIdx.x / G, g = blockIdx.x % G;
+    const int cpg = C / G;
+    const size_t base = ((size_t)n * C + (size_t)g * cpg) * HW;
+    const float mean = mean_in[blockIdx.x], rstd = rstd_in[blockIdx.x];
+    float s1 = 0.f, s2 = 0.f;   // Σ γ·dy, Σ γ·dy·x̂ over the group (identical in every thread after the block sums)
+    for (int cc = 0; cc < cpg; ++cc) {
+        const int c = g * cpg + cc;
+        const float gamma = w ? w[c] : 1.f;
+        float a = 0.f, bsum = 0.f;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+            const float d = dy[base + (size_t)cc * HW + i];
+            const float xh = (x[base + (size_t)cc * HW + i] - mean) * rstd;
+            a += d; bsum = fmaf(d, xh, bsum);
+        }
+        a = block_sum(a, red); bsum = block_sum(bsum, red);
+        if (threadIdx.x == 0) { db_part[(size_t)n * C + c] = a; dg_part[(size_t)n * C + c] = bsum; }
+        s1 = fmaf(gamma, a, s1); s2 = fmaf(gamma, bsum, s2);
+    }
+    const float inv = 1.f / (float)(cpg * HW);
+    const float m1 = s1 * inv, m2 = s2 * inv;
+    for (int i = threadIdx.x; i < cpg * HW; i += blockDim.x) {
+        const int c = g * cpg + i / HW;
+        const float gamma = w ? w[c] : 1.f;
+        const float xh = (x[base + i] - mean) * rstd;
+        dx[base + i] = rstd * (gamma * dy[base + i] - m1 - xh * m2);
+    }
+}
+int group_norm_bwd_launch(const float* x, const float* dy, const float* w, const float* mean, const float* rstd, float* dx, float* dg_part,
+                          float* db_part, int N, int C, int HW, int G, cudaStream_t stream) {
+    group_norm_bwd_kernel<<<N * G, 256, 0, stream>>>(x, dy, w, mean, rstd, dx, dg_part, db_part, C, HW, G);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

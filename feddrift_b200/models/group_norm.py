@@ -1,9 +1,10 @@
 """GroupNorm2d / GroupNorm3d (K16).
 
 Parity: ``fedml_api/model/cv/group_normalization.py:7-118`` (the reference implements GN by reshaping into
-``F.batch_norm``).  Here inference (``torch.no_grad``) runs the fused sm_100a kernel ``ops.group_norm`` (one CTA
-per (sample, group), two passes over the contiguous slab); training goes through ``F.group_norm`` so autograd
-works.  Parameter names (``weight``, ``bias``) match.
+``F.batch_norm``).  On CUDA both directions are the fused sm_100a kernels of ``csrc/misc.cu`` through ``ops.group_norm``
+(forward: one CTA per (sample, group), two passes over the contiguous slab, saves mean / rstd; backward: one CTA per
+(sample, group) producing dx and per-sample dγ / dβ partials); CPU tensors use ``F.group_norm``.  Parameter names
+(``weight``, ``bias``) match.
 """
 from __future__ import annotations
 
@@ -39,7 +40,7 @@ class _GroupNorm(nn.Module):
 
     def forward(self, x):
         self._check_input_dim(x)
-        if not torch.is_grad_enabled():
+        if x.is_cuda:
             return ops.group_norm(x, self.num_groups, self.weight, self.bias, self.eps)
         return F.group_norm(x, self.num_groups, self.weight, self.bias, self.eps)
 

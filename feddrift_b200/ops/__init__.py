@@ -208,7 +208,27 @@ def vfl_bce_grad(logit_parts, y):
     return ref.vfl_bce_grad(logit_parts, y)
 
 
+class _GroupNormFn(torch.autograd.Function):
+    """K16 with autograd: fused forward (saves per-group mean / rstd) + fused backward kernel (csrc/misc.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups, eps):
+        xc = x.float().contiguous()
+        y, mean, rstd = _ext.load().group_norm_fwd_train(xc, int(groups), weight, bias, float(eps))
+        ctx.save_for_backward(xc, weight, mean, rstd)
+        ctx.groups, ctx.has_bias = int(groups), bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dg, db = _ext.load().group_norm_bwd(x, dy.float().contiguous(), weight, mean, rstd, ctx.groups)
+        return dx, (dg if weight is not None else None), (db if ctx.has_bias else None), None, None
+
+
 def group_norm(x, groups: int, weight=None, bias=None, eps: float = 1e-5):
-    if native(x) and not torch.is_grad_enabled():
+    if native(x):
+        if torch.is_grad_enabled() and (x.requires_grad or (weight is not None and weight.requires_grad)):
+            return _GroupNormFn.apply(x, weight, bias, int(groups), float(eps))
         return _ext.load().group_norm_fwd(x.float().contiguous(), int(groups), weight, bias, float(eps))
     return ref.group_norm(x, groups, weight, bias, eps)

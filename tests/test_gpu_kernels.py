@@ -225,3 +225,19 @@ def test_group_norm_module_trains_through_fused_kernels():
     x = torch.randn(2, 16, 6, 6, device="cuda", requires_grad=True)
     m(x).square().sum().backward()
     assert x.grad is not None and m.weight.grad is not None and torch.isfinite(x.grad).all()
+
+
+@pytest.mark.parametrize("p", [2 ** 31 - 1, 2 ** 61 - 1, (1 << 62) + 135, 65537, 97, 1 << 20, (1 << 40) + 2])
+def test_modp_matmul_montgomery_exact(p):
+    """K13: Montgomery (odd p) / shift-subtract (even p) finite-field GEMM is bit-exact vs python big-int arithmetic."""
+    g = torch.Generator().manual_seed(p % 1000)
+    M, K, N = 37, 83, 21
+    hi = min(p, 2 ** 62)
+    A = torch.randint(0, hi, (M, K), generator=g, dtype=torch.int64)
+    B = torch.randint(0, hi, (K, N), generator=g, dtype=torch.int64)
+    A[0, :] = p - 1
+    B[:, 0] = p - 1           # worst-case residues
+    A[1, 0] = -5              # negative inputs are reduced into [0, p)
+    want = [[sum((int(A[i, k]) % p) * (int(B[k, j]) % p) for k in range(K)) % p for j in range(N)] for i in range(M)]
+    got = ops.modp_matmul(A.cuda(), B.cuda(), p).cpu()
+    assert got.tolist() == want

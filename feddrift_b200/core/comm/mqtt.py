@@ -5,10 +5,13 @@ Parity: ``fedml_core/distributed/communication/mqtt/mqtt_comm_manager.py:14-126`
 ``<topic>0_<cid>``; clients do the reverse; payload = ``Message.to_json()`` so
 tensors travel as nested lists (the ``is_mobile`` wire form).
 
-paho-mqtt is not part of this image, so the default broker is an in-process
-:class:`LocalBroker` with the same topic semantics (used by the mobile serving
-façade and its tests).  If ``paho`` is importable and a host is given, a real
-network broker is used instead.
+Transports: with ``host``/``port`` the manager speaks REAL MQTT 3.1.1 over TCP
+through the dependency-free client of :mod:`.mqtt_wire` (CONNECT / SUBSCRIBE /
+PUBLISH QoS-0 / PINGREQ framing, interoperable with mosquitto / EMQX and with
+the embedded :class:`~.mqtt_wire.MqttBroker`); if ``paho`` happens to be
+importable it is used instead.  Without a host, an in-process
+:class:`LocalBroker` with the same topic semantics is used (single-process
+simulations and tests).
 """
 from __future__ import annotations
 
@@ -65,6 +68,7 @@ class MqttCommManager(BaseCommunicationManager):
         self._inbox: "queue.Queue" = queue.Queue()
         self.is_running = True
         self._paho = None
+        self._wire = None
         if broker is None and host is not None:
             try:  # pragma: no cover - paho is not in this image
                 import paho.mqtt.client as mqtt
@@ -74,10 +78,18 @@ class MqttCommManager(BaseCommunicationManager):
                 self._paho.loop_start()
             except ImportError:
                 self._paho = None
-        self._broker = broker if broker is not None else (None if self._paho else LocalBroker.default())
+            if self._paho is None:
+                # the real protocol without paho: MQTT 3.1.1 over a TCP socket (mqtt_wire.MqttClient)
+                from .mqtt_wire import MqttClient
+                self._wire = MqttClient(f"{topic}-{self._client_id}",
+                                        on_message=lambda t, p: self._on_message(t, p.decode("utf-8")))
+                self._wire.connect(host, port)
+        self._broker = broker if broker is not None else (None if (self._paho or self._wire) else LocalBroker.default())
         for t in self._rx_topics():
             if self._paho is not None:  # pragma: no cover
                 self._paho.subscribe(t, 0)
+            elif self._wire is not None:
+                self._wire.subscribe(t, 0)
             else:
                 self._broker.subscribe(t, self._on_message)
 
@@ -106,6 +118,8 @@ class MqttCommManager(BaseCommunicationManager):
         payload = msg.to_json()
         if self._paho is not None:  # pragma: no cover
             self._paho.publish(self._tx_topic(msg), payload=payload)
+        elif self._wire is not None:
+            self._wire.publish(self._tx_topic(msg), payload)
         else:
             self._broker.publish(self._tx_topic(msg), payload)
 
@@ -136,3 +150,5 @@ class MqttCommManager(BaseCommunicationManager):
         if self._paho is not None:  # pragma: no cover
             self._paho.loop_stop()
             self._paho.disconnect()
+        if self._wire is not None:
+            self._wire.disconnect()

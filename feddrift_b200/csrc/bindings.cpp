@@ -504,9 +504,13 @@ static fdb::LstmArgs lstm_args(const Tensor& params, const Tensor& row_off, cons
 }
 
 void lstm2_forward(Tensor params, Tensor row_off, std::vector<int64_t> offs, Tensor tokens, c10::optional<Tensor> gates,
-                   c10::optional<Tensor> cst, c10::optional<Tensor> hhist, Tensor hlast, int64_t E) {
+                   c10::optional<Tensor> cst, c10::optional<Tensor> hhist, Tensor hlast, int64_t E, c10::optional<Tensor> dbg) {
     c10::cuda::CUDAGuard guard(params.device());
     fdb::LstmArgs a = lstm_args(params, row_off, offs, tokens, gates, cst, hhist, hlast, E);
+    if (dbg.has_value() && dbg->defined()) {
+        TORCH_CHECK(dbg->is_cuda() && dbg->scalar_type() == torch::kInt64 && dbg->numel() >= 8, "dbg must be a CUDA int64[8] tensor");
+        a.dbg = reinterpret_cast<long long*>(dbg->data_ptr<int64_t>());
+    }
     CHECK_OK(fdb::lstm2_fwd_launch(a, (int)tokens.size(0), cur_stream()), "lstm2_fwd (tcgen05 cluster kernel)");
 }
 
@@ -552,6 +556,29 @@ void lstm_head(Tensor params, Tensor row_off, int64_t off_fcw, int64_t off_fcb, 
     CHECK_OK(fdb::lstm_head_launch(a, (int)n, cur_stream()), "lstm_head");
 }
 
+// bias / W_ih1 / embedding gradients of every chunk from the gate-gradient histories (lstm_tc.cu::lstm_small_grads_kernel)
+std::vector<Tensor> lstm_small_grads(Tensor params, Tensor row_off, int64_t off_emb, int64_t off_wih1, Tensor tokens, Tensor dgates,
+                                     int64_t E, int64_t V) {
+    CHECK_CUDA_F32(params); CHECK_CUDA_I32(tokens);
+    TORCH_CHECK(row_off.is_cuda() && row_off.scalar_type() == torch::kInt64, "row_off must be a CUDA int64 tensor");
+    TORCH_CHECK(dgates.is_cuda() && dgates.scalar_type() == torch::kBFloat16 && dgates.is_contiguous(), "dgates must be CUDA bf16");
+    c10::cuda::CUDAGuard guard(params.device());
+    const int64_t n = tokens.size(0), T = tokens.size(2);
+    TORCH_CHECK(row_off.numel() == n && dgates.numel() == 2 * n * T * 16 * 1024, "lstm_small_grads: sizes");
+    auto o = params.options();
+    auto db1 = torch::empty({n, 1024}, o), db2 = torch::empty({n, 1024}, o), dw = torch::empty({n, 1024, E}, o);
+    auto de = torch::empty({n, 8, V, E}, o);
+    fdb::LstmSmallArgs a{};
+    a.params = params.data_ptr<float>();
+    a.row_off = reinterpret_cast<const long long*>(row_off.data_ptr<int64_t>());
+    a.off_emb = off_emb; a.off_wih1 = off_wih1;
+    a.tokens = tokens.data_ptr<int>(); a.dgates = dgates.data_ptr();
+    a.db1 = db1.data_ptr<float>(); a.db2 = db2.data_ptr<float>(); a.dwih1 = dw.data_ptr<float>(); a.demb_part = de.data_ptr<float>();
+    a.T = (int)T; a.E = (int)E; a.V = (int)V;
+    CHECK_OK(fdb::lstm_small_grads_launch(a, (int)n, cur_stream()), "lstm_small_grads");
+    return {db1, db2, dw, de.sum(1)};
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -591,4 +618,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("lstm2_forward", &lstm2_forward);
     m.def("lstm2_backward", &lstm2_backward);
     m.def("lstm_head", &lstm_head);
+    m.def("lstm_small_grads", &lstm_small_grads);
 }

@@ -69,6 +69,7 @@ struct LstmArgs {
     const float* dh2_last;        // [npairs, 16, 256] gradient wrt h2_{T-1}            (used when dh2_all == nullptr)
     const float* dh2_all;         // [npairs, T, 16, 256] gradient wrt every h2_t, or nullptr
     void* dgates;                 // [2, npairs, T, 16, 1024] bf16 pre-activation gate gradients (PyTorch row order)
+    long long* dbg;               // optional [8] per-segment SM-clock sums of the forward phase loop (CTA 0, thread 0)
     int T, E;
 };
 struct LstmHeadArgs {
@@ -85,6 +86,19 @@ struct LstmHeadArgs {
     int V;
 };
 int lstm_head_launch(const LstmHeadArgs& a, int nchunks, cudaStream_t stream);
+struct LstmSmallArgs {
+    const float* params;          // parameter arena base
+    const long long* row_off;     // [nchunks]
+    long long off_emb, off_wih1;
+    const int* tokens;            // [nchunks, 16, T]
+    const void* dgates;           // [2, nchunks, T, 16, 1024] bf16
+    float* db1;                   // [nchunks, 1024]
+    float* db2;                   // [nchunks, 1024]
+    float* dwih1;                 // [nchunks, 1024, E]
+    float* demb_part;             // [nchunks, 8, V, E]  (summed over the 8 column slices by the caller)
+    int T, E, V;
+};
+int lstm_small_grads_launch(const LstmSmallArgs& a, int nchunks, cudaStream_t stream);
 int lstm2_fwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream);
 int lstm2_bwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream);
 }  // namespace fdb

@@ -40,8 +40,10 @@ namespace fdb {
 
 namespace lstm {
 constexpr int H = 256, CL = 8, U = 32, NB = 16, KX = 16;
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;      // backward kernel
+constexpr int kFwdThreads = 288;   // forward: 2 epilogue groups of 4 warps + 1 issuer warp
 // forward TMEM map (columns)
+// accumulators: D1 = 2 × 16 columns (split K), D2 = 4 × 16 columns
 constexpr uint32_t A1_COL = 0, A1_XCOL = 128, A2_COL = 136, D1_COL = 392, D2_COL = 424, F_TMEM = 512;
 // backward TMEM map: three transposed matrices × 2 tiles × 64 columns, then 6 accumulators × 16 columns
 constexpr uint32_t BT_HH2 = 0, BT_IH2 = 128, BT_HH1 = 256, BD_REC2 = 384, BD_IN1 = 416, BD_REC1 = 448, B_TMEM = 512;
@@ -117,6 +119,11 @@ FDB_DEVICE uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x (low half) = lo
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// MUFU.TANH: one instruction, |abs err| ≲ 5e-4 — far below the bf16 rounding of the operands these activations feed; the
+// forward saves the activations it used, so BPTT differentiates exactly the function that was evaluated
+FDB_DEVICE float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+FDB_DEVICE float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+FDB_DEVICE void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 FDB_DEVICE float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
 FDB_DEVICE float tanh_f(float x) { return 2.f / (1.f + __expf(-2.f * x)) - 1.f; }
 
@@ -138,14 +145,21 @@ FDB_DEVICE void load_row_chunk_to_tmem(const float* __restrict__ src, uint32_t t
 }
 
 // ======================================================================================================= forward
-__global__ void __cluster_dims__(lstm::CL, 1, 1) __launch_bounds__(lstm::kThreads, 1)
+// Warp roles (288 threads): warps 0-3 = layer-1 epilogue group, warps 4-7 = layer-2 epilogue group (warp w reads TMEM lanes
+// 32·(w mod 4) … = gate (w mod 4) of the CTA's 32 units), warp 8 = tcgen05.mma issuer.  Per phase the issuer waits for the
+// inbound hidden-state slices (mbarrier tx count), issues the layer-1 chain (2 interleaved accumulators → commit bar 1) and
+// the layer-2 chain (4 interleaved accumulators → commit bar 2): tiny M128×N16×K16 MMAs that accumulate into ONE tile are
+// latency-bound (~57 cycles each back to back), independent accumulators overlap that latency and are summed by the
+// epilogue.  Each group runs epilogue → cell update → staging → DSMEM broadcast on its own named barrier, so the layer-1
+// epilogue overlaps the layer-2 MMAs.
+__global__ void __cluster_dims__(lstm::CL, 1, 1) __launch_bounds__(lstm::kFwdThreads, 1)
 lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
     using namespace lstm;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int pair = blockIdx.x / CL;
-    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
     const int T = a.T, E = a.E;
 
     // ---- shared memory carve-up
@@ -155,8 +169,8 @@ lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
     __nv_bfloat16* stage = Xs + 2 * NB * KX;                                     // [2 parities][2 layers][NB*32]
     float* act_s = reinterpret_cast<float*>(stage + 2 * 2 * NB * U);             // [2 layers][4 gates][NB][32]
     uint64_t* hbar = reinterpret_cast<uint64_t*>(act_s + 2 * 4 * NB * U);        // [2]
-    uint64_t* mma_bar = hbar + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    uint64_t* mma_bar = hbar + 2;                                                // [2]: layer 1, layer 2
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 2);
 
     const float* prow = a.params + a.row_off[pair];
     const float* w_ih1 = prow + a.off_wih1;
@@ -167,26 +181,29 @@ lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
     const int* tok = a.tokens + (size_t)pair * NB * T;
 
     if (tid == 0) {
-        mbar_init(hbar + 0, 1); mbar_init(hbar + 1, 1); mbar_init(mma_bar, 1);
+        mbar_init(hbar + 0, 1); mbar_init(hbar + 1, 1); mbar_init(mma_bar + 0, 1); mbar_init(mma_bar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (w == 0) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(F_TMEM));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // zero the operand buffers (h_{-1} = 0, padded x columns = 0) and write x_0
-    for (int i = tid; i < (2 * NB * H * 2 + 2 * NB * KX) / 2; i += kThreads) reinterpret_cast<uint32_t*>(H1s)[i] = 0u;
+    // zero the operand buffers (h_{-1} = 0, padded x columns = 0)
+    for (int i = tid; i < (2 * NB * H * 2 + 2 * NB * KX) / 2; i += kFwdThreads) reinterpret_cast<uint32_t*>(H1s)[i] = 0u;
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_ptr_smem;
-    const uint32_t lane_addr = tmem + ((uint32_t)(w * 32) << 16);
 
-    // ---- weights → TMEM (this thread owns gate row r = tid: gate w, local unit l)
-    const int R = w * H + crank * U + l;              // row of the PyTorch [4H, K] weight matrices
+    const int grp = warp >> 2;                      // 0: layer-1 group, 1: layer-2 group, 2: issuer warp
+    const int w = warp & 3, gt = tid & 127;         // gate index / thread index inside the group
+    const uint32_t lane_addr = tmem + ((uint32_t)(w * 32) << 16);
+    const int R = w * H + crank * U + l;            // row of the PyTorch [4H, K] weight matrices owned by this thread
+    float bias = 0.f;
+    if (grp == 0) {
+        // ---- layer-1 weights → TMEM: A1 = [W_hh1 | W_ih1]
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_hh1 + (size_t)R * H + 64 * c, lane_addr + A1_COL + 32 * c);
-    {
+        for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_hh1 + (size_t)R * H + 64 * c, lane_addr + A1_COL + 32 * c);
         uint32_t v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -195,156 +212,162 @@ lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
             v[j] = pack_bf16(lo, hi);
         }
         tmem_st_x8(lane_addr + A1_XCOL, v);
-    }
+        tmem_st_wait();
+        bias = __ldg(prow + a.off_bih1 + R) + __ldg(prow + a.off_bhh1 + R);
+        for (int i = gt; i < NB * KX; i += 128) {    // x_0 → Xs[0]
+            const int b = i / KX, k = i % KX;
+            const float xv = (k < E) ? __ldg(emb + (size_t)tok[b * T + 0] * E + k) : 0.f;
+            Xs[op_off(b, k)] = __float2bfloat16(xv);
+        }
+    } else if (grp == 1) {
+        // ---- layer-2 weights → TMEM: A2 = [W_ih2 | W_hh2]
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_ih2 + (size_t)R * H + 64 * c, lane_addr + A2_COL + 32 * c);
+        for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_ih2 + (size_t)R * H + 64 * c, lane_addr + A2_COL + 32 * c);
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_hh2 + (size_t)R * H + 64 * c, lane_addr + A2_COL + 128 + 32 * c);
-    tmem_st_wait();
-    const float bias1 = __ldg(prow + a.off_bih1 + R) + __ldg(prow + a.off_bhh1 + R);
-    const float bias2 = __ldg(prow + a.off_bih2 + R) + __ldg(prow + a.off_bhh2 + R);
-
-    // x_0 → Xs[0]
-    for (int i = tid; i < NB * KX; i += kThreads) {
-        const int b = i / KX, k = i % KX;
-        const float v = (k < E) ? __ldg(emb + (size_t)tok[b * T + 0] * E + k) : 0.f;
-        Xs[op_off(b, k)] = __float2bfloat16(v);
+        for (int c = 0; c < 4; ++c) load_row_chunk_to_tmem(w_hh2 + (size_t)R * H + 64 * c, lane_addr + A2_COL + 128 + 32 * c);
+        tmem_st_wait();
+        bias = __ldg(prow + a.off_bih2 + R) + __ldg(prow + a.off_bhh2 + R);
     }
     fence_proxy_async_smem();
     tcgen05_fence_before();
     cluster.sync();            // every CTA's barriers / buffers are initialised before any peer writes into them
     tcgen05_fence_after();
 
-    // cell-phase ownership: unit ul = l, batch rows b = w + 4 i
-    float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-    const int unit = crank * U + l;
-    // history layout is LAYER-outermost: [2][npairs][T (+1)][16][...] so that one layer's rows of consecutive pairs form one
-    // [npairs·T·16, 1024] matrix for the batched weight-gradient GEMMs
+    // history layout is LAYER-outermost: [2][npairs][T (+1)][16][...]
     const int NP = (int)gridDim.x / CL;
     const bool keep = a.gates != nullptr;            // training: save gates / cell states for BPTT
     const bool keep_h = a.hhist != nullptr;
-    float* gates_l[2] = {a.gates + (size_t)(0 * NP + pair) * T * NB * 4 * H, a.gates + (size_t)(1 * NP + pair) * T * NB * 4 * H};
-    float* cst_l[2] = {a.cst + (size_t)(0 * NP + pair) * T * NB * H, a.cst + (size_t)(1 * NP + pair) * T * NB * H};
-    __nv_bfloat16* hh_l[2] = {reinterpret_cast<__nv_bfloat16*>(a.hhist) + (size_t)(0 * NP + pair) * (T + 1) * NB * H,
-                              reinterpret_cast<__nv_bfloat16*>(a.hhist) + (size_t)(1 * NP + pair) * (T + 1) * NB * H};
-    // history row 0 (h_{-1} = 0) is zeroed by the host once; rows t+1 are written below
+    const int unit = crank * U + l;
+    const bool dbg = a.dbg != nullptr && blockIdx.x == 0;
+    const uint32_t bytes_each = NB * U * 2;
 
-    for (int p = 0; p <= T; ++p) {
-        const bool doL1 = p < T, doL2 = p >= 1;
-        if (p >= 1) mbar_wait_long(hbar + ((p - 1) & 1), ((p - 1) >> 1) & 1);   // h1_{p-1} (and h2_{p-2}) from all 8 CTAs
-        if (tid == 0) {
+    if (grp == 2) {
+        // =================================================== MMA issuer (one elected lane)
+        if (l == 0) {
+            long long seg[3] = {0, 0, 0}, tprev = clock64();
+            for (int p = 0; p <= T; ++p) {
+                const bool doL1 = p < T, doL2 = p >= 1;
+                // arm this phase's inbound barrier first (the slices of phase p land in hbar[p&1])
+                if (p < T) mbar_expect_tx(hbar + (p & 1), CL * bytes_each * ((doL1 ? 1u : 0u) + (doL2 ? 1u : 0u)));
+                if (p >= 1) mbar_wait_long(hbar + ((p - 1) & 1), ((p - 1) >> 1) & 1);   // h1_{p-1} (and h2_{p-2}) from all 8 CTAs
+                if (dbg) { const long long tn = clock64(); seg[0] += tn - tprev; tprev = tn; }
+                tcgen05_fence_after();
+                const uint32_t h1prev = smem_u32(H1s + ((p + 1) & 1) * NB * H);     // h1_{p-1}
+                if (doL1) {
+                    // two accumulators: k-steps alternate; the x step joins accumulator 1
+#pragma unroll
+                    for (int s = 0; s < 16; ++s)
+                        umma_ts_f16(tmem + D1_COL + 16 * (s & 1), tmem + A1_COL + 8 * s, make_desc_nosw(h1prev + s * 2 * kLBO), kIdesc, s > 1 ? 1u : 0u);
+                    umma_ts_f16(tmem + D1_COL + 16, tmem + A1_XCOL, make_desc_nosw(smem_u32(Xs + (p & 1) * NB * KX)), kIdesc, 1u);
+                    tcgen05_commit(mma_bar + 0);
+                }
+                if (doL2) {
+                    const uint32_t h2prev = smem_u32(H2s + (p & 1) * NB * H);       // h2_{p-2}
+                    // four accumulators: (h1 even, h1 odd, h2 even, h2 odd) k-steps, issued round-robin
+#pragma unroll
+                    for (int s = 0; s < 16; ++s) {
+                        umma_ts_f16(tmem + D2_COL + 16 * (s & 1), tmem + A2_COL + 8 * s, make_desc_nosw(h1prev + s * 2 * kLBO), kIdesc, s > 1 ? 1u : 0u);
+                        umma_ts_f16(tmem + D2_COL + 32 + 16 * (s & 1), tmem + A2_COL + 128 + 8 * s, make_desc_nosw(h2prev + s * 2 * kLBO), kIdesc,
+                                    s > 1 ? 1u : 0u);
+                    }
+                    tcgen05_commit(mma_bar + 1);
+                }
+                if (dbg) { const long long tn = clock64(); seg[1] += tn - tprev; tprev = tn; }
+            }
+            if (dbg) { a.dbg[0] = seg[0]; a.dbg[1] = seg[1]; }
+        }
+    } else {
+        // =================================================== epilogue / cell groups (layer = grp)
+        const int layer = grp;
+        float* gates_l = a.gates + (size_t)(layer * NP + pair) * T * NB * 4 * H;
+        float* cst_l = a.cst + (size_t)(layer * NP + pair) * T * NB * H;
+        __nv_bfloat16* hh_l = reinterpret_cast<__nv_bfloat16*>(a.hhist) + (size_t)(layer * NP + pair) * (T + 1) * NB * H;
+        float* act = act_s + layer * 4 * NB * U;
+        float creg[4] = {0.f, 0.f, 0.f, 0.f};
+        const int nacc = layer == 0 ? 2 : 4;
+        const uint32_t dcol = layer == 0 ? D1_COL : D2_COL;
+        long long seg[4] = {0, 0, 0, 0}, tprev = clock64();
+        const bool dbgt = dbg && gt == 0 && layer == 0;
+        // layer 1 runs in phases 0 … T-1 (time p), layer 2 in phases 1 … T (time p-1)
+        const int p_lo = layer == 0 ? 0 : 1, p_hi = layer == 0 ? T - 1 : T;
+        for (int p = p_lo; p <= p_hi; ++p) {
+            const int t = p - layer;
+            // prefetch next step's token / embedding values early (layer-1 group only): 2 values per thread
+            float xv[2] = {0.f, 0.f};
+            if (layer == 0 && p + 1 < T) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int i = gt + 128 * q, b = i / KX, k = i % KX;
+                    if (k < E) xv[q] = __ldg(emb + (size_t)__ldg(tok + b * T + p + 1) * E + k);
+                }
+            }
+            mbar_wait_long(mma_bar + layer, (p - p_lo) & 1);
             tcgen05_fence_after();
-            const uint32_t h1prev = smem_u32(H1s + ((p + 1) & 1) * NB * H);     // h1_{p-1}
-            if (doL1) {
+            if (dbgt) { const long long tn = clock64(); seg[0] += tn - tprev; tprev = tn; }
+            // ---- epilogue: this thread = gate row (gate w, unit l); 16 batch columns; sum the split accumulators
+            {
+                float z[16], z2[16];
+                tmem_ld_x16(lane_addr + dcol, z);
+                for (int q = 1; q < nacc; ++q) {
+                    tmem_ld_x16(lane_addr + dcol + 16 * q, z2);
 #pragma unroll
-                for (int s = 0; s < 16; ++s)
-                    umma_ts_f16(tmem + D1_COL, tmem + A1_COL + 8 * s, make_desc_nosw(h1prev + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
-                umma_ts_f16(tmem + D1_COL, tmem + A1_XCOL, make_desc_nosw(smem_u32(Xs + (p & 1) * NB * KX)), kIdesc, 1u);
+                    for (int b = 0; b < NB; ++b) z[b] += z2[b];
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float x = z[b] + bias;
+                    act[(w * NB + b) * U + l] = (w == 2) ? tanh_fast(x) : sigmoid_fast(x);
+                }
             }
-            if (doL2) {
-                const uint32_t h2prev = smem_u32(H2s + (p & 1) * NB * H);       // h2_{p-2}
+            tcgen05_fence_before();
+            named_bar_sync(1 + layer, 128);
+            if (dbgt) { const long long tn = clock64(); seg[1] += tn - tprev; tprev = tn; }
+            // ---- cell update for the own 32 units (unit l) × rows b = w + 4 i; stage the bf16 slice in operand layout
+            __nv_bfloat16* st = stage + ((p & 1) * 2 + layer) * NB * U;
 #pragma unroll
-                for (int s = 0; s < 16; ++s)
-                    umma_ts_f16(tmem + D2_COL, tmem + A2_COL + 8 * s, make_desc_nosw(h1prev + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
-#pragma unroll
-                for (int s = 0; s < 16; ++s)
-                    umma_ts_f16(tmem + D2_COL, tmem + A2_COL + 128 + 8 * s, make_desc_nosw(h2prev + s * 2 * kLBO), kIdesc, 1u);
-            }
-            tcgen05_commit(mma_bar);
-        }
-        mbar_wait_long(mma_bar, p & 1);
-        tcgen05_fence_after();
-
-        // ---- epilogue: this thread = gate row (gate w, unit l); 16 batch columns
-        if (doL1) {
-            float z[16];
-            tmem_ld_x16(lane_addr + D1_COL, z);
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float x = z[b] + bias1;
-                act_s[((0 * 4 + w) * NB + b) * U + l] = (w == 2) ? tanh_f(x) : sigmoid_f(x);
-            }
-        }
-        if (doL2) {
-            float z[16];
-            tmem_ld_x16(lane_addr + D2_COL, z);
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const float x = z[b] + bias2;
-                act_s[((1 * 4 + w) * NB + b) * U + l] = (w == 2) ? tanh_f(x) : sigmoid_f(x);
-            }
-        }
-        tcgen05_fence_before();
-        __syncthreads();
-
-        // ---- cell update for the own 32 units × 16 rows; stage the bf16 slice in operand layout
-        __nv_bfloat16* st1 = stage + ((p & 1) * 2 + 0) * NB * U;
-        __nv_bfloat16* st2 = stage + ((p & 1) * 2 + 1) * NB * U;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int b = w + 4 * i;
-            if (doL1) {
-                const float gi = act_s[((0 * 4 + 0) * NB + b) * U + l], gf = act_s[((0 * 4 + 1) * NB + b) * U + l];
-                const float gg = act_s[((0 * 4 + 2) * NB + b) * U + l], go = act_s[((0 * 4 + 3) * NB + b) * U + l];
-                c1[i] = gf * c1[i] + gi * gg;
-                const float h = go * tanh_f(c1[i]);
-                const size_t row = (size_t)p * NB + b;
+            for (int i = 0; i < 4; ++i) {
+                const int b = w + 4 * i;
+                const float gi = act[(0 * NB + b) * U + l], gf = act[(1 * NB + b) * U + l];
+                const float gg = act[(2 * NB + b) * U + l], go = act[(3 * NB + b) * U + l];
+                creg[i] = gf * creg[i] + gi * gg;
+                const float h = go * tanh_fast(creg[i]);
+                const size_t row = (size_t)t * NB + b;
                 if (keep) {
-                    float* g = gates_l[0] + row * 4 * H + unit;
+                    float* g = gates_l + row * 4 * H + unit;
                     g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
-                    cst_l[0][row * H + unit] = c1[i];
+                    cst_l[row * H + unit] = creg[i];
                 }
                 const __nv_bfloat16 hb = __float2bfloat16(h);
-                if (keep_h) hh_l[0][((size_t)(p + 1) * NB + b) * H + unit] = hb;
-                st1[op_off(b, l)] = hb;     // k_core = l/8 local to the slice
+                if (keep_h) hh_l[((size_t)(t + 1) * NB + b) * H + unit] = hb;
+                st[op_off(b, l)] = hb;     // k_core = l/8 local to the slice
+                if (layer == 1 && t == T - 1) a.hlast[((size_t)pair * NB + b) * H + unit] = h;
             }
-            if (doL2) {
-                const int t2 = p - 1;
-                const float gi = act_s[((1 * 4 + 0) * NB + b) * U + l], gf = act_s[((1 * 4 + 1) * NB + b) * U + l];
-                const float gg = act_s[((1 * 4 + 2) * NB + b) * U + l], go = act_s[((1 * 4 + 3) * NB + b) * U + l];
-                c2[i] = gf * c2[i] + gi * gg;
-                const float h = go * tanh_f(c2[i]);
-                const size_t row = (size_t)t2 * NB + b;
-                if (keep) {
-                    float* g = gates_l[1] + row * 4 * H + unit;
-                    g[0] = gi; g[H] = gf; g[2 * H] = gg; g[3 * H] = go;
-                    cst_l[1][row * H + unit] = c2[i];
+            if (layer == 0 && p + 1 < T) {   // x_{p+1} → Xs[(p+1)&1]
+                __nv_bfloat16* xd = Xs + ((p + 1) & 1) * NB * KX;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int i = gt + 128 * q;
+                    xd[op_off(i / KX, i % KX)] = __float2bfloat16(xv[q]);
                 }
-                const __nv_bfloat16 hb = __float2bfloat16(h);
-                if (keep_h) hh_l[1][((size_t)(t2 + 1) * NB + b) * H + unit] = hb;
-                st2[op_off(b, l)] = hb;
-                if (t2 == T - 1) a.hlast[((size_t)pair * NB + b) * H + unit] = h;
             }
-        }
-        if (p + 1 < T) {   // x_{p+1} → Xs[(p+1)&1]
-            __nv_bfloat16* xd = Xs + ((p + 1) & 1) * NB * KX;
-            for (int i = tid; i < NB * KX; i += kThreads) {
-                const int b = i / KX, k = i % KX;
-                const float v = (k < E) ? __ldg(emb + (size_t)tok[b * T + p + 1] * E + k) : 0.f;
-                xd[op_off(b, k)] = __float2bfloat16(v);
+            fence_proxy_async_smem();   // generic-proxy writes (stage, Xs) → visible to the async proxy (bulk copy, tcgen05)
+            named_bar_sync(1 + layer, 128);
+            if (dbgt) { const long long tn = clock64(); seg[2] += tn - tprev; tprev = tn; }
+            // ---- all-gather: my 1-KB slice → every CTA's next-step operand buffer (incl. my own); lane d serves CTA d.
+            //      (the last phase's h2_{T-1} is only needed as hlast, no exchange)
+            if (p < T && gt < CL) {
+                const uint32_t bar = smem_u32(hbar + (p & 1));
+                const uint32_t dst = (layer == 0 ? smem_u32(H1s + (p & 1) * NB * H) : smem_u32(H2s + ((p + 1) & 1) * NB * H)) + crank * bytes_each;
+                bulk_copy_s2c(mapa_u32(dst, gt), smem_u32(st), bytes_each, mapa_u32(bar, gt));
             }
+            if (dbgt) { const long long tn = clock64(); seg[3] += tn - tprev; tprev = tn; }
         }
-        fence_proxy_async_smem();   // generic-proxy writes (stage, Xs) → visible to the async proxy (bulk copy, tcgen05)
-        __syncthreads();
-        if (p < T && tid == 0) {
-            // ---- all-gather: my 1-KB slices → every CTA's next-step operand buffers (incl. my own)
-            const uint32_t bytes_each = NB * U * 2;
-            mbar_expect_tx(hbar + (p & 1), CL * bytes_each * ((doL1 ? 1u : 0u) + (doL2 ? 1u : 0u)));
-            const uint32_t bar = smem_u32(hbar + (p & 1));
-            const uint32_t d1 = smem_u32(H1s + (p & 1) * NB * H) + crank * bytes_each;         // h1_p slot of my units
-            const uint32_t d2 = smem_u32(H2s + ((p + 1) & 1) * NB * H) + crank * bytes_each;   // h2_{p-1}
-#pragma unroll 1
-            for (int d = 0; d < CL; ++d) {
-                const uint32_t rbar = mapa_u32(bar, d);
-                if (doL1) bulk_copy_s2c(mapa_u32(d1, d), smem_u32(st1), bytes_each, rbar);
-                if (doL2) bulk_copy_s2c(mapa_u32(d2, d), smem_u32(st2), bytes_each, rbar);
-            }
-        }
+        if (dbgt) for (int i = 0; i < 4; ++i) a.dbg[2 + i] = seg[i];
     }
     // ---- teardown: nobody may exit while peers still copy into its shared memory
     tcgen05_fence_before();
     cluster.sync();
-    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(F_TMEM));
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(F_TMEM));
 }
 
 // ======================================================================================================= backward
@@ -360,25 +383,32 @@ FDB_DEVICE void load_col_chunk_to_tmem(const float* __restrict__ W, int ldw, int
     tmem_st_x32(taddr, v);
 }
 
-__global__ void __cluster_dims__(lstm::CL, 1, 1) __launch_bounds__(lstm::kThreads, 1)
+// Warp roles (288 threads): warps 0-3 = layer-2 group (time p), warps 4-7 = layer-1 group (time p+1), warp 8 = MMA issuer.
+// Per phase each group: prefetch its history rows → wait for the inbox → Σ partial dh → LSTM cell backward → dG (bf16) to the
+// smem operand + global history → signal the issuer (mbarrier) → wait for its accumulator tiles → tcgen05.ld → staging →
+// DSMEM bulk reduce-scatter (one lane per copy).  The issuer runs the layer-2 chains (4 independent accumulators, 32 MMAs)
+// and the layer-1 chains (2 accumulators, 16 MMAs) as soon as the respective dG operand is ready, so one layer's
+// epilogue / exchange overlaps the other layer's tensor work.
+__global__ void __cluster_dims__(lstm::CL, 1, 1) __launch_bounds__(lstm::kFwdThreads, 1)
 lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
     using namespace lstm;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int pair = blockIdx.x / CL;
-    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
     const int T = a.T;
 
-    // ---- shared memory: inbox [2 bufs][8 src][3 kinds][NB][32] fp32, out staging [3 kinds][8 dst][NB][32] fp32 (double-buffered),
+    // ---- shared memory: inbox [2 bufs][8 src][3 kinds][NB][32] fp32, out staging [2 bufs][3 kinds][8 dst][NB][32] fp32,
     //      dG operands [2 layers][NB × 128] bf16
     constexpr int BLK = NB * U;   // 512 floats = 2 KB
     float* inbox = reinterpret_cast<float*>(smem_raw);                  // 2*8*3*BLK
     float* outst = inbox + 2 * CL * 3 * BLK;                            // 2*3*8*BLK
-    __nv_bfloat16* dGs = reinterpret_cast<__nv_bfloat16*>(outst + 2 * 3 * CL * BLK);   // [2][NB*128]
-    uint64_t* ibar = reinterpret_cast<uint64_t*>(dGs + 2 * NB * 128);  // [2]
-    uint64_t* mma_bar = ibar + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 1);
+    __nv_bfloat16* dGs = reinterpret_cast<__nv_bfloat16*>(outst + 2 * 3 * CL * BLK);   // [2][NB*128]: [0] layer 1, [1] layer 2
+    uint64_t* ibar = reinterpret_cast<uint64_t*>(dGs + 2 * NB * 128);  // [2] inbox arrival (tx bytes)
+    uint64_t* gbar = ibar + 2;                                          // [2] dG operand ready: [0] layer 2, [1] layer 1
+    uint64_t* mma_bar = gbar + 2;                                       // [2] accumulators ready: [0] layer 2, [1] layer 1
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(mma_bar + 2);
 
     const float* prow = a.params + a.row_off[pair];
     const float* w_hh1 = prow + a.off_whh1;
@@ -386,10 +416,10 @@ lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
     const float* w_hh2 = prow + a.off_whh2;
 
     if (tid == 0) {
-        mbar_init(ibar + 0, 1); mbar_init(ibar + 1, 1); mbar_init(mma_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(ibar + i, 1); mbar_init(gbar + i, 1); mbar_init(mma_bar + i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (w == 0) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(B_TMEM));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -397,159 +427,163 @@ lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_ptr_smem;
+    const int grp = warp >> 2;                 // 0: layer 2, 1: layer 1, 2: issuer
+    const int w = warp & 3, gt = tid & 127;
     const uint32_t lane_addr = tmem + ((uint32_t)(w * 32) << 16);
 
-    // ---- transposed weight slices → TMEM: tile h, lane = hidden column k = 128 h + tid; K = own 128 gate rows
+    // ---- transposed weight slices → TMEM: tile h, lane = hidden column k = 128 h + gt; K = own 128 gate rows.
+    //      group 0 loads W_hh2ᵀ and half of W_ih2ᵀ, group 1 the other half and W_hh1ᵀ
+    if (grp < 2) {
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-        const int k = 128 * h + tid;
+        for (int h = 0; h < 2; ++h) {
+            const int k = 128 * h + gt;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            load_col_chunk_to_tmem(w_hh2, H, k, crank, 64 * c, lane_addr + BT_HH2 + 64 * h + 32 * c);
-            load_col_chunk_to_tmem(w_ih2, H, k, crank, 64 * c, lane_addr + BT_IH2 + 64 * h + 32 * c);
-            load_col_chunk_to_tmem(w_hh1, H, k, crank, 64 * c, lane_addr + BT_HH1 + 64 * h + 32 * c);
+            for (int c = 0; c < 2; ++c) {
+                if (grp == 0) {
+                    load_col_chunk_to_tmem(w_hh2, H, k, crank, 64 * c, lane_addr + BT_HH2 + 64 * h + 32 * c);
+                    if (h == 0) load_col_chunk_to_tmem(w_ih2, H, k, crank, 64 * c, lane_addr + BT_IH2 + 64 * h + 32 * c);
+                } else {
+                    load_col_chunk_to_tmem(w_hh1, H, k, crank, 64 * c, lane_addr + BT_HH1 + 64 * h + 32 * c);
+                    if (h == 1) load_col_chunk_to_tmem(w_ih2, H, k, crank, 64 * c, lane_addr + BT_IH2 + 64 * h + 32 * c);
+                }
+            }
         }
+        tmem_st_wait();
     }
-    tmem_st_wait();
     tcgen05_fence_before();
     cluster.sync();
     tcgen05_fence_after();
 
     const int unit = crank * U + l;
     const int NP = (int)gridDim.x / CL;
-    const float* gates_l[2] = {a.gates + (size_t)(0 * NP + pair) * T * NB * 4 * H, a.gates + (size_t)(1 * NP + pair) * T * NB * 4 * H};
-    const float* cst_l[2] = {a.cst + (size_t)(0 * NP + pair) * T * NB * H, a.cst + (size_t)(1 * NP + pair) * T * NB * H};
-    __nv_bfloat16* dG_l[2] = {reinterpret_cast<__nv_bfloat16*>(a.dgates) + (size_t)(0 * NP + pair) * T * NB * 4 * H,
-                              reinterpret_cast<__nv_bfloat16*>(a.dgates) + (size_t)(1 * NP + pair) * T * NB * 4 * H};
-    float dc1[4] = {0.f, 0.f, 0.f, 0.f}, dc2[4] = {0.f, 0.f, 0.f, 0.f};
 
-    // phase p = T-1 … -1: layer 2 at time p, layer 1 at time p+1
-    for (int p = T - 1, it = 0; p >= -1; --p, ++it) {
-        const bool doL2 = p >= 0, doL1 = p + 1 <= T - 1;
-        const bool have_in = it > 0;                 // partial blocks of the previous phase
-        const int ibuf = (it + 1) & 1;               // inbox buffer written during phase it-1
-        if (have_in) mbar_wait_long(ibar + ibuf, ((it - 1) >> 1) & 1);
-        const float* in = inbox + (size_t)ibuf * CL * 3 * BLK;
-        // what the previous phase produced: kind 0 = rec2 (for layer 2 at time p), kind 1 = dh1in (layer 1 at time p+1),
-        // kind 2 = rec1 (layer 1 at time p+1)
-        const bool prev_had_L2 = have_in;                       // phase it-1 ran layer 2 at time p+1 (always, for it ≥ 1)
-        const bool prev_had_L1 = have_in && (p + 2 <= T - 1);   // … and layer 1 at time p+2
+    if (grp == 2) {
+        // =================================================== MMA issuer
+        if (l == 0) {
+            for (int p = T - 1, it = 0; p >= 0; --p, ++it) {
+                const bool doL1 = p + 1 <= T - 1;
+                mbar_expect_tx(ibar + (it & 1), (uint32_t)(CL * (doL1 ? 3 : 2) * BLK * 4));   // this phase's inbound partial blocks
+                const uint32_t g2 = smem_u32(dGs + NB * 128), g1 = smem_u32(dGs);
+                mbar_wait_long(gbar + 0, it & 1);          // dG of layer 2 (time p) is in shared memory
+                tcgen05_fence_after();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int b = w + 4 * i;
-            if (doL2) {
-                float dh = 0.f;
-                if (a.dh2_all) dh = a.dh2_all[(((size_t)pair * T + p) * NB + b) * H + unit];
-                else if (p == T - 1) dh = a.dh2_last[((size_t)pair * NB + b) * H + unit];
-                if (prev_had_L2) {
+                for (int s = 0; s < 8; ++s) {
 #pragma unroll
-                    for (int s = 0; s < CL; ++s) dh += in[(s * 3 + 0) * BLK + b * U + l];
+                    for (int h = 0; h < 2; ++h) {
+                        umma_ts_f16(tmem + BD_REC2 + 16 * h, tmem + BT_HH2 + 64 * h + 8 * s, make_desc_nosw(g2 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                        umma_ts_f16(tmem + BD_IN1 + 16 * h, tmem + BT_IH2 + 64 * h + 8 * s, make_desc_nosw(g2 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                    }
                 }
-                const size_t row = (size_t)p * NB + b;
-                const float* g = gates_l[1] + row * 4 * H + unit;
-                const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
-                const float c = cst_l[1][row * H + unit];
-                const float cprev = (p > 0) ? cst_l[1][((size_t)(p - 1) * NB + b) * H + unit] : 0.f;
-                const float tc = tanh_f(c);
-                const float dcv = dc2[i] + dh * go * (1.f - tc * tc);
-                const float dzi = dcv * gg * gi * (1.f - gi), dzf = dcv * cprev * gf * (1.f - gf);
-                const float dzg = dcv * gi * (1.f - gg * gg), dzo = dh * tc * go * (1.f - go);
-                dc2[i] = dcv * gf;
-                __nv_bfloat16* o = dG_l[1] + row * 4 * H + unit;
-                const __nv_bfloat16 bi = __float2bfloat16(dzi), bf = __float2bfloat16(dzf), bg = __float2bfloat16(dzg), bo = __float2bfloat16(dzo);
-                o[0] = bi; o[H] = bf; o[2 * H] = bg; o[3 * H] = bo;
-                __nv_bfloat16* s2 = dGs + 1 * NB * 128;
-                s2[op_off(b, 0 * 32 + l)] = bi; s2[op_off(b, 1 * 32 + l)] = bf; s2[op_off(b, 2 * 32 + l)] = bg; s2[op_off(b, 3 * 32 + l)] = bo;
-            }
-            if (doL1) {
-                const int t1 = p + 1;
-                float dh = 0.f;
-                if (prev_had_L2) {
-#pragma unroll
-                    for (int s = 0; s < CL; ++s) dh += in[(s * 3 + 1) * BLK + b * U + l];
-                }
-                if (prev_had_L1) {
-#pragma unroll
-                    for (int s = 0; s < CL; ++s) dh += in[(s * 3 + 2) * BLK + b * U + l];
-                }
-                const size_t row = (size_t)t1 * NB + b;
-                const float* g = gates_l[0] + row * 4 * H + unit;
-                const float gi = g[0], gf = g[H], gg = g[2 * H], go = g[3 * H];
-                const float c = cst_l[0][row * H + unit];
-                const float cprev = (t1 > 0) ? cst_l[0][((size_t)(t1 - 1) * NB + b) * H + unit] : 0.f;
-                const float tc = tanh_f(c);
-                const float dcv = dc1[i] + dh * go * (1.f - tc * tc);
-                const float dzi = dcv * gg * gi * (1.f - gi), dzf = dcv * cprev * gf * (1.f - gf);
-                const float dzg = dcv * gi * (1.f - gg * gg), dzo = dh * tc * go * (1.f - go);
-                dc1[i] = dcv * gf;
-                __nv_bfloat16* o = dG_l[0] + row * 4 * H + unit;
-                const __nv_bfloat16 bi = __float2bfloat16(dzi), bf = __float2bfloat16(dzf), bg = __float2bfloat16(dzg), bo = __float2bfloat16(dzo);
-                o[0] = bi; o[H] = bf; o[2 * H] = bg; o[3 * H] = bo;
-                __nv_bfloat16* s1 = dGs;
-                s1[op_off(b, 0 * 32 + l)] = bi; s1[op_off(b, 1 * 32 + l)] = bf; s1[op_off(b, 2 * 32 + l)] = bg; s1[op_off(b, 3 * 32 + l)] = bo;
-            }
-        }
-        if (p == -1) break;            // time 0 of layer 1 has no consumer for its dh_{-1}
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tcgen05_fence_after();
-            const uint32_t g2 = smem_u32(dGs + NB * 128), g1 = smem_u32(dGs);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                // doL2 is always true here (p ≥ 0)
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    umma_ts_f16(tmem + BD_REC2 + 16 * h, tmem + BT_HH2 + 64 * h + 8 * s, make_desc_nosw(g2 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    umma_ts_f16(tmem + BD_IN1 + 16 * h, tmem + BT_IH2 + 64 * h + 8 * s, make_desc_nosw(g2 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                tcgen05_commit(mma_bar + 0);
                 if (doL1) {
+                    mbar_wait_long(gbar + 1, (it - 1) & 1);   // dG of layer 1 (time p+1)
+                    tcgen05_fence_after();
 #pragma unroll
-                    for (int s = 0; s < 8; ++s)
-                        umma_ts_f16(tmem + BD_REC1 + 16 * h, tmem + BT_HH1 + 64 * h + 8 * s, make_desc_nosw(g1 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                    for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            umma_ts_f16(tmem + BD_REC1 + 16 * h, tmem + BT_HH1 + 64 * h + 8 * s, make_desc_nosw(g1 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                    }
+                    tcgen05_commit(mma_bar + 1);
                 }
             }
-            tcgen05_commit(mma_bar);
         }
-        mbar_wait_long(mma_bar, it & 1);
-        tcgen05_fence_after();
-        // ---- partial dhᵀ tiles → staging blocks [b][unit-in-owner] (this warp's 32 lanes = 32 hidden units of owner 4h + w)
-        float* ob = outst + (size_t)(it & 1) * 3 * CL * BLK;
-        const int nk = doL1 ? 3 : 2;
-        for (int kind = 0; kind < nk; ++kind) {
-            const uint32_t col = (kind == 0) ? BD_REC2 : (kind == 1 ? BD_IN1 : BD_REC1);
+    } else {
+        // =================================================== layer groups
+        const int layer = 1 - grp;                 // group 0 ↔ layer index 1 (second layer), group 1 ↔ layer index 0
+        const float* gates_l = a.gates + (size_t)(layer * NP + pair) * T * NB * 4 * H;
+        const float* cst_l = a.cst + (size_t)(layer * NP + pair) * T * NB * H;
+        __nv_bfloat16* dG_l = reinterpret_cast<__nv_bfloat16*>(a.dgates) + (size_t)(layer * NP + pair) * T * NB * 4 * H;
+        __nv_bfloat16* dg_s = dGs + layer * NB * 128;
+        float dcar[4] = {0.f, 0.f, 0.f, 0.f};
+        // group 0 (layer 2) runs in phases it = 0 … T-1 at time t = T-1-it; group 1 (layer 1) in phases it = 1 … T at time t = T-it
+        const int it_lo = grp, it_hi = T - 1 + grp;
+        for (int it = it_lo; it <= it_hi; ++it) {
+            const int t = T - 1 - it + grp;
+            const int p = T - 1 - it;                                  // the phase's layer-2 time (−1 in the last phase)
+            // ---- prefetch this step's history rows (independent of the inbox) before waiting
+            float hg[4][4], hc[4], hcp[4];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float z[16];
-                tmem_ld_x16(lane_addr + col + 16 * h, z);
-                float* dst = ob + (size_t)(kind * CL + (4 * h + w)) * BLK;
-#pragma unroll
-                for (int b = 0; b < NB; ++b) dst[b * U + l] = z[b];
+            for (int i = 0; i < 4; ++i) {
+                const int b = w + 4 * i;
+                const size_t row = (size_t)t * NB + b;
+                const float* g = gates_l + row * 4 * H + unit;
+                hg[i][0] = g[0]; hg[i][1] = g[H]; hg[i][2] = g[2 * H]; hg[i][3] = g[3 * H];
+                hc[i] = cst_l[row * H + unit];
+                hcp[i] = (t > 0) ? cst_l[((size_t)(t - 1) * NB + b) * H + unit] : 0.f;
             }
-        }
-        fence_proxy_async_smem();
-        tcgen05_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            // ---- reduce-scatter: block (kind, owner d) → owner d's inbox slot [src = me][kind]
-            const int obuf = it & 1;
-            mbar_expect_tx(ibar + obuf, (uint32_t)(CL * nk * BLK * 4));
-            const uint32_t bar = smem_u32(ibar + obuf);
-#pragma unroll 1
-            for (int d = 0; d < CL; ++d) {
-                const uint32_t rbar = mapa_u32(bar, d);
-                for (int kind = 0; kind < nk; ++kind) {
+            const bool have_in = it > 0;
+            const int ibuf = (it + 1) & 1;                             // inbox buffer written during phase it-1
+            if (have_in) mbar_wait_long(ibar + ibuf, ((it - 1) >> 1) & 1);
+            const float* in = inbox + (size_t)ibuf * CL * 3 * BLK;
+            const bool prev_had_L1 = have_in && (p + 2 <= T - 1);      // phase it-1 also ran layer 1 (at time p+2)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = w + 4 * i;
+                float dh = 0.f;
+                if (grp == 0) {
+                    if (a.dh2_all) dh = a.dh2_all[(((size_t)pair * T + t) * NB + b) * H + unit];
+                    else if (t == T - 1) dh = a.dh2_last[((size_t)pair * NB + b) * H + unit];
+                    if (have_in) {
+#pragma unroll
+                        for (int sidx = 0; sidx < CL; ++sidx) dh += in[(sidx * 3 + 0) * BLK + b * U + l];
+                    }
+                } else {
+#pragma unroll
+                    for (int sidx = 0; sidx < CL; ++sidx) dh += in[(sidx * 3 + 1) * BLK + b * U + l];
+                    if (prev_had_L1) {
+#pragma unroll
+                        for (int sidx = 0; sidx < CL; ++sidx) dh += in[(sidx * 3 + 2) * BLK + b * U + l];
+                    }
+                }
+                const float gi = hg[i][0], gf = hg[i][1], gg = hg[i][2], go = hg[i][3];
+                const float tc = tanh_fast(hc[i]);
+                const float dcv = dcar[i] + dh * go * (1.f - tc * tc);
+                const float dzi = dcv * gg * gi * (1.f - gi), dzf = dcv * hcp[i] * gf * (1.f - gf);
+                const float dzg = dcv * gi * (1.f - gg * gg), dzo = dh * tc * go * (1.f - go);
+                dcar[i] = dcv * gf;
+                __nv_bfloat16* o = dG_l + ((size_t)t * NB + b) * 4 * H + unit;
+                const __nv_bfloat16 bi = __float2bfloat16(dzi), bf = __float2bfloat16(dzf), bg = __float2bfloat16(dzg), bo = __float2bfloat16(dzo);
+                o[0] = bi; o[H] = bf; o[2 * H] = bg; o[3 * H] = bo;
+                dg_s[op_off(b, 0 * 32 + l)] = bi; dg_s[op_off(b, 1 * 32 + l)] = bf; dg_s[op_off(b, 2 * 32 + l)] = bg; dg_s[op_off(b, 3 * 32 + l)] = bo;
+            }
+            if (p < 0) break;                                          // layer 1 at time 0: its dh_{-1} has no consumer
+            fence_proxy_async_smem();
+            named_bar_sync(1 + grp, 128);
+            if (gt == 0) mbar_arrive(gbar + grp);                      // → issuer: this layer's dG operand is ready
+            // ---- my accumulator tiles → staging blocks [b][unit-in-owner] (this warp's lanes = 32 hidden units of owner 4h + w)
+            mbar_wait_long(mma_bar + grp, (it - it_lo) & 1);
+            tcgen05_fence_after();
+            float* ob = outst + (size_t)(it & 1) * 3 * CL * BLK;
+            const int k_lo = grp == 0 ? 0 : 2, k_hi = grp == 0 ? 1 : 2;
+            for (int kind = k_lo; kind <= k_hi; ++kind) {
+                const uint32_t col = (kind == 0) ? BD_REC2 : (kind == 1 ? BD_IN1 : BD_REC1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float z[16];
+                    tmem_ld_x16(lane_addr + col + 16 * h, z);
+                    float* dst = ob + (size_t)(kind * CL + (4 * h + w)) * BLK;
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) dst[b * U + l] = z[b];
+                }
+            }
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            named_bar_sync(1 + grp, 128);
+            // ---- reduce-scatter: block (kind, owner d) → owner d's inbox slot [src = me][kind]; one lane per copy
+            {
+                const int obuf = it & 1, ncopy = (k_hi - k_lo + 1) * CL;
+                if (gt < ncopy) {
+                    const int kind = k_lo + gt / CL, d = gt % CL;
                     const uint32_t dst = smem_u32(inbox + ((size_t)obuf * CL + crank) * 3 * BLK + kind * BLK);
-                    bulk_copy_s2c(mapa_u32(dst, d), smem_u32(ob + (size_t)(kind * CL + d) * BLK), BLK * 4, rbar);
+                    bulk_copy_s2c(mapa_u32(dst, d), smem_u32(ob + (size_t)(kind * CL + d) * BLK), BLK * 4, mapa_u32(smem_u32(ibar + obuf), d));
                 }
             }
         }
     }
     tcgen05_fence_before();
     cluster.sync();
-    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(B_TMEM));
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(B_TMEM));
 }
 
 // ======================================================================================================= classifier head
@@ -639,22 +673,95 @@ int lstm_head_launch(const LstmHeadArgs& a, int nchunks, cudaStream_t stream) {
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
+// ======================================================================================================= small gradients
+// Bias, W_ih1 and embedding gradients of every chunk in one pass over the bf16 gate-gradient histories.  Because the layer-1
+// input is x_r = emb[tok_r], all three follow from the token-segmented column sums S[v][col] = Σ_{r: tok_r = v} dG1[r][col]:
+//   db1[col] = Σ_v S[v][col],   dW_ih1[col][e] = Σ_v S[v][col]·emb[v][e],   d emb[v][e] = Σ_col S[v][col]·W_ih1[col][e]
+// (emb / W_ih1 rounded to bf16 exactly as the forward kernel fed them to the tensor core); db2 is a plain column sum of dG2.
+// grid = (chunks, 8 column slices of 128); one thread per gate column; S lives in shared memory (no atomics: a thread owns
+// its column).  Replaces ~12 eager kernels that converted both histories to fp32 (≈1.3 GB of traffic per local step).
+__global__ void __launch_bounds__(128) lstm_small_grads_kernel(const __grid_constant__ LstmSmallArgs a) {
+    constexpr int H4 = 4 * lstm::H, NB = lstm::NB, VP = 96, EP = 16;
+    extern __shared__ float sg[];
+    float* S = sg;                       // [VP][129]
+    float* embq = S + VP * 129;          // [VP][EP]
+    float* wq = embq + VP * EP;          // [128][EP]
+    int* tokr = reinterpret_cast<int*>(wq + 128 * EP);   // [T*NB] token of history row r = t*16 + b
+    const int ch = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, col = slice * 128 + tid;
+    const int T = a.T, E = a.E, V = a.V, TB = T * NB, NP = (int)gridDim.x;
+    const float* prow = a.params + a.row_off[ch];
+    for (int i = tid; i < VP * 129; i += 128) S[i] = 0.f;
+    for (int i = tid; i < VP * EP; i += 128) {
+        const int v = i / EP, e = i % EP;
+        embq[i] = (v < V && e < E) ? __bfloat162float(__float2bfloat16(__ldg(prow + a.off_emb + (size_t)v * E + e))) : 0.f;
+    }
+    for (int i = tid; i < 128 * EP; i += 128) {
+        const int c = i / EP, e = i % EP;
+        wq[i] = (e < E) ? __bfloat162float(__float2bfloat16(__ldg(prow + a.off_wih1 + (size_t)(slice * 128 + c) * E + e))) : 0.f;
+    }
+    const int* tk = a.tokens + (size_t)ch * NB * T;
+    for (int r = tid; r < TB; r += 128) tokr[r] = tk[(r % NB) * T + r / NB];
+    __syncthreads();
+    const __nv_bfloat16* g1 = reinterpret_cast<const __nv_bfloat16*>(a.dgates) + ((size_t)(0 * NP + ch) * TB) * H4 + col;
+    const __nv_bfloat16* g2 = reinterpret_cast<const __nv_bfloat16*>(a.dgates) + ((size_t)(1 * NP + ch) * TB) * H4 + col;
+    float b2 = 0.f;
+    int r = 0;
+    for (; r + 4 <= TB; r += 4) {          // 8 independent loads in flight per thread
+        float x1[4], x2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { x1[q] = __bfloat162float(g1[(size_t)(r + q) * H4]); x2[q] = __bfloat162float(g2[(size_t)(r + q) * H4]); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { S[tokr[r + q] * 129 + tid] += x1[q]; b2 += x2[q]; }
+    }
+    for (; r < TB; ++r) { S[tokr[r] * 129 + tid] += __bfloat162float(g1[(size_t)r * H4]); b2 += __bfloat162float(g2[(size_t)r * H4]); }
+    // per-column results (this thread's column only: no sync needed yet)
+    float b1 = 0.f, dw[EP];
+#pragma unroll
+    for (int e = 0; e < EP; ++e) dw[e] = 0.f;
+    for (int v = 0; v < V; ++v) {
+        const float sv = S[v * 129 + tid];
+        b1 += sv;
+#pragma unroll
+        for (int e = 0; e < EP; ++e) dw[e] = fmaf(sv, embq[v * EP + e], dw[e]);
+    }
+    a.db1[(size_t)ch * H4 + col] = b1;
+    a.db2[(size_t)ch * H4 + col] = b2;
+    for (int e = 0; e < E; ++e) a.dwih1[((size_t)ch * H4 + col) * E + e] = dw[e];
+    __syncthreads();
+    // embedding partial of this column slice: demb_part[ch][slice][v][e] = Σ_c S[v][c]·W_ih1[c][e]
+    for (int i = tid; i < V * E; i += 128) {
+        const int v = i / E, e = i % E;
+        float acc = 0.f;
+        for (int c = 0; c < 128; ++c) acc = fmaf(S[v * 129 + c], wq[c * EP + e], acc);
+        a.demb_part[(((size_t)ch * 8 + slice) * V + v) * E + e] = acc;
+    }
+}
+
+int lstm_small_grads_launch(const LstmSmallArgs& a, int nchunks, cudaStream_t stream) {
+    if (a.V > 96 || a.E > 16) return -5;
+    const size_t smem = (size_t)(96 * 129 + 96 * 16 + 128 * 16) * 4 + (size_t)a.T * lstm::NB * 4;
+    cudaError_t e = cudaFuncSetAttribute(lstm_small_grads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -3;
+    lstm_small_grads_kernel<<<dim3(nchunks, 8), 128, smem, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
 // ======================================================================================================= launchers
 static size_t fwd_smem_bytes() {
     using namespace lstm;
-    size_t b = (size_t)(2 * NB * H + 2 * NB * H + 2 * NB * KX + 2 * 2 * NB * U) * 2 + (size_t)2 * 4 * NB * U * 4 + 64;
+    size_t b = (size_t)(2 * NB * H + 2 * NB * H + 2 * NB * KX + 2 * 2 * NB * U) * 2 + (size_t)2 * 4 * NB * U * 4 + 128;
     return b < 120 * 1024 ? 120 * 1024 : b;   // > half an SM's shared memory: exactly one CTA (one 512-column TMEM owner) per SM
 }
 static size_t bwd_smem_bytes() {
     using namespace lstm;
-    return (size_t)(2 * CL * 3 + 2 * 3 * CL) * NB * U * 4 + (size_t)2 * NB * 128 * 2 + 64;
+    return (size_t)(2 * CL * 3 + 2 * 3 * CL) * NB * U * 4 + (size_t)2 * NB * 128 * 2 + 128;
 }
 
 int lstm2_fwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream) {
     const size_t smem = fwd_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(lstm2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -3;
-    lstm2_fwd_kernel<<<npairs * lstm::CL, lstm::kThreads, smem, stream>>>(a);
+    lstm2_fwd_kernel<<<npairs * lstm::CL, lstm::kFwdThreads, smem, stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -662,7 +769,7 @@ int lstm2_bwd_launch(const LstmArgs& a, int npairs, cudaStream_t stream) {
     const size_t smem = bwd_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(lstm2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -3;
-    lstm2_bwd_kernel<<<npairs * lstm::CL, lstm::kThreads, smem, stream>>>(a);
+    lstm2_bwd_kernel<<<npairs * lstm::CL, lstm::kFwdThreads, smem, stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -111,9 +111,10 @@ def train_pairs(sim, pairs: List, seed: int, rnd: int, E: int, use_adam: bool, l
     if ws is None or sim.__dict__.get("_lstm_ws_key") != key:
         ws = sim._lstm_ws = L.Lstm2Workspace(nch, T, dev, train=True)
         sim._lstm_ws_key = key
-    TB = T * L.NB
+    from ..ops import _ext
+    ext = _ext.load(required=True)
     o_emb, n_emb, _ = lay["emb"]
-    o_wih1, n_wih1, _ = lay["w_ih1"]
+    o_wih1 = lay["w_ih1"][0]
 
     def put(name: str, t: torch.Tensor) -> None:                         # per-pair gradient block → its slot in the gradient rows
         off, n, _ = lay[name]
@@ -127,19 +128,8 @@ def train_pairs(sim, pairs: List, seed: int, rnd: int, E: int, use_adam: bool, l
                                         labels_all[e].reshape(nch, L.NB).contiguous(), scale_all[e], V)
         L.lstm2_pairs_backward(arena, chunk_off, lay["offs9"], tok, Eemb, ws, dh)
         big = L.lstm2_weight_grads_per_chunk(ws)
-        # small tensors: biases, W_ih1, embedding (reductions over the [T·16] history rows of every chunk)
-        dG1f = ws.dgates[0].reshape(nch, TB, 4 * L.H).float()
-        dG2f = ws.dgates[1].reshape(nch, TB, 4 * L.H).float()
-        b1, b2 = dG1f.sum(1), dG2f.sum(1)
-        tokl = tok.long().permute(0, 2, 1).reshape(nch, TB)
-        # current local embedding / W_ih1 of every chunk's pair (column slices of the arena rows: a few KB per chunk)
-        embw = params2[:, o_emb:o_emb + n_emb].index_select(0, chunk_rows).reshape(nch, -1, Eemb)
-        gi = tokl.unsqueeze(-1).expand(-1, -1, Eemb)
-        Xe = embw.gather(1, gi).to(torch.bfloat16).float()               # the kernel fed bf16 embeddings to the tensor core
-        dWih1 = torch.bmm(dG1f.transpose(1, 2), Xe)                      # [nch, 1024, E]
-        wih1 = params2[:, o_wih1:o_wih1 + n_wih1].index_select(0, chunk_rows).reshape(nch, 4 * L.H, Eemb).to(torch.bfloat16).float()
-        dX = torch.bmm(dG1f, wih1)                                       # [nch, T·16, E]
-        demb = torch.zeros(nch, embw.shape[1], Eemb, dtype=torch.float32, device=dev).scatter_add_(1, gi, dX)
+        # small tensors (biases, W_ih1, embedding): one fused pass over the bf16 gate-gradient histories
+        b1, b2, dWih1, demb = ext.lstm_small_grads(arena, chunk_off, o_emb, o_wih1, tok, ws.dgates, Eemb, n_emb // Eemb)
         demb[:, 0] = 0                                                   # nn.Embedding(padding_idx=0)
         put("w_hh1", big["w_hh1"]); put("w_ih2", big["w_ih2"]); put("w_hh2", big["w_hh2"])
         put("b_ih1", b1); put("b_hh1", b1); put("b_ih2", b2); put("b_hh2", b2)

@@ -201,7 +201,10 @@ class GKTClientTrainer:
 
 class GKTServerTrainer:
     """Server side: trains the large model on the clients' feature maps with KD + α·CE, returns per-batch logits
-    (``GKTServerTrainer.py:14-325``); ReduceLROnPlateau on the test accuracy; best/last checkpoints in memory."""
+    (``GKTServerTrainer.py:14-325``); ReduceLROnPlateau on the test accuracy; best/last checkpoints are kept in memory and,
+    like the reference (``GKTServerTrainer.py:213-231``), written to ``<checkpoint_dir>/{last,best}.pth`` (model + optimizer
+    + epoch + accuracies) and ``test_best_metrics.json`` — ``args.checkpoint_dir`` defaults to ``./checkpoint``; ``None``/``""``
+    disables the files.  ``resume(path)`` restores model, optimizer and best accuracy."""
 
     def __init__(self, client_num, device, server_model, args):
         self.client_num, self.device, self.args = client_num, device, args
@@ -239,13 +242,44 @@ class GKTServerTrainer:
         ev = self.eval_large_model_on_the_server()
         self.scheduler.step(ev["test_accTop1"])
         self.checkpoints["last"] = copy.deepcopy(self.model_global.state_dict())
-        if ev["test_accTop1"] >= self.best_acc:
+        is_best = ev["test_accTop1"] >= self.best_acc
+        if is_best:
             self.best_acc = ev["test_accTop1"]
             self.checkpoints["best"] = self.checkpoints["last"]
+        self._save_files(round_idx, ev, is_best)
         sink = get_sink()
         sink.log({"Train/Loss": m["train_loss"], "Train/AccTop1": m["train_accTop1"], "Test/AccTop1": ev["test_accTop1"],
                   "Test/Loss": ev["test_loss"], "round": round_idx})
         return m, ev
+
+    def _save_files(self, round_idx: int, ev: Dict, is_best: bool) -> None:
+        import json
+        import os
+        import shutil
+        cdir = getattr(self.args, "checkpoint_dir", "./checkpoint")
+        if not cdir:
+            return
+        os.makedirs(cdir, exist_ok=True)
+        last = os.path.join(cdir, "last.pth")
+        tmp = last + ".tmp"
+        torch.save({"state_dict": {k: v.detach().cpu() for k, v in self.model_global.state_dict().items()},
+                    "optim_dict": self.optimizer.state_dict(), "epoch": round_idx + 1,
+                    "test_accTop1": float(ev["test_accTop1"]), "test_accTop5": float(ev.get("test_accTop5", 0.0))}, tmp)
+        os.replace(tmp, last)   # atomic: a crash never leaves a torn checkpoint
+        if is_best:
+            best = {k: (float(v) if isinstance(v, (int, float)) or hasattr(v, "item") else v) for k, v in ev.items()}
+            best["epoch"] = round_idx + 1
+            with open(os.path.join(cdir, "test_best_metrics.json"), "w") as fh:
+                json.dump(best, fh, indent=4)
+            shutil.copyfile(last, os.path.join(cdir, "best.pth"))
+
+    def resume(self, path: str) -> int:
+        """Restore model / optimizer / best accuracy from ``last.pth`` or ``best.pth``; returns the next round index."""
+        blob = torch.load(path, map_location=self.device, weights_only=True)
+        self.model_global.load_state_dict(blob["state_dict"])
+        self.optimizer.load_state_dict(blob["optim_dict"])
+        self.best_acc = max(self.best_acc, float(blob.get("test_accTop1", 0.0)))
+        return int(blob.get("epoch", 0))
 
     def get_server_epoch_strategy(self, round_idx):
         return int(getattr(self.args, "epochs_server", 1))

@@ -166,17 +166,29 @@ def test_splitnn_round_robin():
     assert len(res) == 6 and res[-1]["acc"] >= res[0]["acc"] and all(np.isfinite(r["loss"]) for r in res)
 
 
-def test_fedgkt_two_stage_training():
-    from feddrift_b200.fl.split import FedML_FedGKT_distributed
+def test_fedgkt_two_stage_training(tmp_path):
+    import json
+    import os
+    from feddrift_b200.fl.split import FedML_FedGKT_distributed, GKTServerTrainer
     from feddrift_b200.models.resnet import resnet8_56, ResNet, Bottleneck
     sink = set_sink(MetricsSink())
+    cdir = str(tmp_path / "checkpoint")
     a = SimpleNamespace(comm_round=2, epochs_client=1, epochs_server=1, lr=0.01, wd=1e-4, optimizer="SGD", temperature=3.0,
-                        alpha=1.0, whether_training_on_client=1, whether_distill_on_the_server=1)
+                        alpha=1.0, whether_training_on_client=1, whether_distill_on_the_server=1, checkpoint_dir=cdir)
     loaders = _img_loaders()
     server_model = ResNet(Bottleneck, [1, 1, 1], 4, stem="features")
     srv, hist = FedML_FedGKT_distributed([resnet8_56(4) for _ in loaders], server_model, loaders, "cpu", a)
     assert len(hist) == 2 and "best" in srv.checkpoints and len(sink.series("Test/AccTop1")) == 2
     assert set(srv.get_global_logits(0).keys()) == {0, 1, 2}
+    # file checkpoints like the reference (GKTServerTrainer.py:213-231): last.pth, best.pth, test_best_metrics.json
+    assert sorted(os.listdir(cdir)) == ["best.pth", "last.pth", "test_best_metrics.json"]
+    last = torch.load(os.path.join(cdir, "last.pth"), weights_only=True)
+    assert last["epoch"] == 2 and set(last) >= {"state_dict", "optim_dict", "test_accTop1", "test_accTop5"}
+    assert json.load(open(os.path.join(cdir, "test_best_metrics.json")))["epoch"] in (1, 2)
+    fresh = GKTServerTrainer(len(loaders), "cpu", ResNet(Bottleneck, [1, 1, 1], 4, stem="features"), a)
+    assert fresh.resume(os.path.join(cdir, "last.pth")) == 2
+    for k, v in srv.model_global.state_dict().items():
+        assert torch.equal(v, fresh.model_global.state_dict()[k])
 
 
 def test_vertical_fl_distributed_and_standalone():

@@ -556,6 +556,68 @@ void lstm_head(Tensor params, Tensor row_off, int64_t off_fcw, int64_t off_fcb, 
     CHECK_OK(fdb::lstm_head_launch(a, (int)n, cur_stream()), "lstm_head");
 }
 
+// ---------------------------------------------------------------------------------- implicit-GEMM convolution (conv_igemm.cu)
+static Tensor pack_conv_weights(const Tensor& w, int mode) {
+    CHECK_CUDA_F32(w);
+    TORCH_CHECK(w.dim() == 4 && w.is_contiguous(), "conv weights must be contiguous OIHW");
+    const int K = (int)w.size(0), C = (int)w.size(1), R = (int)w.size(2), S = (int)w.size(3);
+    auto out = torch::empty({mode == 0 ? K : C, R, S, mode == 0 ? C : K}, w.options().dtype(torch::kBFloat16));
+    CHECK_OK(fdb::conv_pack_weights_launch(w.data_ptr<float>(), out.data_ptr(), K, C, R, S, mode, cur_stream()), "conv_pack_weights");
+    return out;
+}
+// x: NHWC fp32 [N, H, W, C]; w: fp32 OIHW; -> y NHWC fp32 [N, P, Q, K] = act(conv(x, w) + bias)
+Tensor conv_igemm_fwd(Tensor x, Tensor w, c10::optional<Tensor> bias, int64_t stride, int64_t pad_h, int64_t pad_w, bool relu) {
+    CHECK_CUDA_F32(x);
+    TORCH_CHECK(x.dim() == 4 && x.is_contiguous(), "conv_igemm: x must be contiguous NHWC");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int N = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), C = (int)x.size(3);
+    const int K = (int)w.size(0), R = (int)w.size(2), S = (int)w.size(3);
+    TORCH_CHECK(w.size(1) == C, "conv_igemm: channel mismatch");
+    const int P = (H + 2 * (int)pad_h - R) / (int)stride + 1, Q = (W + 2 * (int)pad_w - S) / (int)stride + 1;
+    auto wq = pack_conv_weights(w, 0);
+    auto y = torch::empty({N, P, Q, K}, x.options());
+    Tensor bias_f;
+    fdb::ConvArgs a{};
+    a.x = x.data_ptr<float>(); a.wq = reinterpret_cast<const __nv_bfloat16*>(wq.data_ptr()); a.y = y.data_ptr<float>();
+    if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); a.bias = bias_f.data_ptr<float>(); }
+    a.N = N; a.H = H; a.W = W; a.C = C; a.Kout = K; a.R = R; a.S = S; a.P = P; a.Q = Q;
+    a.pad_h = (int)pad_h; a.pad_w = (int)pad_w; a.stride = (int)stride; a.mode = 0; a.relu = relu ? 1 : 0;
+    CHECK_OK(fdb::conv_igemm_launch(a, cur_stream()), "conv_igemm forward (tcgen05)");
+    return y;
+}
+// dy: NHWC fp32 [N, P, Q, K]; w: fp32 OIHW [K, C, R, S]; -> dx NHWC fp32 [N, H, W, C]
+Tensor conv_igemm_dgrad(Tensor dy, Tensor w, int64_t H, int64_t W, int64_t stride, int64_t pad_h, int64_t pad_w) {
+    CHECK_CUDA_F32(dy);
+    TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous(), "conv_igemm_dgrad: dy must be contiguous NHWC");
+    c10::cuda::CUDAGuard guard(dy.device());
+    const int N = (int)dy.size(0), P = (int)dy.size(1), Q = (int)dy.size(2), K = (int)dy.size(3);
+    const int C = (int)w.size(1), R = (int)w.size(2), S = (int)w.size(3);
+    TORCH_CHECK(w.size(0) == K, "conv_igemm_dgrad: channel mismatch");
+    auto wq = pack_conv_weights(w, 1);                   // [C][R][S][K]
+    auto dx = torch::empty({N, H, W, C}, dy.options());
+    fdb::ConvArgs a{};
+    a.x = dy.data_ptr<float>(); a.wq = reinterpret_cast<const __nv_bfloat16*>(wq.data_ptr()); a.y = dx.data_ptr<float>();
+    a.N = N; a.H = P; a.W = Q; a.C = K; a.Kout = C; a.R = R; a.S = S; a.P = (int)H; a.Q = (int)W;
+    a.pad_h = (int)pad_h; a.pad_w = (int)pad_w; a.stride = (int)stride; a.mode = 1; a.relu = 0;
+    CHECK_OK(fdb::conv_igemm_launch(a, cur_stream()), "conv_igemm dgrad (tcgen05)");
+    return dx;
+}
+// x: NHWC fp32 [N, H, W, C]; dy: NHWC fp32 [N, P, Q, K]; -> dW fp32 [K, R, S, C]
+Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t stride, int64_t pad_h, int64_t pad_w) {
+    CHECK_CUDA_F32(x); CHECK_CUDA_F32(dy);
+    TORCH_CHECK(x.is_contiguous() && dy.is_contiguous() && x.dim() == 4 && dy.dim() == 4, "conv_igemm_wgrad: contiguous NHWC tensors");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int N = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), C = (int)x.size(3);
+    const int P = (int)dy.size(1), Q = (int)dy.size(2), K = (int)dy.size(3);
+    auto dw = torch::zeros({K, R, S, C}, x.options());
+    fdb::ConvArgs a{};
+    a.x = x.data_ptr<float>(); a.dy = dy.data_ptr<float>(); a.dw = dw.data_ptr<float>();
+    a.N = N; a.H = H; a.W = W; a.C = C; a.Kout = K; a.R = (int)R; a.S = (int)S; a.P = P; a.Q = Q;
+    a.pad_h = (int)pad_h; a.pad_w = (int)pad_w; a.stride = (int)stride;
+    CHECK_OK(fdb::conv_wgrad_launch(a, cur_stream()), "conv_igemm wgrad (tcgen05)");
+    return dw;
+}
+
 // bias / W_ih1 / embedding gradients of every chunk from the gate-gradient histories (lstm_tc.cu::lstm_small_grads_kernel)
 std::vector<Tensor> lstm_small_grads(Tensor params, Tensor row_off, int64_t off_emb, int64_t off_wih1, Tensor tokens, Tensor dgates,
                                      int64_t E, int64_t V) {
@@ -619,4 +681,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("lstm2_backward", &lstm2_backward);
     m.def("lstm_head", &lstm_head);
     m.def("lstm_small_grads", &lstm_small_grads);
+    m.def("conv_igemm_fwd", &conv_igemm_fwd);
+    m.def("conv_igemm_dgrad", &conv_igemm_dgrad);
+    m.def("conv_igemm_wgrad", &conv_igemm_wgrad);
 }

@@ -1,5 +1,6 @@
 // Host-callable launchers of the feddrift_b200 sm_100a kernels (raw pointers; bindings.cpp wraps them).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -55,6 +56,19 @@ int gemm_batched_mn_launch(const void* A, const void* B, float* D, int M, int N,
                            int a_k0, int a_kstride, int b_k0, int b_kstride, cudaStream_t stream);
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,
                    cudaStream_t stream);
+// conv_igemm.cu : implicit-GEMM convolution on tcgen05 (forward / dgrad / wgrad), NHWC fp32 activations
+struct ConvArgs {
+    const float* x;        // NHWC input of the gather: [N, H, W, C]   (forward: activations; dgrad: dY; wgrad: activations)
+    const __nv_bfloat16* wq;   // packed bf16 weights [Kout][R][S][C] (forward / dgrad)
+    const float* bias;     // [Kout] or nullptr (forward)
+    float* y;              // [N, P, Q, Kout] output of forward / dgrad
+    const float* dy;       // wgrad: [N·P·Q, Kout]
+    float* dw;             // wgrad: zeroed [Kout][R][S][C] fp32
+    int N, H, W, C, Kout, R, S, P, Q, pad_h, pad_w, stride, mode, relu;
+};
+int conv_igemm_launch(const ConvArgs& a, cudaStream_t stream);
+int conv_wgrad_launch(const ConvArgs& a, cudaStream_t stream);
+int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream);
 // lstm_tc.cu : persistent cluster-resident 2-layer LSTM(256) forward / BPTT over many (client, model) pairs per launch
 struct LstmArgs {
     const float* params;          // parameter arena base

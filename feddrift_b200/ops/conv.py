@@ -1,18 +1,23 @@
-"""``TcConv2d`` — nn.Conv2d-compatible layer whose CUDA path is im2col (fused bf16 cast, ``csrc/conv_im2col.cu``) +
-the hand-written tcgen05 GEMM with fused bias(+ReLU) epilogue (``csrc/gemm_tc.cu``).
+"""``TcConv2d`` — nn.Conv2d-compatible layer whose CUDA path is the hand-written IMPLICIT-GEMM convolution on tcgen05
+(``csrc/conv_igemm.cu``): forward, data gradient and weight gradient, NHWC activations end to end.
 
-* forward : cols = im2col(x) [B·Ho·Wo, Cin·kh·kw] bf16;  y = act(cols · Wᵀ + b) written as NHWC and returned as an
-            NCHW *view* in channels_last memory format (no transpose kernel);
-* backward: dcols = dy · W → dx = col2im(dcols) (gather form, no atomics);  dW = dyᵀ · cols;  db = Σ dy.  Both GEMMs
-            use the kernel's MN-major operand descriptors, so no tensor is transposed in memory.
+* forward : the producer warps gather each output pixel's (tap, channel) slice straight from the NHWC input into the
+            tensor-core operand tile (no im2col matrix in memory), bias(+ReLU) fused in the epilogue; the result is
+            returned as an NCHW *view* with channels_last strides, so a chain of convolutions never transposes;
+* dgrad   : the same kernel gathers from dY with the transposed weight pack (strided convolutions skip non-integer taps);
+* wgrad   : a GEMM whose reduction runs over the output pixels, both operands MN-major straight from the NHWC tensors,
+            split over pixel ranges with coalesced ``red.global.add`` into the fp32 gradient.
 
-bf16 operands, fp32 accumulation in TMEM, fp32 master weights.  Ineligible shapes (groups/dilation ≠ 1, reduction
-length Cin·kh·kw not a multiple of 8 or < 64 — e.g. a 1-channel stem) and CPU tensors use ``F.conv2d``.  State-dict
-keys and the init law equal ``nn.Conv2d``'s.  Reference: cuDNN fp32 ``nn.Conv2d`` (``fedml_api/model/cv/cnn.py:110-117``).
+fp32 activations / master weights, bf16 tensor-core operands, fp32 accumulation in TMEM.  Shapes the kernels do not cover
+(groups / dilation ≠ 1, Cin not a multiple of 16 — e.g. the 1- or 3-channel stems —, Cout not a multiple of 32) and CPU
+tensors use ``F.conv2d``.  ``FDB_CONV_IM2COL=1`` selects the round-1 explicit-im2col + GEMM formulation (kept for A/B
+measurements).  State-dict keys and the init law equal ``nn.Conv2d``'s.  Reference: cuDNN fp32 ``nn.Conv2d``
+(``fedml_api/model/cv/cnn.py:110-117``).
 """
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -21,10 +26,55 @@ from torch import nn
 from . import _ext
 
 TC_CONV_CALLS = 0
+IGEMM_CALLS = {"fwd": 0, "dgrad": 0, "wgrad": 0}
 
 
 def _pair(v):
     return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous NHWC view of an NCHW-logical tensor (free when it already is channels_last)."""
+    return t.float().contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+
+
+def igemm_eligible(cin: int, cout: int, stride, dilation, groups: int) -> bool:
+    return groups == 1 and tuple(dilation) == (1, 1) and stride[0] == stride[1] and cin % 16 == 0 and cout % 32 == 0
+
+
+class _ConvIgemmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, relu: bool):
+        global TC_CONV_CALLS
+        TC_CONV_CALLS += 1
+        IGEMM_CALLS["fwd"] += 1
+        ext = _ext.load(required=True)
+        xh = _nhwc(x)
+        w = weight.detach().float().contiguous()
+        y = ext.conv_igemm_fwd(xh, w, bias.detach() if bias is not None else None, stride[0], padding[0], padding[1], bool(relu))
+        ctx.save_for_backward(xh, w, y if relu else None)
+        ctx.geom = (stride, padding, tuple(weight.shape))
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        return y.permute(0, 3, 1, 2)                                          # NCHW view, channels_last strides
+
+    @staticmethod
+    def backward(ctx, gy):
+        ext = _ext.load(required=True)
+        xh, w, y = ctx.saved_tensors
+        stride, padding, (Co, Ci, kh, kw) = ctx.geom
+        g = _nhwc(gy)
+        if ctx.relu:
+            g = g * (y > 0)
+        gx = gw = gbias = None
+        if ctx.needs_input_grad[0]:
+            IGEMM_CALLS["dgrad"] += 1
+            gx = ext.conv_igemm_dgrad(g, w, xh.shape[1], xh.shape[2], stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            IGEMM_CALLS["wgrad"] += 1
+            gw = ext.conv_igemm_wgrad(xh, g, kh, kw, stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)    # [K,R,S,C] → OIHW view
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gbias = g.sum((0, 1, 2))
+        return gx, gw, gbias, None, None, None
 
 
 class _TcConvFn(torch.autograd.Function):
@@ -90,7 +140,11 @@ class TcConv2d(nn.Module):
 
     def forward(self, x):
         relu = self.activation == "relu"
-        if self._eligible(x):
+        if (x.is_cuda and x.dim() == 4 and _ext.available() and os.environ.get("FDB_CONV_IM2COL") != "1"
+                and os.environ.get("FDB_NO_TC_CONV") != "1" and hasattr(_ext.load(), "conv_igemm_fwd")
+                and igemm_eligible(self.in_channels, self.out_channels, self.stride, self.dilation, self.groups)):
+            return _ConvIgemmFn.apply(x, self.weight, self.bias, self.stride, self.padding, relu)
+        if self._eligible(x) and os.environ.get("FDB_CONV_IM2COL") == "1":
             return _TcConvFn.apply(x, self.weight, self.bias, self.stride, self.padding, relu)
         y = F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
         return F.relu(y) if relu else y

@@ -1,0 +1,63 @@
+"""Implicit-GEMM convolution kernels (csrc/conv_igemm.cu) vs F.conv2d in fp32 (cuDNN): forward, dgrad, wgrad."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GEOMS = [
+    # N, Cin, H, W, Cout, k, stride, pad
+    (4, 32, 26, 26, 64, 3, 1, 0),      # CNN_DropOut conv2
+    (2, 64, 16, 16, 64, 3, 1, 1),      # ResNet-18 layer1
+    (2, 64, 16, 16, 128, 3, 2, 1),     # ResNet-18 layer2 downsampling 3x3
+    (2, 64, 16, 16, 128, 1, 2, 0),     # ResNet-18 1x1 shortcut
+    (3, 128, 8, 8, 256, 3, 1, 1),
+    (2, 256, 4, 4, 512, 3, 2, 1),
+    (5, 16, 9, 11, 32, 5, 1, 2),       # odd sizes, 5x5, small channels
+    (2, 96, 7, 7, 96, 3, 1, 1),        # Cout multiple of 32 only
+]
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_igemm_matches_conv2d(geom):
+    from feddrift_b200.ops import conv as C
+    N, Ci, H, W, Co, k, st, pad = geom
+    torch.manual_seed(0)
+    x = torch.randn(N, Ci, H, W, device="cuda", requires_grad=True)
+    w = (torch.randn(Co, Ci, k, k, device="cuda") / (Ci * k * k) ** 0.5).requires_grad_(True)
+    b = torch.randn(Co, device="cuda", requires_grad=True)
+    ref = F.conv2d(x, w, b, st, pad)
+    dy = torch.randn_like(ref)
+    gx, gw, gb = torch.autograd.grad(ref, (x, w, b), dy)
+    n0 = dict(C.IGEMM_CALLS)
+    got = C._ConvIgemmFn.apply(x, w, b, (st, st), (pad, pad), False)
+    hx, hw, hb = torch.autograd.grad(got, (x, w, b), dy)
+    torch.cuda.synchronize()
+    assert C.IGEMM_CALLS["fwd"] == n0["fwd"] + 1 and C.IGEMM_CALLS["dgrad"] == n0["dgrad"] + 1 and C.IGEMM_CALLS["wgrad"] == n0["wgrad"] + 1
+    assert got.shape == ref.shape
+
+    def rel(a, b_):
+        return (a - b_).abs().max().item() / (b_.abs().max().item() + 1e-6)
+
+    assert rel(got, ref) < 2e-2, f"forward rel err {rel(got, ref)}"
+    assert rel(hx, gx) < 2e-2, f"dgrad rel err {rel(hx, gx)}"
+    assert rel(hw, gw) < 2e-2, f"wgrad rel err {rel(hw, gw)}"
+    assert rel(hb, gb) < 1e-4
+
+
+def test_tcconv2d_module_relu_and_cnn_model_use_igemm():
+    from feddrift_b200.ops import conv as C
+    from feddrift_b200.ops.conv import TcConv2d
+    torch.manual_seed(0)
+    m = TcConv2d(32, 64, 3, padding=1, activation="relu").cuda()
+    x = torch.randn(2, 32, 10, 10, device="cuda", requires_grad=True)
+    n0 = C.IGEMM_CALLS["fwd"]
+    y = m(x)
+    assert C.IGEMM_CALLS["fwd"] == n0 + 1
+    ref = F.relu(F.conv2d(x, m.weight, m.bias, 1, 1))
+    assert (y - ref).abs().max().item() < 3e-2
+    y.sum().backward()
+    gx = x.grad.clone()
+    x.grad = None
+    ref.sum().backward()
+    assert (gx - x.grad).abs().max().item() / (x.grad.abs().max().item() + 1e-6) < 3e-2

@@ -569,11 +569,12 @@ static Tensor pack_conv_weights(const Tensor& w, int mode) {
 Tensor conv_igemm_fwd(Tensor x, Tensor w, c10::optional<Tensor> bias, int64_t stride, int64_t pad_h, int64_t pad_w, bool relu) {
     CHECK_CUDA_F32(x);
     TORCH_CHECK(x.dim() == 4 && x.is_contiguous(), "conv_igemm: x must be contiguous NHWC");
-    c10::cuda::CUDAGuard guard(x.device());
     const int N = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), C = (int)x.size(3);
     const int K = (int)w.size(0), R = (int)w.size(2), S = (int)w.size(3);
     TORCH_CHECK(w.size(1) == C, "conv_igemm: channel mismatch");
+    TORCH_CHECK(C % 16 == 0 && K % 32 == 0, "conv_igemm forward needs Cin % 16 == 0 and Cout % 32 == 0 (got ", C, ", ", K, ")");
     const int P = (H + 2 * (int)pad_h - R) / (int)stride + 1, Q = (W + 2 * (int)pad_w - S) / (int)stride + 1;
+    c10::cuda::CUDAGuard guard(x.device());
     auto wq = pack_conv_weights(w, 0);
     auto y = torch::empty({N, P, Q, K}, x.options());
     Tensor bias_f;
@@ -589,6 +590,8 @@ Tensor conv_igemm_fwd(Tensor x, Tensor w, c10::optional<Tensor> bias, int64_t st
 Tensor conv_igemm_dgrad(Tensor dy, Tensor w, int64_t H, int64_t W, int64_t stride, int64_t pad_h, int64_t pad_w) {
     CHECK_CUDA_F32(dy);
     TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous(), "conv_igemm_dgrad: dy must be contiguous NHWC");
+    TORCH_CHECK(w.size(0) % 16 == 0 && w.size(1) % 32 == 0, "conv_igemm dgrad needs Cout % 16 == 0 and Cin % 32 == 0 (got ", w.size(0), ", ",
+                w.size(1), ")");
     c10::cuda::CUDAGuard guard(dy.device());
     const int N = (int)dy.size(0), P = (int)dy.size(1), Q = (int)dy.size(2), K = (int)dy.size(3);
     const int C = (int)w.size(1), R = (int)w.size(2), S = (int)w.size(3);
@@ -606,6 +609,7 @@ Tensor conv_igemm_dgrad(Tensor dy, Tensor w, int64_t H, int64_t W, int64_t strid
 Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t stride, int64_t pad_h, int64_t pad_w) {
     CHECK_CUDA_F32(x); CHECK_CUDA_F32(dy);
     TORCH_CHECK(x.is_contiguous() && dy.is_contiguous() && x.dim() == 4 && dy.dim() == 4, "conv_igemm_wgrad: contiguous NHWC tensors");
+    TORCH_CHECK(x.size(3) % 8 == 0 && dy.size(3) % 32 == 0, "conv_igemm wgrad needs Cin % 8 == 0 and Cout % 32 == 0");
     c10::cuda::CUDAGuard guard(x.device());
     const int N = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), C = (int)x.size(3);
     const int P = (int)dy.size(1), Q = (int)dy.size(2), K = (int)dy.size(3);

@@ -9,7 +9,7 @@
             split over pixel ranges with coalesced ``red.global.add`` into the fp32 gradient.
 
 fp32 activations / master weights, bf16 tensor-core operands, fp32 accumulation in TMEM.  Shapes the kernels do not cover
-(groups / dilation ≠ 1, Cin not a multiple of 16 — e.g. the 1- or 3-channel stems —, Cout not a multiple of 32) and CPU
+(groups / dilation ≠ 1, Cin or Cout not a multiple of 32 — e.g. the 1- or 3-channel stems) and CPU
 tensors use ``F.conv2d``.  ``FDB_CONV_IM2COL=1`` selects the round-1 explicit-im2col + GEMM formulation (kept for A/B
 measurements).  State-dict keys and the init law equal ``nn.Conv2d``'s.  Reference: cuDNN fp32 ``nn.Conv2d``
 (``fedml_api/model/cv/cnn.py:110-117``).
@@ -39,7 +39,8 @@ def _nhwc(t: torch.Tensor) -> torch.Tensor:
 
 
 def igemm_eligible(cin: int, cout: int, stride, dilation, groups: int) -> bool:
-    return groups == 1 and tuple(dilation) == (1, 1) and stride[0] == stride[1] and cin % 16 == 0 and cout % 32 == 0
+    # forward needs Cin % 16 / Cout % 32; the data gradient swaps the roles → both multiples of 32
+    return groups == 1 and tuple(dilation) == (1, 1) and stride[0] == stride[1] and cin % 32 == 0 and cout % 32 == 0
 
 
 class _ConvIgemmFn(torch.autograd.Function):

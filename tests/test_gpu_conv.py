@@ -13,7 +13,7 @@ GEOMS = [
     (2, 64, 16, 16, 128, 1, 2, 0),     # ResNet-18 1x1 shortcut
     (3, 128, 8, 8, 256, 3, 1, 1),
     (2, 256, 4, 4, 512, 3, 2, 1),
-    (5, 16, 9, 11, 32, 5, 1, 2),       # odd sizes, 5x5, small channels
+    (5, 32, 9, 11, 32, 5, 1, 2),       # odd sizes, 5x5, small channels
     (2, 96, 7, 7, 96, 3, 1, 1),        # Cout multiple of 32 only
 ]
 
@@ -61,3 +61,14 @@ def test_tcconv2d_module_relu_and_cnn_model_use_igemm():
     x.grad = None
     ref.sum().backward()
     assert (gx - x.grad).abs().max().item() / (x.grad.abs().max().item() + 1e-6) < 3e-2
+
+
+def test_unsupported_channel_counts_raise_cleanly_and_module_falls_back():
+    from feddrift_b200.ops import _ext
+    from feddrift_b200.ops.conv import TcConv2d
+    ext = _ext.load(required=True)
+    with pytest.raises(RuntimeError):
+        ext.conv_igemm_dgrad(torch.zeros(1, 4, 4, 32, device="cuda"), torch.zeros(32, 16, 3, 3, device="cuda"), 4, 4, 1, 0, 0)
+    m = TcConv2d(3, 64, 3, padding=1).cuda()          # 3-channel stem → F.conv2d
+    y = m(torch.randn(2, 3, 8, 8, device="cuda"))
+    assert y.shape == (2, 64, 8, 8)

@@ -317,6 +317,11 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols /*K*/
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// exported for conv_igemm.cu: K-major 128B-swizzled map of a bf16 [rows, cols] matrix with (64 × box_rows) boxes
+int make_kmajor_sw128_map(void* map_out, const void* base, int rows, int cols, int box_rows) {
+    return make_map(reinterpret_cast<CUtensorMap*>(map_out), base, rows, cols, box_rows);
+}
+
 // output map: 32-row × 128-byte boxes (32 fp32 or 64 bf16 columns), 128B swizzle — what one epilogue warp stages per chunk.
 // Returns 0 and sets *ok = 1 when D qualifies for TMA stores (16-byte aligned base and row pitch).
 static int make_out_map(CUtensorMap* map, void* D, int M, int N, int out_fp32, int* ok) {

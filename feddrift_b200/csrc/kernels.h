@@ -66,6 +66,7 @@ struct ConvArgs {
     float* dw;             // wgrad: zeroed [Kout][R][S][C] fp32
     int N, H, W, C, Kout, R, S, P, Q, pad_h, pad_w, stride, mode, relu;
 };
+int make_kmajor_sw128_map(void* map_out /* CUtensorMap* */, const void* base, int rows, int cols, int box_rows);   // gemm_tc.cu
 int conv_igemm_launch(const ConvArgs& a, cudaStream_t stream);
 int conv_wgrad_launch(const ConvArgs& a, cudaStream_t stream);
 int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream);

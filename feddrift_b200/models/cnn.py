@@ -5,10 +5,10 @@ and ``:71-136`` (CNN_DropOut, 1 199 882 params: conv3×3(1→32) → conv3×3(32
 with NO ReLU between the convs, maxpool2, dropout .25, fc 9216→128 ReLU,
 dropout .5, fc →10, **Softmax before CrossEntropy**; flat 784 input reshaped).
 The fully-connected layers are :class:`~feddrift_b200.ops.linear.TcLinear` (tcgen05 GEMM with fused bias/ReLU
-epilogue on sm_100a, plain ``F.linear`` on CPU).  The 32→64 convolutions can run on
-:class:`~feddrift_b200.ops.conv.TcConv2d` (im2col + the same tcgen05 GEMM) with ``FDB_TC_CONV=1``; measured on B200
-(``profiles/README.md``, conv table) cuDNN is still 1.1–2.2× faster than the explicit-im2col formulation at these
-shapes, so the library conv is the default until the TMA-im2col (implicit GEMM) producer lands.
+epilogue on sm_100a, plain ``F.linear`` on CPU).  The 32→64 convolutions are
+:class:`~feddrift_b200.ops.conv.TcConv2d`: implicit-GEMM forward / dgrad / wgrad kernels on tcgen05
+(``csrc/conv_igemm.cu``; ``FDB_NO_TC_CONV=1`` routes them to the library conv for A/B measurements).  The 1-channel stem
+convolution (9 or 25 multiply-adds per output) stays a library call.
 """
 from __future__ import annotations
 
@@ -21,7 +21,7 @@ from ..ops.linear import TcLinear
 
 
 def _conv(*a, **k):
-    return TcConv2d(*a, **k) if os.environ.get("FDB_TC_CONV") == "1" else nn.Conv2d(*a, **k)
+    return TcConv2d(*a, **k)
 
 
 class CNN_OriginalFedAvg(nn.Module):

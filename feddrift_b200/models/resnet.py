@@ -14,16 +14,17 @@ from typing import Callable, List
 import torch
 from torch import nn
 
+from ..ops.conv import TcConv2d
 from ..ops.linear import TcLinear
 from .group_norm import GroupNorm2d
 
 
 def conv3x3(i, o, stride=1):
-    return nn.Conv2d(i, o, 3, stride, 1, bias=False)
+    return TcConv2d(i, o, 3, stride, 1, bias=False)   # implicit-GEMM tcgen05 conv; library conv when ineligible / on CPU
 
 
 def conv1x1(i, o, stride=1):
-    return nn.Conv2d(i, o, 1, stride, bias=False)
+    return TcConv2d(i, o, 1, stride, bias=False)
 
 
 class BasicBlock(nn.Module):
@@ -86,7 +87,7 @@ class ResNet(nn.Module):
         self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
         self.fc = TcLinear(widths[len(layers) - 1] * block.expansion, num_classes)
         for m in self.modules():
-            if isinstance(m, nn.Conv2d):
+            if isinstance(m, (nn.Conv2d, TcConv2d)):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
             elif isinstance(m, (nn.BatchNorm2d, nn.GroupNorm, GroupNorm2d)) and getattr(m, "weight", None) is not None:
                 nn.init.constant_(m.weight, 1)

@@ -12,8 +12,10 @@ def resnet18(num_classes: int = 1000, small_input: bool = False) -> nn.Module:
     if small_input:  # CIFAR-sized inputs: 3×3 stem, no max-pool
         m.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
         m.maxpool = nn.Identity()
-    return m
+    from ..ops.conv import convert_convs_
+    return convert_convs_(m)     # body convolutions → implicit-GEMM tcgen05 kernels (same state-dict keys)
 
 
 def densenet121(num_classes: int = 1000) -> nn.Module:
-    return torchvision.models.densenet121(weights=None, num_classes=num_classes)
+    from ..ops.conv import convert_convs_
+    return convert_convs_(torchvision.models.densenet121(weights=None, num_classes=num_classes))

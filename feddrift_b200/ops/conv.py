@@ -153,3 +153,20 @@ class TcConv2d(nn.Module):
     def extra_repr(self) -> str:
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
                 f"padding={self.padding}, activation={self.activation}")
+
+
+def convert_convs_(module: nn.Module) -> nn.Module:
+    """Replace every eligible ``nn.Conv2d`` of ``module`` (in place) by a :class:`TcConv2d` sharing the same parameters —
+    state-dict keys, shapes and values are unchanged.  Used for the torchvision / model-zoo networks so that their 3×3 and
+    1×1 body convolutions run on the implicit-GEMM tcgen05 kernels (stems with 1 or 3 input channels stay library convs)."""
+    for name, child in list(module.named_children()):
+        if type(child) is nn.Conv2d and child.padding_mode == "zeros" and not isinstance(child.padding, str) and \
+                igemm_eligible(child.in_channels, child.out_channels, _pair(child.stride), _pair(child.dilation), child.groups):
+            tc = TcConv2d(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding, child.dilation,
+                          child.groups, bias=child.bias is not None)
+            tc.weight = child.weight
+            tc.bias = child.bias
+            setattr(module, name, tc)
+        else:
+            convert_convs_(child)
+    return module

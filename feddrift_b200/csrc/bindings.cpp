@@ -557,25 +557,28 @@ void lstm_head(Tensor params, Tensor row_off, int64_t off_fcw, int64_t off_fcb, 
 }
 
 // ---------------------------------------------------------------------------------- implicit-GEMM convolution (conv_igemm.cu)
-static Tensor pack_conv_weights(const Tensor& w, int mode) {
+// -> (bf16 [K][R][S][C] for the forward kernel, bf16 [C][R][S][K] for the data-gradient kernel) in ONE launch
+std::vector<Tensor> conv_pack_weights(Tensor w) {
     CHECK_CUDA_F32(w);
     TORCH_CHECK(w.dim() == 4 && w.is_contiguous(), "conv weights must be contiguous OIHW");
+    c10::cuda::CUDAGuard guard(w.device());
     const int K = (int)w.size(0), C = (int)w.size(1), R = (int)w.size(2), S = (int)w.size(3);
-    auto out = torch::empty({mode == 0 ? K : C, R, S, mode == 0 ? C : K}, w.options().dtype(torch::kBFloat16));
-    CHECK_OK(fdb::conv_pack_weights_launch(w.data_ptr<float>(), out.data_ptr(), K, C, R, S, mode, cur_stream()), "conv_pack_weights");
-    return out;
+    auto o0 = torch::empty({K, R, S, C}, w.options().dtype(torch::kBFloat16));
+    auto o1 = torch::empty({C, R, S, K}, w.options().dtype(torch::kBFloat16));
+    CHECK_OK(fdb::conv_pack_weights_both_launch(w.data_ptr<float>(), o0.data_ptr(), o1.data_ptr(), K, C, R, S, cur_stream()), "conv_pack_weights");
+    return {o0, o1};
 }
-// x: NHWC fp32 [N, H, W, C]; w: fp32 OIHW; -> y NHWC fp32 [N, P, Q, K] = act(conv(x, w) + bias)
-Tensor conv_igemm_fwd(Tensor x, Tensor w, c10::optional<Tensor> bias, int64_t stride, int64_t pad_h, int64_t pad_w, bool relu) {
+// x: NHWC fp32 [N, H, W, C]; wq: packed bf16 [K][R][S][C]; -> y NHWC fp32 [N, P, Q, K] = act(conv(x, w) + bias)
+Tensor conv_igemm_fwd(Tensor x, Tensor wq, c10::optional<Tensor> bias, int64_t stride, int64_t pad_h, int64_t pad_w, bool relu) {
     CHECK_CUDA_F32(x);
     TORCH_CHECK(x.dim() == 4 && x.is_contiguous(), "conv_igemm: x must be contiguous NHWC");
+    TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kBFloat16 && wq.dim() == 4 && wq.is_contiguous(), "conv_igemm: wq must be packed bf16 [K,R,S,C]");
     const int N = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), C = (int)x.size(3);
-    const int K = (int)w.size(0), R = (int)w.size(2), S = (int)w.size(3);
-    TORCH_CHECK(w.size(1) == C, "conv_igemm: channel mismatch");
+    const int K = (int)wq.size(0), R = (int)wq.size(1), S = (int)wq.size(2);
+    TORCH_CHECK(wq.size(3) == C, "conv_igemm: channel mismatch");
     TORCH_CHECK(C % 16 == 0 && K % 32 == 0, "conv_igemm forward needs Cin % 16 == 0 and Cout % 32 == 0 (got ", C, ", ", K, ")");
     const int P = (H + 2 * (int)pad_h - R) / (int)stride + 1, Q = (W + 2 * (int)pad_w - S) / (int)stride + 1;
     c10::cuda::CUDAGuard guard(x.device());
-    auto wq = pack_conv_weights(w, 0);
     auto y = torch::empty({N, P, Q, K}, x.options());
     Tensor bias_f;
     fdb::ConvArgs a{};
@@ -586,26 +589,25 @@ Tensor conv_igemm_fwd(Tensor x, Tensor w, c10::optional<Tensor> bias, int64_t st
     CHECK_OK(fdb::conv_igemm_launch(a, cur_stream()), "conv_igemm forward (tcgen05)");
     return y;
 }
-// dy: NHWC fp32 [N, P, Q, K]; w: fp32 OIHW [K, C, R, S]; -> dx NHWC fp32 [N, H, W, C]
-Tensor conv_igemm_dgrad(Tensor dy, Tensor w, int64_t H, int64_t W, int64_t stride, int64_t pad_h, int64_t pad_w) {
+// dy: NHWC fp32 [N, P, Q, K]; wq_t: packed bf16 [C][R][S][K]; -> dx NHWC fp32 [N, H, W, C]
+Tensor conv_igemm_dgrad(Tensor dy, Tensor wq_t, int64_t H, int64_t W, int64_t stride, int64_t pad_h, int64_t pad_w) {
     CHECK_CUDA_F32(dy);
     TORCH_CHECK(dy.dim() == 4 && dy.is_contiguous(), "conv_igemm_dgrad: dy must be contiguous NHWC");
-    TORCH_CHECK(w.size(0) % 16 == 0 && w.size(1) % 32 == 0, "conv_igemm dgrad needs Cout % 16 == 0 and Cin % 32 == 0 (got ", w.size(0), ", ",
-                w.size(1), ")");
-    c10::cuda::CUDAGuard guard(dy.device());
+    TORCH_CHECK(wq_t.is_cuda() && wq_t.scalar_type() == torch::kBFloat16 && wq_t.dim() == 4 && wq_t.is_contiguous(), "conv_igemm_dgrad: wq_t must be packed bf16 [C,R,S,K]");
     const int N = (int)dy.size(0), P = (int)dy.size(1), Q = (int)dy.size(2), K = (int)dy.size(3);
-    const int C = (int)w.size(1), R = (int)w.size(2), S = (int)w.size(3);
-    TORCH_CHECK(w.size(0) == K, "conv_igemm_dgrad: channel mismatch");
-    auto wq = pack_conv_weights(w, 1);                   // [C][R][S][K]
+    const int C = (int)wq_t.size(0), R = (int)wq_t.size(1), S = (int)wq_t.size(2);
+    TORCH_CHECK(wq_t.size(3) == K, "conv_igemm_dgrad: channel mismatch");
+    TORCH_CHECK(K % 16 == 0 && C % 32 == 0, "conv_igemm dgrad needs Cout % 16 == 0 and Cin % 32 == 0 (got ", K, ", ", C, ")");
+    c10::cuda::CUDAGuard guard(dy.device());
     auto dx = torch::empty({N, H, W, C}, dy.options());
     fdb::ConvArgs a{};
-    a.x = dy.data_ptr<float>(); a.wq = reinterpret_cast<const __nv_bfloat16*>(wq.data_ptr()); a.y = dx.data_ptr<float>();
+    a.x = dy.data_ptr<float>(); a.wq = reinterpret_cast<const __nv_bfloat16*>(wq_t.data_ptr()); a.y = dx.data_ptr<float>();
     a.N = N; a.H = P; a.W = Q; a.C = K; a.Kout = C; a.R = R; a.S = S; a.P = (int)H; a.Q = (int)W;
     a.pad_h = (int)pad_h; a.pad_w = (int)pad_w; a.stride = (int)stride; a.mode = 1; a.relu = 0;
     CHECK_OK(fdb::conv_igemm_launch(a, cur_stream()), "conv_igemm dgrad (tcgen05)");
     return dx;
 }
-// x: NHWC fp32 [N, H, W, C]; dy: NHWC fp32 [N, P, Q, K]; -> dW fp32 [K, R, S, C]
+// x: NHWC fp32 [N, H, W, C]; dy: NHWC fp32 [N, P, Q, K]; -> dW fp32 OIHW [K, C, R, S]
 Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t stride, int64_t pad_h, int64_t pad_w) {
     CHECK_CUDA_F32(x); CHECK_CUDA_F32(dy);
     TORCH_CHECK(x.is_contiguous() && dy.is_contiguous() && x.dim() == 4 && dy.dim() == 4, "conv_igemm_wgrad: contiguous NHWC tensors");
@@ -613,7 +615,8 @@ Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t strid
     c10::cuda::CUDAGuard guard(x.device());
     const int N = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), C = (int)x.size(3);
     const int P = (int)dy.size(1), Q = (int)dy.size(2), K = (int)dy.size(3);
-    auto dw = torch::zeros({K, R, S, C}, x.options());
+    auto dw = torch::empty({K, C, R, S}, x.options());
+    cudaMemsetAsync(dw.data_ptr<float>(), 0, (size_t)dw.numel() * sizeof(float), cur_stream());
     fdb::ConvArgs a{};
     a.x = x.data_ptr<float>(); a.dy = dy.data_ptr<float>(); a.dw = dw.data_ptr<float>();
     a.N = N; a.H = H; a.W = W; a.C = C; a.Kout = K; a.R = (int)R; a.S = (int)S; a.P = P; a.Q = Q;
@@ -685,6 +688,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("lstm2_backward", &lstm2_backward);
     m.def("lstm_head", &lstm_head);
     m.def("lstm_small_grads", &lstm_small_grads);
+    m.def("conv_pack_weights", &conv_pack_weights);
     m.def("conv_igemm_fwd", &conv_igemm_fwd);
     m.def("conv_igemm_dgrad", &conv_igemm_dgrad);
     m.def("conv_igemm_wgrad", &conv_igemm_wgrad);

@@ -281,6 +281,28 @@ __global__ void conv_pack_weights_kernel(const float* __restrict__ w, __nv_bfloa
     }
 }
 
+// both packs in one launch: out0 = [k][r][s][c] (forward), out1 = [c][r][s][k] (dgrad)
+__global__ void conv_pack_weights_both_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out0, __nv_bfloat16* __restrict__ out1,
+                                              int K, int C, int R, int S) {
+    const long long total = (long long)K * C * R * S;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;                                         // i indexes the OIHW source: coalesced reads
+        const int s = (int)(t % S); t /= S;
+        const int r = (int)(t % R); t /= R;
+        const int c = (int)(t % C);
+        const int k = (int)(t / C);
+        const __nv_bfloat16 v = __float2bfloat16(w[i]);
+        out0[(((size_t)k * R + r) * S + s) * C + c] = v;
+        out1[(((size_t)c * R + r) * S + s) * K + k] = v;
+    }
+}
+int conv_pack_weights_both_launch(const float* w, void* out0, void* out1, int K, int C, int R, int S, cudaStream_t stream) {
+    const long long total = (long long)K * C * R * S;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    conv_pack_weights_both_kernel<<<blocks, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out0), reinterpret_cast<__nv_bfloat16*>(out1), K, C, R, S);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
 int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream) {
     const long long total = (long long)K * C * R * S;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
@@ -430,9 +452,10 @@ __global__ void __launch_bounds__(cv::kFwdThreads, 1) conv_wgrad_kernel(const __
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (j < RSC) {
+            if (j < RSC) {   // dW is written in the framework's OIHW layout: [k][c][r][s]
+                const int tap = j / a.C, c = j - tap * a.C, RS = a.R * a.S;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(a.dw + (size_t)(n_blk * BN + c0 + i) * RSC + j, __uint_as_float(v[i]));
+                for (int i = 0; i < 32; ++i) atomicAdd(a.dw + ((size_t)(n_blk * BN + c0 + i) * a.C + c) * RS + tap, __uint_as_float(v[i]));
             }
         }
     }
@@ -497,6 +520,8 @@ static int launch_conv_m(const ConvArgs& a, cudaStream_t stream) {
     if (!a.relu && tiles * 2 <= sms && nKall >= 8) {          // too few tiles to fill the machine and a long reduction
         splits = std::min(std::min(sms / tiles, nKall / 4), 16);
         if (splits < 2) splits = 1;
+        const int kper = (nKall + splits - 1) / splits;
+        splits = (nKall + kper - 1) / kper;                   // every split gets a non-empty k range
     }
     if (splits > 1) cudaMemsetAsync(a.y, 0, (size_t)Mtot * a.Kout * sizeof(float), stream);
     conv_igemm_kernel<BN, CK, MODE><<<std::min(tiles * splits, sms), kFwdThreads, smem, stream>>>(a, map_w, tma_w, splits);

@@ -63,12 +63,13 @@ struct ConvArgs {
     const float* bias;     // [Kout] or nullptr (forward)
     float* y;              // [N, P, Q, Kout] output of forward / dgrad
     const float* dy;       // wgrad: [N·P·Q, Kout]
-    float* dw;             // wgrad: zeroed [Kout][R][S][C] fp32
+    float* dw;             // wgrad: zeroed fp32 gradient in OIHW layout [Kout][C][R][S]
     int N, H, W, C, Kout, R, S, P, Q, pad_h, pad_w, stride, mode, relu;
 };
 int make_kmajor_sw128_map(void* map_out /* CUtensorMap* */, const void* base, int rows, int cols, int box_rows);   // gemm_tc.cu
 int conv_igemm_launch(const ConvArgs& a, cudaStream_t stream);
 int conv_wgrad_launch(const ConvArgs& a, cudaStream_t stream);
+int conv_pack_weights_both_launch(const float* w, void* out0, void* out1, int K, int C, int R, int S, cudaStream_t stream);
 int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream);
 // lstm_tc.cu : persistent cluster-resident 2-layer LSTM(256) forward / BPTT over many (client, model) pairs per launch
 struct LstmArgs {

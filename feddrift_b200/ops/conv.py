@@ -51,9 +51,9 @@ class _ConvIgemmFn(torch.autograd.Function):
         IGEMM_CALLS["fwd"] += 1
         ext = _ext.load(required=True)
         xh = _nhwc(x)
-        w = weight.detach().float().contiguous()
-        y = ext.conv_igemm_fwd(xh, w, bias.detach() if bias is not None else None, stride[0], padding[0], padding[1], bool(relu))
-        ctx.save_for_backward(xh, w, y if relu else None)
+        wq, wq_t = ext.conv_pack_weights(weight.detach().float().contiguous())     # both tensor-core packs, one launch
+        y = ext.conv_igemm_fwd(xh, wq, bias.detach() if bias is not None else None, stride[0], padding[0], padding[1], bool(relu))
+        ctx.save_for_backward(xh, wq_t, y if relu else None)
         ctx.geom = (stride, padding, tuple(weight.shape))
         ctx.relu, ctx.has_bias = relu, bias is not None
         return y.permute(0, 3, 1, 2)                                          # NCHW view, channels_last strides
@@ -61,7 +61,7 @@ class _ConvIgemmFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         ext = _ext.load(required=True)
-        xh, w, y = ctx.saved_tensors
+        xh, wq_t, y = ctx.saved_tensors
         stride, padding, (Co, Ci, kh, kw) = ctx.geom
         g = _nhwc(gy)
         if ctx.relu:
@@ -69,10 +69,10 @@ class _ConvIgemmFn(torch.autograd.Function):
         gx = gw = gbias = None
         if ctx.needs_input_grad[0]:
             IGEMM_CALLS["dgrad"] += 1
-            gx = ext.conv_igemm_dgrad(g, w, xh.shape[1], xh.shape[2], stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
+            gx = ext.conv_igemm_dgrad(g, wq_t, xh.shape[1], xh.shape[2], stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             IGEMM_CALLS["wgrad"] += 1
-            gw = ext.conv_igemm_wgrad(xh, g, kh, kw, stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)    # [K,R,S,C] → OIHW view
+            gw = ext.conv_igemm_wgrad(xh, g, kh, kw, stride[0], padding[0], padding[1])                  # written directly as OIHW
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gbias = g.sum((0, 1, 2))
         return gx, gw, gbias, None, None, None

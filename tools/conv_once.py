@@ -13,7 +13,8 @@ w = torch.randn(cout, cin, k, k, device="cuda") * 0.05
 Ho = (hw + 2 * pad - k) // stride + 1
 dy = torch.randn(B, Ho, Ho, cout, device="cuda")
 for _ in range(2):
-    y = ext.conv_igemm_fwd(x, w, None, stride, pad, pad, False)
-    dx = ext.conv_igemm_dgrad(dy, w, hw, hw, stride, pad, pad)
+    wpk = ext.conv_pack_weights(w)
+    y = ext.conv_igemm_fwd(x, wpk[0], None, stride, pad, pad, False)
+    dx = ext.conv_igemm_dgrad(dy, wpk[1], hw, hw, stride, pad, pad)
     dw = ext.conv_igemm_wgrad(x, dy, k, k, stride, pad, pad)
 torch.cuda.synchronize()

@@ -608,15 +608,24 @@ Tensor conv_igemm_dgrad(Tensor dy, Tensor wq_t, int64_t H, int64_t W, int64_t st
     return dx;
 }
 // x: NHWC fp32 [N, H, W, C]; dy: NHWC fp32 [N, P, Q, K]; -> dW fp32 OIHW [K, C, R, S]
-Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t stride, int64_t pad_h, int64_t pad_w) {
+// `accum_into`: an existing fp32 OIHW gradient buffer to ADD into (no zero-fill, no extra accumulate kernel) — the federated
+// executor's parameters already own a zeroed `.grad` view of the flat gradient row
+Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t stride, int64_t pad_h, int64_t pad_w, c10::optional<Tensor> accum_into) {
     CHECK_CUDA_F32(x); CHECK_CUDA_F32(dy);
     TORCH_CHECK(x.is_contiguous() && dy.is_contiguous() && x.dim() == 4 && dy.dim() == 4, "conv_igemm_wgrad: contiguous NHWC tensors");
     TORCH_CHECK(x.size(3) % 8 == 0 && dy.size(3) % 32 == 0, "conv_igemm wgrad needs Cin % 8 == 0 and Cout % 32 == 0");
     c10::cuda::CUDAGuard guard(x.device());
     const int N = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), C = (int)x.size(3);
     const int P = (int)dy.size(1), Q = (int)dy.size(2), K = (int)dy.size(3);
-    auto dw = torch::empty({K, C, R, S}, x.options());
-    cudaMemsetAsync(dw.data_ptr<float>(), 0, (size_t)dw.numel() * sizeof(float), cur_stream());
+    Tensor dw;
+    if (accum_into.has_value() && accum_into->defined()) {
+        dw = *accum_into;
+        CHECK_CUDA_F32(dw);
+        TORCH_CHECK(dw.is_contiguous() && dw.numel() == (int64_t)K * C * R * S, "conv_igemm_wgrad: accum_into must be a contiguous OIHW buffer");
+    } else {
+        dw = torch::empty({K, C, R, S}, x.options());
+        cudaMemsetAsync(dw.data_ptr<float>(), 0, (size_t)dw.numel() * sizeof(float), cur_stream());
+    }
     fdb::ConvArgs a{};
     a.x = x.data_ptr<float>(); a.dy = dy.data_ptr<float>(); a.dw = dw.data_ptr<float>();
     a.N = N; a.H = H; a.W = W; a.C = C; a.Kout = K; a.R = (int)R; a.S = (int)S; a.P = P; a.Q = Q;

@@ -54,6 +54,7 @@ class _ConvIgemmFn(torch.autograd.Function):
         wq, wq_t = ext.conv_pack_weights(weight.detach().float().contiguous())     # both tensor-core packs, one launch
         y = ext.conv_igemm_fwd(xh, wq, bias.detach() if bias is not None else None, stride[0], padding[0], padding[1], bool(relu))
         ctx.save_for_backward(xh, wq_t, y if relu else None)
+        ctx.weight_ref = weight if isinstance(weight, torch.nn.Parameter) else None
         ctx.geom = (stride, padding, tuple(weight.shape))
         ctx.relu, ctx.has_bias = relu, bias is not None
         return y.permute(0, 3, 1, 2)                                          # NCHW view, channels_last strides
@@ -72,7 +73,14 @@ class _ConvIgemmFn(torch.autograd.Function):
             gx = ext.conv_igemm_dgrad(g, wq_t, xh.shape[1], xh.shape[2], stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             IGEMM_CALLS["wgrad"] += 1
-            gw = ext.conv_igemm_wgrad(xh, g, kh, kw, stride[0], padding[0], padding[1])                  # written directly as OIHW
+            wp = ctx.weight_ref
+            acc = wp.grad if (wp is not None and wp.grad is not None and wp.grad.is_contiguous() and wp.grad.dtype == torch.float32
+                              and wp.grad.shape == wp.shape and wp.grad.is_cuda) else None
+            # with a preallocated .grad (the federated executor binds every parameter's .grad to its slice of the flat, zeroed
+            # gradient row) the kernel adds straight into it: no zero-fill launch, no AccumulateGrad add launch
+            gw = ext.conv_igemm_wgrad(xh, g, kh, kw, stride[0], padding[0], padding[1], acc)           # OIHW
+            if acc is not None:
+                gw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gbias = g.sum((0, 1, 2))
         return gx, gw, gbias, None, None, None

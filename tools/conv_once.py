@@ -16,5 +16,5 @@ for _ in range(2):
     wpk = ext.conv_pack_weights(w)
     y = ext.conv_igemm_fwd(x, wpk[0], None, stride, pad, pad, False)
     dx = ext.conv_igemm_dgrad(dy, wpk[1], hw, hw, stride, pad, pad)
-    dw = ext.conv_igemm_wgrad(x, dy, k, k, stride, pad, pad)
+    dw = ext.conv_igemm_wgrad(x, dy, k, k, stride, pad, pad, None)
 torch.cuda.synchronize()

@@ -57,7 +57,7 @@ for B, cin, cout, k, stride, pad, hw in ((50, 32, 64, 3, 1, 0, 26), (32, 64, 64,
     r = {"shape": f"B{B} {cin}->{cout} k{k} s{stride} p{pad} {hw}x{hw}", "GFLOP_per_dir": 2.0 * B * Ho * Ho * cout * cin * k * k / 1e9}
     r["ours_fwd_us"] = timeit(lambda: ext.conv_igemm_fwd(xh, ext.conv_pack_weights(w)[0], tc.bias.detach(), stride, pad, pad, False))
     r["ours_dgrad_us"] = timeit(lambda: ext.conv_igemm_dgrad(dyh, wpk[1], hw, hw, stride, pad, pad))
-    r["ours_wgrad_us"] = timeit(lambda: ext.conv_igemm_wgrad(xh, dyh, k, k, stride, pad, pad))
+    r["ours_wgrad_us"] = timeit(lambda: ext.conv_igemm_wgrad(xh, dyh, k, k, stride, pad, pad, None))
     r["cudnn_fp32_fwd_us"] = timeit(lambda: F.conv2d(x, w, tc.bias.detach(), stride, pad))
     r["cudnn_fp32_bwd_us"] = timeit(lambda: torch.ops.aten.convolution_backward(dy_nchw, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, mask))
     r["cudnn_bf16cl_fwd_us"] = timeit(lambda: F.conv2d(xb, wb, None, stride, pad))

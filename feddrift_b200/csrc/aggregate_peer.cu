@@ -1,20 +1,23 @@
 // fedavg_reduce_apply_peer — the multi-GPU per-cluster FedAvg aggregation + broadcast as ONE kernel per rank, with the
-// collective done by the kernel itself over NVLink peer memory (no NCCL):
+// collective done by the kernel itself over NVLink peer memory (no NCCL), PIPELINED chunk by chunk:
 //
-//   phase 0  every rank reduces its local clients' weights  Σ_c n[c,m]  and pushes the M totals to all peers
-//   phase 1  local weighted partial sums   part_g[m,:] = Σ_{c on g} n[c,m]·θ_c[m,:]        (HBM-bound, like K1)
-//   barrier  grid-wide (cooperative launch) + cross-GPU epoch flags (st.release.sys / ld.acquire.sys)
-//   phase 2  reduce-scatter + apply + all-gather fused: rank g owns the slice [g·P/W, (g+1)·P/W) of every cluster
-//            model; it pulls that slice of every peer's partial with 128-bit peer loads (W independent loads in
-//            flight per thread), divides by the global weight total and pushes the finished slice into EVERY rank's
-//            θ buffer with peer stores — the broadcast of the new cluster models is the epilogue of the reduction
-//            — or, when the symmetric buffer has an NVLS multicast mapping, ONE multimem.ld_reduce (in-switch add of the
-//            W partials) and ONE multimem.st (in-switch replication of the finished slice) per 16 bytes
-//   barrier  cross-GPU epoch flag so θ is complete everywhere when the kernel retires
+//   producer CTAs   stream the local clients' rows IN PLACE from the client arena (row list `cidx`, no gather copy) and
+//                   write un-normalised partial sums part_g[m, chunk] = Σ_{c on g} n[c,m]·θ_c[m, chunk]   (HBM-bound, like K1);
+//                   the last producer CTA to finish a chunk publishes a per-chunk epoch flag to every peer
+//                   (fence.sys + st.release.sys);
+//   consumer CTAs   run concurrently: as soon as chunk k is flagged by ALL ranks they reduce-scatter + normalise +
+//                   all-gather it: rank g owns 1/W of the chunk, pulls it from every peer's partial buffer (128-bit peer
+//                   loads, or ONE multimem.ld_reduce = in-switch add when the buffer has an NVLS multicast mapping),
+//                   divides by the global weight total and pushes the finished piece into EVERY rank's θ buffer
+//                   (peer stores / multimem.st) — the broadcast of the new cluster models is the epilogue of the reduction;
+//   so the HBM stream of chunk k+1 overlaps the NVLink traffic of chunk k (round 1 ran the two phases back to back behind
+//   a grid barrier + peer barrier).  One final barrier makes θ complete everywhere before the kernel retires.
 //
 // Wire bytes per rank: (W-1)/W·M·P·4 in + the same out — the reduce-scatter/all-gather minimum; the reference moves
 // N pickled state_dicts of ALL M models to and from rank 0 every round.
 #include <cooperative_groups.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -24,14 +27,19 @@ namespace cg = cooperative_groups;
 namespace fdb {
 
 struct PeerAggParams {
-    const float* cp;      // [C_local, M, P] local client rows
-    const float* n;       // [C_local, M] local weights
+    const float* cp;      // client arena [C_arena, M, P]; row c of the local client list is cidx[c] (or c when cidx == nullptr)
+    const int* cidx;      // [C] arena rows of this rank's clients, or nullptr
+    const float* n;       // [C, M] local weights
     float* part[8];       // part[r]: rank r's symmetric partial buffer [M, P] (part[rank] is local)
     float* theta[8];      // theta[r]: rank r's symmetric model buffer  [M, theta_stride]
     float* tot_inbox[8];  // tot_inbox[r]: rank r's [world, M] weight-total inbox
     float* mc_part;       // NVLS: multicast alias of the partial buffers (nullptr → peer loads)
     float* mc_theta;      // NVLS: multicast alias of the θ buffers      (nullptr → peer stores)
-    unsigned* flags[8];   // flags[r]: rank r's [3, world] epoch words
+    unsigned* flags[8];   // flags[r]: rank r's [2 + nchunks, world] epoch words: slot 0 totals, slot 1 final, slot 2+k chunk k
+    unsigned* chunk_done; // local [nchunks] monotonic counters (producer CTAs that finished the chunk)
+    int n_prod;           // producer CTAs (the rest of the grid consumes)
+    int chunk4;           // chunk length in float4
+    unsigned launch_idx;  // number of earlier launches (chunk_done holds launch_idx · n_prod before this one)
     unsigned* grid_sync;  // local monotonically increasing grid-barrier counter
     unsigned epoch;       // this launch's epoch (monotonic across launches)
     unsigned grid_base;   // grid_sync value expected before this launch
@@ -98,100 +106,143 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
     const int C = p.C, M = p.M, P = p.P, W = p.world;
     const int P4 = P >> 2;  // host guarantees P % 4 == 0 (rows are padded)
     float* tot_s = wsm + C;
+    const int GP = p.n_prod, GC = (int)gridDim.x - GP;
+    const int cpm = (P4 + p.chunk4 - 1) / p.chunk4, nchunks = M * cpm;
 
-    // ---- phase 0: local weight totals → every peer's inbox
-    if (blockIdx.x == 0) {
-        for (int m = 0; m < M; ++m) {
-            float part = 0.f;
-            for (int c = threadIdx.x; c < C; c += blockDim.x) part += p.n[c * M + m];
-            const float tot = block_sum(part, red);
-            if (threadIdx.x == 0)
-                for (int r = 0; r < W; ++r) st_relaxed_sys_f32(p.tot_inbox[r] + p.rank * M + m, tot);
+    if ((int)blockIdx.x < GP) {
+        // ================================================================ producers
+        if (blockIdx.x == 0) {
+            // local weight totals → every peer's inbox, published with the slot-0 flag
+            for (int m = 0; m < M; ++m) {
+                float part = 0.f;
+                for (int c = threadIdx.x; c < C; c += blockDim.x) part += p.n[c * M + m];
+                const float tot = block_sum(part, red);
+                if (threadIdx.x == 0)
+                    for (int r = 0; r < W; ++r) st_relaxed_sys_f32(p.tot_inbox[r] + p.rank * M + m, tot);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < W) st_release_sys(p.flags[threadIdx.x] + 0 * W + p.rank, p.epoch);
         }
-    }
-    // ---- phase 1: un-normalised local partial sums (same streaming pattern as cluster_aggregate_kernel)
-    float* mine = p.part[p.rank];
-    for (int m = 0; m < M; ++m) {
-        __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) wsm[c] = p.n[c * M + m];
-        __syncthreads();
-        const float* base = p.cp + (size_t)m * P;
+        float* mine = p.part[p.rank];
+        int cur_m = -1;
         const size_t cstride = (size_t)M * P;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P4; i += gridDim.x * blockDim.x) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            int c = 0;
-            for (; c + 4 <= C; c += 4) {
-                float4 v[4];
+        for (int ck = 0; ck < nchunks; ++ck) {
+            const int m = ck / cpm, k = ck - m * cpm;
+            if (m != cur_m) {
+                __syncthreads();
+                for (int c = threadIdx.x; c < C; c += blockDim.x) wsm[c] = p.n[c * M + m];
+                __syncthreads();
+                cur_m = m;
+            }
+            const int lo = k * p.chunk4, hi = min(P4, lo + p.chunk4);
+            const float* base = p.cp + (size_t)m * P;
+            for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += GP * blockDim.x) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int c = 0;
+                for (; c + 4 <= C; c += 4) {
+                    float4 v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(base + (size_t)(c + u) * cstride) + i);
+                    for (int u = 0; u < 4; ++u) {
+                        const int row = p.cidx ? p.cidx[c + u] : c + u;
+                        v[u] = __ldcs(reinterpret_cast<const float4*>(base + (size_t)row * cstride) + i);
+                    }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float w = wsm[c + u];
-                    acc.x = fmaf(v[u].x, w, acc.x); acc.y = fmaf(v[u].y, w, acc.y);
-                    acc.z = fmaf(v[u].z, w, acc.z); acc.w = fmaf(v[u].w, w, acc.w);
+                    for (int u = 0; u < 4; ++u) {
+                        const float w = wsm[c + u];
+                        acc.x = fmaf(v[u].x, w, acc.x); acc.y = fmaf(v[u].y, w, acc.y);
+                        acc.z = fmaf(v[u].z, w, acc.z); acc.w = fmaf(v[u].w, w, acc.w);
+                    }
+                }
+                for (; c < C; ++c) {
+                    const int row = p.cidx ? p.cidx[c] : c;
+                    const float4 v = __ldcs(reinterpret_cast<const float4*>(base + (size_t)row * cstride) + i);
+                    const float w = wsm[c];
+                    acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+                }
+                reinterpret_cast<float4*>(mine + (size_t)m * P)[i] = acc;
+            }
+            // chunk complete on this CTA; the LAST producer CTA publishes the chunk to every peer
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned old = atomicAdd(p.chunk_done + ck, 1u);
+                if (old == p.launch_idx * (unsigned)GP + (unsigned)GP - 1u) {
+                    __threadfence_system();
+                    for (int r = 0; r < W; ++r) st_release_sys(p.flags[r] + (2 + ck) * W + p.rank, p.epoch);
                 }
             }
-            for (; c < C; ++c) {
-                const float4 v = __ldcs(reinterpret_cast<const float4*>(base + (size_t)c * cstride) + i);
-                const float w = wsm[c];
-                acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+        }
+    } else {
+        // ================================================================ consumers
+        const int cb = (int)blockIdx.x - GP;
+        if ((int)threadIdx.x < W) {   // weight totals of every rank
+            const unsigned* f = p.flags[p.rank] + 0 * W + threadIdx.x;
+            const long long t0 = globaltimer_ns();
+            while ((int)(ld_acquire_sys(f) - p.epoch) < 0) {
+                if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 4); break; }
             }
-            reinterpret_cast<float4*>(mine + (size_t)m * P)[i] = acc;
+        }
+        __syncthreads();
+        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+            float t = 0.f;
+            for (int r = 0; r < W; ++r) t += ld_relaxed_sys_f32(p.tot_inbox[p.rank] + r * M + m);
+            tot_s[m] = t;
+        }
+        __syncthreads();
+        for (int ck = 0; ck < nchunks; ++ck) {
+            const int m = ck / cpm, k = ck - m * cpm;
+            const float tot = tot_s[m];
+            if (!(tot > 0.f)) continue;       // unused cluster: leave θ untouched everywhere (block-uniform)
+            if ((int)threadIdx.x < W) {       // chunk k of EVERY rank's partial buffer is complete
+                const unsigned* f = p.flags[p.rank] + (2 + ck) * W + threadIdx.x;
+                const long long t0 = globaltimer_ns();
+                while ((int)(ld_acquire_sys(f) - p.epoch) < 0) {
+                    if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 5); break; }
+                }
+            }
+            __syncthreads();
+            const float inv = 1.0f / tot;
+            const int clo = k * p.chunk4, chi = min(P4, clo + p.chunk4);
+            const int per = (chi - clo + W - 1) / W, lo = clo + p.rank * per, hi = min(chi, lo + per);   // my 1/W of the chunk
+            if (p.mc_part != nullptr) {
+                // NVLS: the switch adds the W partials (multimem.ld_reduce) and replicates the finished piece into every θ
+                for (int i = lo + cb * blockDim.x + threadIdx.x; i < hi; i += GC * blockDim.x) {
+                    float4 acc = multimem_ld_reduce_f4(p.mc_part + (size_t)m * P + (size_t)i * 4);
+                    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+                    multimem_st_f4(p.mc_theta + (size_t)m * p.theta_stride + (size_t)i * 4, acc);
+                }
+            } else {
+                for (int i = lo + cb * blockDim.x + threadIdx.x; i < hi; i += GC * blockDim.x) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r < W) v[r] = ld_peer_f4(p.part[r] + (size_t)m * P + (size_t)i * 4);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r < W) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+                    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r < W) st_peer_f4(p.theta[r] + (size_t)m * p.theta_stride + (size_t)i * 4, acc);
+                }
+            }
         }
     }
-    // ---- everyone's partials + totals are in place
+    // ---- θ complete on every rank before anyone leaves (and before the next launch may overwrite the partial buffers)
     grid_barrier(p.grid_sync, p.grid_base + gridDim.x, p.spin_timeout_ns, p.error_flag);
-    peer_barrier(p, 0, p.epoch);
-    for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        float t = 0.f;
-        for (int r = 0; r < W; ++r) t += ld_relaxed_sys_f32(p.tot_inbox[p.rank] + r * M + m);
-        tot_s[m] = t;
-    }
-    __syncthreads();
-
-    // ---- phase 2: my slice of every model: pull from all peers, normalise, push to all peers
-    const int per = (P4 + W - 1) / W, lo = p.rank * per, hi = min(P4, lo + per);
-    for (int m = 0; m < M; ++m) {
-        const float tot = tot_s[m];
-        if (!(tot > 0.f)) continue;  // unused cluster: leave θ untouched everywhere
-        const float inv = 1.0f / tot;
-        if (p.mc_part != nullptr) {
-            // NVLS path: the switch adds the W partials (multimem.ld_reduce) and replicates the finished slice into
-            // every rank's θ (multimem.st): 1 load + 1 store per element instead of W + W
-            for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
-                float4 acc = multimem_ld_reduce_f4(p.mc_part + (size_t)m * P + (size_t)i * 4);
-                acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-                multimem_st_f4(p.mc_theta + (size_t)m * p.theta_stride + (size_t)i * 4, acc);
-            }
-            continue;
-        }
-        for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 v[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r < W) v[r] = ld_peer_f4(p.part[r] + (size_t)m * P + (size_t)i * 4);
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r < W) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
-            acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r < W) st_peer_f4(p.theta[r] + (size_t)m * p.theta_stride + (size_t)i * 4, acc);
-        }
-    }
-    // ---- θ complete on every rank before anyone leaves
-    grid_barrier(p.grid_sync, p.grid_base + 2 * gridDim.x, p.spin_timeout_ns, p.error_flag);
     peer_barrier(p, 1, p.epoch);
 }
 
-int fedavg_reduce_apply_peer_launch(const float* cp, const float* n, int C, int M, int P, int theta_stride, int world, int rank,
+int fedavg_reduce_apply_peer_launch(const float* cp, const int* cidx, const float* n, int C, int M, int P, int theta_stride, int world, int rank,
                                     const long long* part_ptrs, const long long* theta_ptrs, const long long* tot_ptrs,
-                                    const long long* flag_ptrs, long long mc_part, long long mc_theta, unsigned* grid_sync, unsigned epoch,
-                                    unsigned grid_base, int grid, long long timeout_ms, int* error_flag, cudaStream_t stream) {
-    if (world < 1 || world > 8 || (P & 3)) return -5;
+                                    const long long* flag_ptrs, long long mc_part, long long mc_theta, unsigned* grid_sync, unsigned* chunk_done,
+                                    int max_chunks, unsigned launch_idx, unsigned epoch, unsigned grid_base, int grid, long long timeout_ms,
+                                    int* error_flag, cudaStream_t stream) {
+    if (world < 1 || world > 8 || (P & 3) || grid < 2) return -5;
     PeerAggParams p{};
-    p.cp = cp; p.n = n; p.C = C; p.M = M; p.P = P; p.theta_stride = theta_stride; p.world = world; p.rank = rank;
+    p.cp = cp; p.cidx = cidx; p.n = n; p.C = C; p.M = M; p.P = P; p.theta_stride = theta_stride; p.world = world; p.rank = rank;
     for (int r = 0; r < world; ++r) {
         p.part[r] = reinterpret_cast<float*>(part_ptrs[r]);
         p.theta[r] = reinterpret_cast<float*>(theta_ptrs[r]);
@@ -200,6 +251,15 @@ int fedavg_reduce_apply_peer_launch(const float* cp, const float* n, int C, int 
     }
     p.mc_part = reinterpret_cast<float*>(mc_part); p.mc_theta = reinterpret_cast<float*>(mc_theta);
     p.grid_sync = grid_sync; p.epoch = epoch; p.grid_base = grid_base;
+    p.chunk_done = chunk_done; p.launch_idx = launch_idx;
+    // chunking: ~1 MB chunks, but never more than the flag slots that were allocated; the chunk length is a multiple of 4·W
+    // float4 so that every rank's share of a chunk is 64-byte aligned
+    const int P4 = P >> 2;
+    int chunk4 = 65536;
+    while ((long long)M * ((P4 + chunk4 - 1) / chunk4) > max_chunks) chunk4 *= 2;
+    p.chunk4 = chunk4;
+    // NVLink-side consumers need far fewer CTAs than the HBM-side producers
+    p.n_prod = std::max(1, grid - std::max(1, grid / 4));
     p.spin_timeout_ns = timeout_ms * 1000000LL; p.error_flag = error_flag;
     const int smem = (C + M + 8) * (int)sizeof(float);
     void* args[] = {&p};

@@ -181,22 +181,35 @@ Tensor robust_clip(Tensor rows, Tensor g, double bound, c10::optional<Tensor> ma
     return nrm;
 }
 
-int64_t fedavg_reduce_apply_peer(Tensor cp, Tensor n, int64_t P, int64_t theta_stride, int64_t world, int64_t rank,
+// cp: the client arena [C_arena, M, P]; cidx: int32 [C] arena rows of this rank's clients (or None: rows 0..C-1 of cp);
+// n: [C, M] weights of those clients; chunk_done: int32 [max_chunks] local counters; returns the grid size used
+int64_t fedavg_reduce_apply_peer(Tensor cp, c10::optional<Tensor> cidx, Tensor n, int64_t P, int64_t theta_stride, int64_t world, int64_t rank,
                                  std::vector<int64_t> part_ptrs, std::vector<int64_t> theta_ptrs, std::vector<int64_t> tot_ptrs,
-                                 std::vector<int64_t> flag_ptrs, Tensor grid_sync, int64_t epoch, int64_t grid_base, int64_t timeout_ms,
-                                 Tensor error_flag, int64_t mc_part, int64_t mc_theta) {
-    CHECK_CUDA_F32(cp); CHECK_CUDA_F32(n); CHECK_CUDA_I32(grid_sync); CHECK_CUDA_I32(error_flag);
+                                 std::vector<int64_t> flag_ptrs, Tensor grid_sync, Tensor chunk_done, int64_t launch_idx, int64_t epoch,
+                                 int64_t grid_base, int64_t timeout_ms, Tensor error_flag, int64_t mc_part, int64_t mc_theta) {
+    CHECK_CUDA_F32(cp); CHECK_CUDA_F32(n); CHECK_CUDA_I32(grid_sync); CHECK_CUDA_I32(error_flag); CHECK_CUDA_I32(chunk_done);
     c10::cuda::CUDAGuard guard(cp.device());
-    const int C = (int)cp.size(0), M = (int)cp.size(1);
-    TORCH_CHECK(cp.size(2) == P && cp.is_contiguous(), "cp must be contiguous [C, M, P]");
+    const int C = (int)n.size(0), M = (int)cp.size(1);
+    TORCH_CHECK(cp.dim() == 3 && cp.size(2) == P && cp.is_contiguous() && n.dim() == 2 && n.size(1) == M && n.is_contiguous(),
+                "cp must be contiguous [C_arena, M, P] and n contiguous [C, M]");
+    const int* ci = nullptr;
+    if (cidx.has_value() && cidx->defined()) {
+        CHECK_CUDA_I32(*cidx);
+        TORCH_CHECK(cidx->numel() == C && cidx->is_contiguous(), "cidx must hold one arena row per local client");
+        ci = cidx->data_ptr<int>();
+    } else {
+        TORCH_CHECK(cp.size(0) >= C, "cp has fewer rows than n");
+    }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cp.device().index());
     std::vector<long long> a(part_ptrs.begin(), part_ptrs.end()), b(theta_ptrs.begin(), theta_ptrs.end()),
         c(tot_ptrs.begin(), tot_ptrs.end()), d(flag_ptrs.begin(), flag_ptrs.end());
-    const int rc = fdb::fedavg_reduce_apply_peer_launch(cp.data_ptr<float>(), n.data_ptr<float>(), C, M, (int)P, (int)theta_stride, (int)world,
+    const int rc = fdb::fedavg_reduce_apply_peer_launch(cp.data_ptr<float>(), ci, n.data_ptr<float>(), C, M, (int)P, (int)theta_stride, (int)world,
                                                         (int)rank, a.data(), b.data(), c.data(), d.data(), (long long)mc_part, (long long)mc_theta,
-                                                        reinterpret_cast<unsigned*>(grid_sync.data_ptr<int>()), (unsigned)epoch,
-                                                        (unsigned)grid_base, sms, timeout_ms, error_flag.data_ptr<int>(), cur_stream());
+                                                        reinterpret_cast<unsigned*>(grid_sync.data_ptr<int>()),
+                                                        reinterpret_cast<unsigned*>(chunk_done.data_ptr<int>()), (int)chunk_done.numel(),
+                                                        (unsigned)launch_idx, (unsigned)epoch, (unsigned)grid_base, sms, timeout_ms,
+                                                        error_flag.data_ptr<int>(), cur_stream());
     CHECK_OK(rc, "fedavg_reduce_apply_peer");
     return sms;
 }

@@ -23,10 +23,11 @@ int gossip_mix_peer_launch(const long long* x_ptrs, const long long* flag_ptrs, 
 int robust_clip_launch(float* rows, const float* g, const unsigned char* mask, int R, long long P, float bound, float* scratch_nrm2,
                        float* nrm_out, float stddev, unsigned seed, cudaStream_t stream);
 // aggregate_peer.cu : multi-GPU reduce-scatter + apply + all-gather over NVLink peer memory (cooperative launch)
-int fedavg_reduce_apply_peer_launch(const float* cp, const float* n, int C, int M, int P, int theta_stride, int world, int rank,
+int fedavg_reduce_apply_peer_launch(const float* cp, const int* cidx, const float* n, int C, int M, int P, int theta_stride, int world, int rank,
                                     const long long* part_ptrs, const long long* theta_ptrs, const long long* tot_ptrs,
-                                    const long long* flag_ptrs, long long mc_part, long long mc_theta, unsigned* grid_sync, unsigned epoch,
-                                    unsigned grid_base, int grid, long long timeout_ms, int* error_flag, cudaStream_t stream);
+                                    const long long* flag_ptrs, long long mc_part, long long mc_theta, unsigned* grid_sync, unsigned* chunk_done,
+                                    int max_chunks, unsigned launch_idx, unsigned epoch, unsigned grid_base, int grid, long long timeout_ms,
+                                    int* error_flag, cudaStream_t stream);
 // eval.cu
 int eval_logits_launch(const float* logits, const int* target, int B, int K, float* acc3, cudaStream_t stream);
 int aue_sqerr_launch(const float* logits, const int* target, int B, int K, float* out1, cudaStream_t stream);

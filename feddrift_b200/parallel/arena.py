@@ -66,6 +66,17 @@ class ModelBank:
         for _, _, dt, off, n in self.spec:
             self.float_mask[off:off + n] = bool(dt.is_floating_point)
 
+    def rebind_storage(self, storage: torch.Tensor) -> None:
+        """Move the bank onto ``storage`` ([num_models, ≥ P] fp32, e.g. the symmetric-memory θ buffer of the peer
+        aggregation kernel): current values are copied once, afterwards rows written by the kernel ARE the bank — no
+        per-round ``theta.copy_``.  Cached bank-bound modules are dropped (their parameters were views of the old rows)."""
+        assert storage.shape[0] == self.num_models and storage.shape[1] >= self.P and storage.dtype == torch.float32
+        storage[:, : self.P].copy_(self.theta)
+        self.storage = storage
+        self.stride = int(storage.stride(0))
+        self.theta = storage[:, : self.P] if storage.shape[1] != self.P else storage
+        self._modules = {}
+
     # -- state_dict interop ---------------------------------------------------------------
     def state_dict(self, m: int) -> "OrderedDict[str, torch.Tensor]":
         return mutils.unflatten_to_state_dict(self.theta[m], self.spec)

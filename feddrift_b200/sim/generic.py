@@ -133,6 +133,9 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
     if _world_rank(sim)[0] > 1:   # cold path: every rank evaluated only its own clients
         import torch.distributed as dist
         dist.all_reduce(metrics)
+        pa = getattr(sim, "_peer_agg", None)
+        if pa is not None:
+            pa.check()   # a peer that never flagged its chunks: raise instead of training on a partial aggregate
     counts = torch.stack([data.nsamp[t], data.nsamp[t + 1] if t + 1 < T1 else torch.zeros_like(data.nsamp[t])], 1).float()
     return {"metrics": metrics, "counts": counts}
 
@@ -146,14 +149,21 @@ def _world_rank(sim):
 
 def _peer_aggregate(sim, world, rank):
     """Multi-GPU aggregation + broadcast of the cluster models in ONE kernel over NVLink peer memory
-    (``parallel/peer_aggregate.py``): this rank contributes the rows of its own clients."""
+    (``parallel/peer_aggregate.py``): this rank contributes the rows of its own clients, read IN PLACE from the client arena
+    (no gather / pad copies), and the model bank lives in the kernel's symmetric θ buffer (no copy back)."""
     from ..parallel.peer_aggregate import PeerAggregator
     pa = getattr(sim, "_peer_agg", None)
     if pa is None:
         pa = sim._peer_agg = PeerAggregator(sim.M, sim.bank.P, sim.device, sim.bank.theta)
-    mine = [c for c in range(sim.C) if c % world == rank]
-    theta = pa.aggregate(sim.clients.params[mine], sim.clients.n[mine])
-    sim.bank.theta.copy_(theta)
+        if pa.world > 1:
+            sim.bank.rebind_storage(pa.theta_full)          # the kernel's all-gather target IS the bank from now on
+            sim.evaluator.bank = sim.bank
+        mine = [c for c in range(sim.C) if c % world == rank]
+        sim._peer_mine = (mine, torch.tensor(mine, dtype=torch.int32, device=sim.device))
+    mine, cidx = sim._peer_mine
+    pa.aggregate(sim.clients.params, sim.clients.n[mine], cidx)
+    if sim.bank.theta.data_ptr() != pa.theta.data_ptr():    # world == 1 fallback / unpadded rows: plain copy
+        sim.bank.theta.copy_(pa.theta)
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:

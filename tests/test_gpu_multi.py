@@ -68,7 +68,7 @@ from feddrift_b200.ops import reference as ref
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-M, P, C = 3, 100003, 6
+M, P, C = 3, 300004, 6   # > 1 chunk per model (chunks are 2^16 float4)
 g = torch.Generator().manual_seed(0)
 cp_all = torch.randn(C, M, P, generator=g)
 n_all = torch.randint(0, 4, (C, M), generator=g).float()
@@ -77,8 +77,13 @@ theta0 = torch.randn(M, P, generator=g)
 mine = [c for c in range(C) if c % world == rank]
 agg = PeerAggregator(M, P, f"cuda:{rank}", theta0.cuda())
 ok = True
+arena = cp_all.cuda()
+cidx = torch.tensor(mine, dtype=torch.int32, device="cuda")
 for it in range(3):
-    th = agg.aggregate(cp_all[mine].cuda() + it, n_all[mine].cuda())
+    if it == 1:   # in-place form: the whole client arena + the list of this rank's rows (what the engine uses)
+        th = agg.aggregate(arena + it, n_all[mine].cuda(), cidx)
+    else:
+        th = agg.aggregate(cp_all[mine].cuda() + it, n_all[mine].cuda())
     torch.cuda.synchronize()
     agg.check()
     want = theta0.clone()

@@ -19,6 +19,10 @@ dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+from bench import ClockSampler  # noqa: E402
+clk = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+clk.start()
+rows_out = []
 CONFIGS = [("resnet18_2clusters_32clients", 2, 11_699_132, 32), ("cnn_4clusters_64clients", 4, 1_199_882, 64),
            ("charlstm_2clusters_128clients", 2, 822_570, 128)]
 
@@ -68,11 +72,15 @@ for name, M, P, C in CONFIGS:
     ms_nccl = timed(nccl_path)
     wire = (world - 1) / world * M * P4 * 4
     if rank == 0:
-        print(json.dumps({"config": name, "world": world, "fused_ms": ms, "nvls": nvls, "fused_p2p_ms": ms_p2p, "nccl_path_ms": ms_nccl,
+        rows_out.append({"config": name, "world": world, "fused_ms": ms, "nvls": nvls, "fused_p2p_ms": ms_p2p, "nccl_path_ms": ms_nccl,
                           "local_hbm_bytes": Cl * M * P4 * 4, "nvlink_bytes_each_way": wire,
                           "nvlink_GBps_each_way": wire / ms / 1e6 if world > 1 else None,
-                          "frac_of_770GBps": (wire / ms / 1e6) / 770.0 if world > 1 else None}))
+                          "frac_of_770GBps": (wire / ms / 1e6) / 770.0 if world > 1 else None})
     del cp, agg, theta
     torch.cuda.empty_cache()
+clocks = clk.stop()
+for r_ in rows_out:
+    r_["clocks"] = clocks
+    print(json.dumps(r_))
 if world > 1:
     dist.destroy_process_group()

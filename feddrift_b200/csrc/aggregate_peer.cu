@@ -252,14 +252,20 @@ int fedavg_reduce_apply_peer_launch(const float* cp, const int* cidx, const floa
     p.mc_part = reinterpret_cast<float*>(mc_part); p.mc_theta = reinterpret_cast<float*>(mc_theta);
     p.grid_sync = grid_sync; p.epoch = epoch; p.grid_base = grid_base;
     p.chunk_done = chunk_done; p.launch_idx = launch_idx;
-    // chunking: ~1 MB chunks, but never more than the flag slots that were allocated; the chunk length is a multiple of 4·W
-    // float4 so that every rank's share of a chunk is 64-byte aligned
+    // split the grid between the HBM-side producers and the NVLink-side consumers in proportion to the two streams' ideal
+    // times (local rows at ~6.4 TB/s vs (W-1)/W of the models each way at ~0.77 TB/s); NVLink saturates with few CTAs
+    {
+        const double t_hbm = (double)C * M * P * 4.0 / 6.4e12, t_nv = (double)(world - 1) / world * M * P * 4.0 / 0.77e12;
+        int n_cons = (int)(grid * t_nv / (t_hbm + t_nv + 1e-12));
+        n_cons = std::min(std::max(n_cons, 8), std::min(48, grid - 1));
+        p.n_prod = grid - n_cons;
+    }
+    // chunking: every producer thread streams 8 float4 columns per chunk (a chunk barrier costs a fence + an atomic, so
+    // chunks must be coarse enough to amortise it: ~7 MB of partial sums on 148 SMs), capped by the allocated flag slots
     const int P4 = P >> 2;
-    int chunk4 = 65536;
+    int chunk4 = p.n_prod * 512 * 8;
     while ((long long)M * ((P4 + chunk4 - 1) / chunk4) > max_chunks) chunk4 *= 2;
     p.chunk4 = chunk4;
-    // NVLink-side consumers need far fewer CTAs than the HBM-side producers
-    p.n_prod = std::max(1, grid - std::max(1, grid / 4));
     p.spin_timeout_ns = timeout_ms * 1000000LL; p.error_flag = error_flag;
     const int smem = (C + M + 8) * (int)sizeof(float);
     void* args[] = {&p};

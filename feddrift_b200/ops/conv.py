@@ -147,11 +147,23 @@ class TcConv2d(nn.Module):
         return (x.is_cuda and x.dim() == 4 and self.groups == 1 and self.dilation == (1, 1) and k % 8 == 0 and k >= 64
                 and self.out_channels % 8 == 0 and self.out_channels >= 16 and _ext.available())
 
-    def forward(self, x):
-        relu = self.activation == "relu"
-        if (x.is_cuda and x.dim() == 4 and _ext.available() and os.environ.get("FDB_CONV_IM2COL") != "1"
+    def _use_igemm(self, x: torch.Tensor) -> bool:
+        if not (x.is_cuda and x.dim() == 4 and _ext.available() and os.environ.get("FDB_CONV_IM2COL") != "1"
                 and os.environ.get("FDB_NO_TC_CONV") != "1" and hasattr(_ext.load(), "conv_igemm_fwd")
                 and igemm_eligible(self.in_channels, self.out_channels, self.stride, self.dilation, self.groups)):
+            return False
+        # FDB_CONV_POLICY: "igemm" = every eligible layer on the hand-written kernels (default); "auto" = leave layers with
+        # fewer than 2048 output pixels to the library (a 128-pixel-row tile grid cannot fill 148 SMs there; measured
+        # in profiles/conv_probe_r2.jsonl the deep 7×7 / 4×4 stages are 1.5–2.6× slower than cuDNN)
+        if os.environ.get("FDB_CONV_POLICY", "igemm") == "auto":
+            ho = (x.shape[2] + 2 * self.padding[0] - self.kernel_size[0]) // self.stride[0] + 1
+            wo = (x.shape[3] + 2 * self.padding[1] - self.kernel_size[1]) // self.stride[1] + 1
+            return x.shape[0] * ho * wo >= 2048
+        return True
+
+    def forward(self, x):
+        relu = self.activation == "relu"
+        if self._use_igemm(x):
             return _ConvIgemmFn.apply(x, self.weight, self.bias, self.stride, self.padding, relu)
         if self._eligible(x) and os.environ.get("FDB_CONV_IM2COL") == "1":
             return _TcConvFn.apply(x, self.weight, self.bias, self.stride, self.padding, relu)

@@ -206,26 +206,43 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
             const int clo = k * p.chunk4, chi = min(P4, clo + p.chunk4);
             const int per = (chi - clo + W - 1) / W, lo = clo + p.rank * per, hi = min(chi, lo + per);   // my 1/W of the chunk
             if (p.mc_part != nullptr) {
-                // NVLS: the switch adds the W partials (multimem.ld_reduce) and replicates the finished piece into every θ
-                for (int i = lo + cb * blockDim.x + threadIdx.x; i < hi; i += GC * blockDim.x) {
-                    float4 acc = multimem_ld_reduce_f4(p.mc_part + (size_t)m * P + (size_t)i * 4);
-                    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
-                    multimem_st_f4(p.mc_theta + (size_t)m * p.theta_stride + (size_t)i * 4, acc);
+                // NVLS: the switch adds the W partials (multimem.ld_reduce) and replicates the finished piece into every θ.
+                // A multimem round trip is several µs: 4 independent reductions in flight per thread keep the links busy
+                const int stride = GC * blockDim.x;
+                for (int i0 = lo + cb * blockDim.x + threadIdx.x; i0 < hi; i0 += 4 * stride) {
+                    float4 acc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u * stride < hi) acc[u] = multimem_ld_reduce_f4(p.mc_part + (size_t)m * P + (size_t)(i0 + u * stride) * 4);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u * stride < hi) {
+                            acc[u].x *= inv; acc[u].y *= inv; acc[u].z *= inv; acc[u].w *= inv;
+                            multimem_st_f4(p.mc_theta + (size_t)m * p.theta_stride + (size_t)(i0 + u * stride) * 4, acc[u]);
+                        }
                 }
             } else {
-                for (int i = lo + cb * blockDim.x + threadIdx.x; i < hi; i += GC * blockDim.x) {
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 v[8];
+                const int stride = GC * blockDim.x;
+                for (int i0 = lo + cb * blockDim.x + threadIdx.x; i0 < hi; i0 += 2 * stride) {
+                    float4 acc[2];
+                    float4 v[2][8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        if (r < W) v[r] = ld_peer_f4(p.part[r] + (size_t)m * P + (size_t)i * 4);
+                    for (int u = 0; u < 2; ++u)
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        if (r < W) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
-                    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+                        for (int r = 0; r < 8; ++r)
+                            if (r < W && i0 + u * stride < hi) v[u][r] = ld_peer_f4(p.part[r] + (size_t)m * P + (size_t)(i0 + u * stride) * 4);
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        if (r < W) st_peer_f4(p.theta[r] + (size_t)m * p.theta_stride + (size_t)i * 4, acc);
+                    for (int u = 0; u < 2; ++u) {
+                        if (i0 + u * stride >= hi) continue;
+                        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (r < W) { acc[u].x += v[u][r].x; acc[u].y += v[u][r].y; acc[u].z += v[u][r].z; acc[u].w += v[u][r].w; }
+                        acc[u].x *= inv; acc[u].y *= inv; acc[u].z *= inv; acc[u].w *= inv;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r)
+                            if (r < W) st_peer_f4(p.theta[r] + (size_t)m * p.theta_stride + (size_t)(i0 + u * stride) * 4, acc[u]);
+                    }
                 }
             }
         }
@@ -257,13 +274,13 @@ int fedavg_reduce_apply_peer_launch(const float* cp, const int* cidx, const floa
     {
         const double t_hbm = (double)C * M * P * 4.0 / 6.4e12, t_nv = (double)(world - 1) / world * M * P * 4.0 / 0.77e12;
         int n_cons = (int)(grid * t_nv / (t_hbm + t_nv + 1e-12));
-        n_cons = std::min(std::max(n_cons, 8), std::min(48, grid - 1));
+        n_cons = std::min(std::max(n_cons, 8), std::min(96, grid - 16));
         p.n_prod = grid - n_cons;
     }
     // chunking: every producer thread streams 8 float4 columns per chunk (a chunk barrier costs a fence + an atomic, so
     // chunks must be coarse enough to amortise it: ~7 MB of partial sums on 148 SMs), capped by the allocated flag slots
     const int P4 = P >> 2;
-    int chunk4 = p.n_prod * 512 * 8;
+    int chunk4 = std::max(p.n_prod * 512 * 8, world * (grid - p.n_prod) * 512 * 4);   // ≥ 4 float4 per consumer thread too
     while ((long long)M * ((P4 + chunk4 - 1) / chunk4) > max_chunks) chunk4 *= 2;
     p.chunk4 = chunk4;
     p.spin_timeout_ns = timeout_ms * 1000000LL; p.error_flag = error_flag;

@@ -1,11 +1,11 @@
 // fedavg_reduce_apply_peer — the multi-GPU per-cluster FedAvg aggregation + broadcast as ONE kernel per rank, with the
 // collective done by the kernel itself over NVLink peer memory (no NCCL), PIPELINED chunk by chunk:
 //
-//   producer CTAs   stream the local clients' rows IN PLACE from the client arena (row list `cidx`, no gather copy) and
+//   producer warps  (12 of the 16 warps of EVERY CTA) stream the local clients' rows IN PLACE from the client arena (row list `cidx`, no gather copy) and
 //                   write un-normalised partial sums part_g[m, chunk] = Σ_{c on g} n[c,m]·θ_c[m, chunk]   (HBM-bound, like K1);
-//                   the last producer CTA to finish a chunk publishes a per-chunk epoch flag to every peer
+//                   the last CTA to finish a chunk publishes a per-chunk epoch flag to every peer
 //                   (fence.sys + st.release.sys);
-//   consumer CTAs   run concurrently: as soon as chunk k is flagged by ALL ranks they reduce-scatter + normalise +
+//   consumer warps  (the other 4 warps of every CTA) run concurrently: as soon as chunk k is flagged by ALL ranks they reduce-scatter + normalise +
 //                   all-gather it: rank g owns 1/W of the chunk, pulls it from every peer's partial buffer (128-bit peer
 //                   loads, or ONE multimem.ld_reduce = in-switch add when the buffer has an NVLS multicast mapping),
 //                   divides by the global weight total and pushes the finished piece into EVERY rank's θ buffer
@@ -100,29 +100,30 @@ FDB_DEVICE void multimem_st_f4(float* mc_ptr, float4 v) {
                  : "memory");
 }
 
+constexpr int kAggProd = 384, kAggCons = 128;   // per-CTA warp roles: 12 producer warps (HBM stream) + 4 consumer warps (NVLink)
+
+FDB_DEVICE void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __grid_constant__ PeerAggParams p) {
     extern __shared__ float wsm[];  // [C] local weights of the current model, then [M] totals
-    __shared__ float red[32];
     const int C = p.C, M = p.M, P = p.P, W = p.world;
     const int P4 = P >> 2;  // host guarantees P % 4 == 0 (rows are padded)
     float* tot_s = wsm + C;
-    const int GP = p.n_prod, GC = (int)gridDim.x - GP;
+    const int G = (int)gridDim.x;
     const int cpm = (P4 + p.chunk4 - 1) / p.chunk4, nchunks = M * cpm;
+    const int tid = threadIdx.x;
 
-    if ((int)blockIdx.x < GP) {
-        // ================================================================ producers
-        if (blockIdx.x == 0) {
-            // local weight totals → every peer's inbox, published with the slot-0 flag
+    if (tid < kAggProd) {
+        // ================================================================ producers (every CTA: the HBM stream uses all SMs)
+        if (blockIdx.x == 0 && tid == 0) {
+            // local weight totals → every peer's inbox, published with the slot-0 flag (C·M scalars: serial is fine)
             for (int m = 0; m < M; ++m) {
-                float part = 0.f;
-                for (int c = threadIdx.x; c < C; c += blockDim.x) part += p.n[c * M + m];
-                const float tot = block_sum(part, red);
-                if (threadIdx.x == 0)
-                    for (int r = 0; r < W; ++r) st_relaxed_sys_f32(p.tot_inbox[r] + p.rank * M + m, tot);
+                float tot = 0.f;
+                for (int c = 0; c < C; ++c) tot += p.n[c * M + m];
+                for (int r = 0; r < W; ++r) st_relaxed_sys_f32(p.tot_inbox[r] + p.rank * M + m, tot);
             }
             __threadfence_system();
-            __syncthreads();
-            if ((int)threadIdx.x < W) st_release_sys(p.flags[threadIdx.x] + 0 * W + p.rank, p.epoch);
+            for (int r = 0; r < W; ++r) st_release_sys(p.flags[r] + 0 * W + p.rank, p.epoch);
         }
         float* mine = p.part[p.rank];
         int cur_m = -1;
@@ -130,14 +131,14 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
         for (int ck = 0; ck < nchunks; ++ck) {
             const int m = ck / cpm, k = ck - m * cpm;
             if (m != cur_m) {
-                __syncthreads();
-                for (int c = threadIdx.x; c < C; c += blockDim.x) wsm[c] = p.n[c * M + m];
-                __syncthreads();
+                named_bar(1, kAggProd);
+                for (int c = tid; c < C; c += kAggProd) wsm[c] = p.n[c * M + m];
+                named_bar(1, kAggProd);
                 cur_m = m;
             }
             const int lo = k * p.chunk4, hi = min(P4, lo + p.chunk4);
             const float* base = p.cp + (size_t)m * P;
-            for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += GP * blockDim.x) {
+            for (int i = lo + blockIdx.x * kAggProd + tid; i < hi; i += G * kAggProd) {
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 int c = 0;
                 for (; c + 4 <= C; c += 4) {
@@ -162,54 +163,55 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
                 }
                 reinterpret_cast<float4*>(mine + (size_t)m * P)[i] = acc;
             }
-            // chunk complete on this CTA; the LAST producer CTA publishes the chunk to every peer
+            // chunk complete on this CTA; the LAST CTA to finish it publishes the chunk to every peer
             __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) {
+            named_bar(1, kAggProd);
+            if (tid == 0) {
                 const unsigned old = atomicAdd(p.chunk_done + ck, 1u);
-                if (old == p.launch_idx * (unsigned)GP + (unsigned)GP - 1u) {
+                if (old == p.launch_idx * (unsigned)G + (unsigned)G - 1u) {
                     __threadfence_system();
                     for (int r = 0; r < W; ++r) st_release_sys(p.flags[r] + (2 + ck) * W + p.rank, p.epoch);
                 }
             }
         }
     } else {
-        // ================================================================ consumers
-        const int cb = (int)blockIdx.x - GP;
-        if ((int)threadIdx.x < W) {   // weight totals of every rank
-            const unsigned* f = p.flags[p.rank] + 0 * W + threadIdx.x;
+        // ================================================================ consumers (4 warps of every CTA: NVLink has few bytes
+        //                                                                  in flight per SM, it needs breadth, not SM-exclusive CTAs)
+        const int ct = tid - kAggProd;
+        if (ct < W) {   // weight totals of every rank
+            const unsigned* f = p.flags[p.rank] + 0 * W + ct;
             const long long t0 = globaltimer_ns();
             while ((int)(ld_acquire_sys(f) - p.epoch) < 0) {
                 if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 4); break; }
             }
         }
-        __syncthreads();
-        for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        named_bar(2, kAggCons);
+        for (int m = ct; m < M; m += kAggCons) {
             float t = 0.f;
             for (int r = 0; r < W; ++r) t += ld_relaxed_sys_f32(p.tot_inbox[p.rank] + r * M + m);
             tot_s[m] = t;
         }
-        __syncthreads();
+        named_bar(2, kAggCons);
+        const int stride = G * kAggCons;
         for (int ck = 0; ck < nchunks; ++ck) {
             const int m = ck / cpm, k = ck - m * cpm;
             const float tot = tot_s[m];
-            if (!(tot > 0.f)) continue;       // unused cluster: leave θ untouched everywhere (block-uniform)
-            if ((int)threadIdx.x < W) {       // chunk k of EVERY rank's partial buffer is complete
-                const unsigned* f = p.flags[p.rank] + (2 + ck) * W + threadIdx.x;
+            if (!(tot > 0.f)) continue;       // unused cluster: leave θ untouched everywhere (uniform)
+            if (ct < W) {                     // chunk k of EVERY rank's partial buffer is complete
+                const unsigned* f = p.flags[p.rank] + (2 + ck) * W + ct;
                 const long long t0 = globaltimer_ns();
                 while ((int)(ld_acquire_sys(f) - p.epoch) < 0) {
                     if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 5); break; }
                 }
             }
-            __syncthreads();
+            named_bar(2, kAggCons);
             const float inv = 1.0f / tot;
             const int clo = k * p.chunk4, chi = min(P4, clo + p.chunk4);
             const int per = (chi - clo + W - 1) / W, lo = clo + p.rank * per, hi = min(chi, lo + per);   // my 1/W of the chunk
             if (p.mc_part != nullptr) {
                 // NVLS: the switch adds the W partials (multimem.ld_reduce) and replicates the finished piece into every θ.
                 // A multimem round trip is several µs: 4 independent reductions in flight per thread keep the links busy
-                const int stride = GC * blockDim.x;
-                for (int i0 = lo + cb * blockDim.x + threadIdx.x; i0 < hi; i0 += 4 * stride) {
+                for (int i0 = lo + blockIdx.x * kAggCons + ct; i0 < hi; i0 += 4 * stride) {
                     float4 acc[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
@@ -222,8 +224,7 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
                         }
                 }
             } else {
-                const int stride = GC * blockDim.x;
-                for (int i0 = lo + cb * blockDim.x + threadIdx.x; i0 < hi; i0 += 2 * stride) {
+                for (int i0 = lo + blockIdx.x * kAggCons + ct; i0 < hi; i0 += 2 * stride) {
                     float4 acc[2];
                     float4 v[2][8];
 #pragma unroll
@@ -269,18 +270,11 @@ int fedavg_reduce_apply_peer_launch(const float* cp, const int* cidx, const floa
     p.mc_part = reinterpret_cast<float*>(mc_part); p.mc_theta = reinterpret_cast<float*>(mc_theta);
     p.grid_sync = grid_sync; p.epoch = epoch; p.grid_base = grid_base;
     p.chunk_done = chunk_done; p.launch_idx = launch_idx;
-    // split the grid between the HBM-side producers and the NVLink-side consumers in proportion to the two streams' ideal
-    // times (local rows at ~6.4 TB/s vs (W-1)/W of the models each way at ~0.77 TB/s); NVLink saturates with few CTAs
-    {
-        const double t_hbm = (double)C * M * P * 4.0 / 6.4e12, t_nv = (double)(world - 1) / world * M * P * 4.0 / 0.77e12;
-        int n_cons = (int)(grid * t_nv / (t_hbm + t_nv + 1e-12));
-        n_cons = std::min(std::max(n_cons, 8), std::min(96, grid - 16));
-        p.n_prod = grid - n_cons;
-    }
-    // chunking: every producer thread streams 8 float4 columns per chunk (a chunk barrier costs a fence + an atomic, so
-    // chunks must be coarse enough to amortise it: ~7 MB of partial sums on 148 SMs), capped by the allocated flag slots
+    // every CTA hosts both roles; chunks: each producer thread streams 6 float4 columns per chunk (a chunk barrier costs a
+    // fence + an atomic, chunks must amortise it: ~5 MB of partial sums on 148 SMs), capped by the allocated flag slots
+    p.n_prod = grid;
     const int P4 = P >> 2;
-    int chunk4 = std::max(p.n_prod * 512 * 8, world * (grid - p.n_prod) * 512 * 4);   // ≥ 4 float4 per consumer thread too
+    int chunk4 = grid * 384 * 6;
     while ((long long)M * ((P4 + chunk4 - 1) / chunk4) > max_chunks) chunk4 *= 2;
     p.chunk4 = chunk4;
     p.spin_timeout_ns = timeout_ms * 1000000LL; p.error_flag = error_flag;

@@ -138,30 +138,39 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
             }
             const int lo = k * p.chunk4, hi = min(P4, lo + p.chunk4);
             const float* base = p.cp + (size_t)m * P;
-            for (int i = lo + blockIdx.x * kAggProd + tid; i < hi; i += G * kAggProd) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            // two column groups per iteration × 4 client rows each = 8 independent 16-byte streaming loads in flight per thread
+            const int cstep = G * kAggProd;
+            for (int i = lo + blockIdx.x * kAggProd + tid; i < hi; i += 2 * cstep) {
+                const bool two = i + cstep < hi;
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
                 int c = 0;
                 for (; c + 4 <= C; c += 4) {
-                    float4 v[4];
+                    float4 v0[4], v1[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int row = p.cidx ? p.cidx[c + u] : c + u;
-                        v[u] = __ldcs(reinterpret_cast<const float4*>(base + (size_t)row * cstride) + i);
+                        const float4* src = reinterpret_cast<const float4*>(base + (size_t)row * cstride);
+                        v0[u] = __ldcs(src + i);
+                        v1[u] = two ? __ldcs(src + i + cstep) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float w = wsm[c + u];
-                        acc.x = fmaf(v[u].x, w, acc.x); acc.y = fmaf(v[u].y, w, acc.y);
-                        acc.z = fmaf(v[u].z, w, acc.z); acc.w = fmaf(v[u].w, w, acc.w);
+                        a0.x = fmaf(v0[u].x, w, a0.x); a0.y = fmaf(v0[u].y, w, a0.y); a0.z = fmaf(v0[u].z, w, a0.z); a0.w = fmaf(v0[u].w, w, a0.w);
+                        a1.x = fmaf(v1[u].x, w, a1.x); a1.y = fmaf(v1[u].y, w, a1.y); a1.z = fmaf(v1[u].z, w, a1.z); a1.w = fmaf(v1[u].w, w, a1.w);
                     }
                 }
                 for (; c < C; ++c) {
                     const int row = p.cidx ? p.cidx[c] : c;
-                    const float4 v = __ldcs(reinterpret_cast<const float4*>(base + (size_t)row * cstride) + i);
+                    const float4* src = reinterpret_cast<const float4*>(base + (size_t)row * cstride);
+                    const float4 v0 = __ldcs(src + i);
+                    const float4 v1 = two ? __ldcs(src + i + cstep) : make_float4(0.f, 0.f, 0.f, 0.f);
                     const float w = wsm[c];
-                    acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+                    a0.x = fmaf(v0.x, w, a0.x); a0.y = fmaf(v0.y, w, a0.y); a0.z = fmaf(v0.z, w, a0.z); a0.w = fmaf(v0.w, w, a0.w);
+                    a1.x = fmaf(v1.x, w, a1.x); a1.y = fmaf(v1.y, w, a1.y); a1.z = fmaf(v1.z, w, a1.z); a1.w = fmaf(v1.w, w, a1.w);
                 }
-                reinterpret_cast<float4*>(mine + (size_t)m * P)[i] = acc;
+                reinterpret_cast<float4*>(mine + (size_t)m * P)[i] = a0;
+                if (two) reinterpret_cast<float4*>(mine + (size_t)m * P)[i + cstep] = a1;
             }
             // chunk complete on this CTA; the LAST CTA to finish it publishes the chunk to every peer
             __threadfence();

@@ -647,6 +647,67 @@ Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t strid
     return dw;
 }
 
+// ---- TMA-im2col path (gemm_tc.cu): bf16 NHWC operands, the GEMM mainloop's producer fetches im2col boxes with the TMA unit
+Tensor conv_cast_bf16(Tensor x, c10::optional<Tensor> gate) {
+    CHECK_CUDA_F32(x);
+    TORCH_CHECK(x.is_contiguous(), "conv_cast_bf16: contiguous input");
+    c10::cuda::CUDAGuard guard(x.device());
+    auto out = torch::empty(x.sizes(), x.options().dtype(torch::kBFloat16));
+    const float* g = nullptr;
+    if (gate.has_value() && gate->defined()) {
+        CHECK_CUDA_F32((*gate));
+        TORCH_CHECK(gate->is_contiguous() && gate->numel() == x.numel(), "conv_cast_bf16: gate shape");
+        g = gate->data_ptr<float>();
+    }
+    CHECK_OK(fdb::conv_cast_bf16_launch(x.data_ptr<float>(), g, out.data_ptr(), x.numel(), cur_stream()), "conv_cast_bf16");
+    return out;
+}
+// xb: bf16 NHWC [N, H, W, C]; wq: packed bf16 [Cout][R][S][C]; -> fp32 NHWC [N, P, Q, Cout].  flip = taps of wq in reverse order
+// (stride-1 data gradient: xb = dY, wq = the [Cin][R][S][Cout] pack, pad = R - 1 - pad_fwd)
+Tensor conv_tma_fwd(Tensor xb, Tensor wq, c10::optional<Tensor> bias, int64_t stride, int64_t pad, bool relu, bool flip) {
+    TORCH_CHECK(xb.is_cuda() && xb.scalar_type() == torch::kBFloat16 && xb.dim() == 4 && xb.is_contiguous(), "conv_tma_fwd: xb must be contiguous bf16 NHWC");
+    TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kBFloat16 && wq.dim() == 4 && wq.is_contiguous(), "conv_tma_fwd: wq must be packed bf16 [K,R,S,C]");
+    const int N = (int)xb.size(0), H = (int)xb.size(1), W = (int)xb.size(2), C = (int)xb.size(3);
+    const int K = (int)wq.size(0), R = (int)wq.size(1), S = (int)wq.size(2);
+    TORCH_CHECK(wq.size(3) == C && C % 64 == 0 && K % 8 == 0 && R == S, "conv_tma_fwd: needs Cin % 64 == 0, Cout % 8 == 0, square filter");
+    const int P = (H + 2 * (int)pad - R) / (int)stride + 1, Q = (W + 2 * (int)pad - S) / (int)stride + 1;
+    TORCH_CHECK(P > 0 && Q > 0 && pad >= 0 && pad < 128 && stride >= 1 && stride <= 8, "conv_tma_fwd: geometry");
+    c10::cuda::CUDAGuard guard(xb.device());
+    auto y = torch::empty({N, P, Q, K}, xb.options().dtype(torch::kFloat32));
+    Tensor bias_f;
+    const float* bp = nullptr;
+    if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
+    CHECK_OK(fdb::conv_tma_fwd_launch(xb.data_ptr(), wq.data_ptr(), y.data_ptr<float>(), bp, N, H, W, C, K, R, S, P, Q, (int)pad, (int)stride,
+                                      flip ? 1 : 0, relu ? 1 : 0, cur_stream()), "conv_tma_fwd (tcgen05 + TMA im2col)");
+    return y;
+}
+// xb: bf16 NHWC [N, H, W, C]; dyb: bf16 NHWC [N, P, Q, K]; -> dW fp32 OIHW (added into `accum_into` when given)
+Tensor conv_tma_wgrad(Tensor xb, Tensor dyb, int64_t R, int64_t S, int64_t stride, int64_t pad, c10::optional<Tensor> accum_into) {
+    TORCH_CHECK(xb.is_cuda() && xb.scalar_type() == torch::kBFloat16 && xb.dim() == 4 && xb.is_contiguous(), "conv_tma_wgrad: xb must be contiguous bf16 NHWC");
+    TORCH_CHECK(dyb.is_cuda() && dyb.scalar_type() == torch::kBFloat16 && dyb.dim() == 4 && dyb.is_contiguous(), "conv_tma_wgrad: dyb must be contiguous bf16 NHWC");
+    const int N = (int)xb.size(0), H = (int)xb.size(1), W = (int)xb.size(2), C = (int)xb.size(3);
+    const int P = (int)dyb.size(1), Q = (int)dyb.size(2), K = (int)dyb.size(3);
+    TORCH_CHECK(C % 64 == 0 && K % 8 == 0 && R == S && dyb.size(0) == N, "conv_tma_wgrad: needs Cin % 64 == 0, Cout % 8 == 0, square filter");
+    c10::cuda::CUDAGuard guard(xb.device());
+    auto o = xb.options().dtype(torch::kFloat32);
+    auto tmp = torch::empty({K, R, S, C}, o);
+    cudaMemsetAsync(tmp.data_ptr<float>(), 0, (size_t)tmp.numel() * sizeof(float), cur_stream());
+    CHECK_OK(fdb::conv_tma_wgrad_launch(xb.data_ptr(), dyb.data_ptr(), tmp.data_ptr<float>(), N, H, W, C, K, (int)R, (int)S, P, Q, (int)pad,
+                                        (int)stride, cur_stream()), "conv_tma_wgrad (tcgen05 + TMA im2col)");
+    Tensor dw;
+    int accumulate = 0;
+    if (accum_into.has_value() && accum_into->defined()) {
+        dw = *accum_into;
+        CHECK_CUDA_F32(dw);
+        TORCH_CHECK(dw.is_contiguous() && dw.numel() == (int64_t)K * C * R * S, "conv_tma_wgrad: accum_into must be a contiguous OIHW buffer");
+        accumulate = 1;
+    } else {
+        dw = torch::empty({K, C, R, S}, o);
+    }
+    CHECK_OK(fdb::conv_ohwi_to_oihw_launch(tmp.data_ptr<float>(), dw.data_ptr<float>(), K, C, (int)(R * S), accumulate, cur_stream()), "conv_ohwi_to_oihw");
+    return dw;
+}
+
 // bias / W_ih1 / embedding gradients of every chunk from the gate-gradient histories (lstm_tc.cu::lstm_small_grads_kernel)
 std::vector<Tensor> lstm_small_grads(Tensor params, Tensor row_off, int64_t off_emb, int64_t off_wih1, Tensor tokens, Tensor dgates,
                                      int64_t E, int64_t V) {
@@ -712,6 +773,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("lstm_small_grads", &lstm_small_grads);
     m.def("conv_pack_weights", &conv_pack_weights);
     m.def("conv_igemm_fwd", &conv_igemm_fwd);
+    m.def("conv_cast_bf16", &conv_cast_bf16);
+    m.def("conv_tma_fwd", &conv_tma_fwd);
+    m.def("conv_tma_wgrad", &conv_tma_wgrad);
     m.def("conv_igemm_dgrad", &conv_igemm_dgrad);
     m.def("conv_igemm_wgrad", &conv_igemm_wgrad);
 }

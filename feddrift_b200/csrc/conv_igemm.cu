@@ -303,6 +303,60 @@ int conv_pack_weights_both_launch(const float* w, void* out0, void* out1, int K,
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
+// fp32 → bf16 cast of a contiguous tensor (the TMA-im2col path consumes bf16 NHWC operands); with `gate` the value is zeroed where
+// gate ≤ 0 — the ReLU backward mask fused into the cast of dY.  8 elements per thread: two 16-byte loads, one 16-byte store.
+__global__ void conv_cast_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gate, __nv_bfloat16* __restrict__ out, long long n8,
+                                      long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (gate) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gate) + 2 * i), gb = __ldg(reinterpret_cast<const float4*>(gate) + 2 * i + 1);
+            const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = g[j] > 0.f ? v[j] : 0.f;
+        }
+        uint4 o;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+        reinterpret_cast<uint4*>(out)[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {      // tail (n % 8 elements)
+        const long long i = (n & ~7LL) + threadIdx.x;
+        float v = x[i];
+        if (gate && !(gate[i] > 0.f)) v = 0.f;
+        out[i] = __float2bfloat16(v);
+    }
+}
+int conv_cast_bf16_launch(const float* x, const float* gate, void* out, long long n, cudaStream_t stream) {
+    const long long n8 = n / 8;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((n8 + 255) / 256, 148 * 16));
+    conv_cast_bf16_kernel<<<blocks, 256, 0, stream>>>(x, gate, reinterpret_cast<__nv_bfloat16*>(out), n8, n);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// dW[k][c][r][s] (+)= src[k][r][s][c]: the TMA wgrad GEMM produces the gradient in the packed (O, H, W, I) order
+__global__ void conv_ohwi_to_oihw_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int C, int RS, int accumulate) {
+    const long long total = (long long)K * C * RS;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;                                  // i indexes the OIHW destination
+        const int rs = (int)(t % RS); t /= RS;
+        const int c = (int)(t % C);
+        const int k = (int)(t / C);
+        const float v = __ldg(src + ((size_t)k * RS + rs) * C + c);
+        dst[i] = accumulate ? dst[i] + v : v;
+    }
+}
+int conv_ohwi_to_oihw_launch(const float* src, float* dst, int K, int C, int RS, int accumulate, cudaStream_t stream) {
+    const long long total = (long long)K * C * RS;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    conv_ohwi_to_oihw_kernel<<<blocks, 256, 0, stream>>>(src, dst, K, C, RS, accumulate);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
 int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream) {
     const long long total = (long long)K * C * R * S;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);

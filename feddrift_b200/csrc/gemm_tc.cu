@@ -21,6 +21,7 @@
 // (fedml_api/model/fnn/fnn.py:11-15, cv/cnn.py:128-136).
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstring>
 #include <cuda_bf16.h>
 
@@ -34,6 +35,12 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 4;
 constexpr int kGemmThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 epilogue
 constexpr uint32_t kStageBytesA = BM * BK * 2;
 struct GemmBatch { int batch, a_k0, a_kstride, b_k0, b_kstride; };
+// Implicit-GEMM convolution modes: one operand is fetched with TMA *im2col* loads straight from the bf16 NHWC tensor.
+//   mode 1 (forward / stride-1 data gradient): A[pixel, (tap, c)] — K-major 128-pixel × 64-channel boxes, one per k-block
+//           (k-block kb = tap·cchunks + c-chunk); B = packed weights [Cout, R·S·C] (dgrad: taps addressed in flipped order);
+//   mode 2 (weight gradient): reduction over output pixels; A = dY [pixels, Cout] (MN-major tiled loads), B[(tap, c), pixel] —
+//           MN-major 64-pixel × 64-channel im2col boxes, one per 64-wide column group of the N tile.
+struct ConvIm { int mode, S, cchunks, ntaps, Q, PQ, stride, pad_h, pad_w, flip; };
 
 template <int BN> struct GemmCfg {
     static constexpr uint32_t kStageBytesB = BN * BK * 2;
@@ -48,7 +55,7 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, void* __restrict__ D, const float* __restrict__ bias, int M, int N, int K,
-               int relu, int out_fp32, int splits, int tma_out, int a_mn, int b_mn, GemmBatch gb) {
+               int relu, int out_fp32, int splits, int tma_out, int a_mn, int b_mn, GemmBatch gb, ConvIm ci) {
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -99,13 +106,45 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int bt = tile / tiles_per_batch, rem = tile - bt * tiles_per_batch;
                 const int m_blk = rem % m_tiles, n_blk = rem / m_tiles;
                 const int ak = gb.a_k0 + bt * gb.a_kstride, bk = gb.b_k0 + bt * gb.b_kstride;   // 0 unless batched
+                int cw = 0, chh = 0, cn = 0;          // im2col anchor of the tile's first pixel (mode 1)
+                if (ci.mode == 1) {
+                    const int m0 = m_blk * BM;
+                    cn = m0 / ci.PQ;
+                    const int rem2 = m0 - cn * ci.PQ, p = rem2 / ci.Q, q = rem2 - p * ci.Q;
+                    cw = q * ci.stride - ci.pad_w;
+                    chh = p * ci.stride - ci.pad_h;
+                }
+                int nvalid = BN / 64;                  // mode 2: 64-wide (tap, c-chunk) column groups of this N tile that exist
+                if (ci.mode == 2) nvalid = max(0, min(BN / 64, ci.ntaps * ci.cchunks - n_blk * (BN / 64)));
                 for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar + s, ph ^ 1);
-                    mbar_expect_tx(full_bar + s, kStageBytesA + Cfg::kStageBytesB);
                     uint8_t* sa = smem_a + s * kStageBytesA;
                     uint8_t* sb = smem_b + s * Cfg::kStageBytesB;
+                    if (ci.mode == 1) {
+                        mbar_expect_tx(full_bar + s, kStageBytesA + Cfg::kStageBytesB);
+                        const int tap = kb / ci.cchunks, cc = kb - tap * ci.cchunks;
+                        const int r = tap / ci.S, sx = tap - r * ci.S;
+                        tma_load_im2col_4d(&map_a, full_bar + s, sa, cc * 64, cw, chh, cn, (uint16_t)sx, (uint16_t)r);
+                        const int wkb = ci.flip ? (ci.ntaps - 1 - tap) * ci.cchunks + cc : kb;
+                        tma_load_2d(&map_b, full_bar + s, sb, wkb * BK, n_blk * BN);
+                        continue;
+                    }
+                    if (ci.mode == 2) {
+                        mbar_expect_tx(full_bar + s, kStageBytesA + (uint32_t)nvalid * 8192u);
+#pragma unroll
+                        for (int h = 0; h < BM / 64; ++h) tma_load_2d(&map_a, full_bar + s, sa + h * 8192, m_blk * BM + h * 64, kb * BK);
+                        const int p0 = kb * BK, pn = p0 / ci.PQ, prem = p0 - pn * ci.PQ, pp = prem / ci.Q, pq = prem - pp * ci.Q;
+                        for (int h = 0; h < nvalid; ++h) {
+                            const int j = n_blk * (BN / 64) + h, tap = j / ci.cchunks, cc = j - tap * ci.cchunks;
+                            const int r = tap / ci.S, sx = tap - r * ci.S;
+                            tma_load_im2col_4d(&map_b, full_bar + s, sb + h * 8192, cc * 64, pq * ci.stride - ci.pad_w, pp * ci.stride - ci.pad_h,
+                                               pn, (uint16_t)sx, (uint16_t)r);
+                        }
+                        continue;
+                    }
+                    mbar_expect_tx(full_bar + s, kStageBytesA + Cfg::kStageBytesB);
                     if (a_mn) {   // [K, M] tensor: two 64(M)×64(K) boxes
 #pragma unroll
                         for (int h = 0; h < BM / 64; ++h) tma_load_2d(&map_a, full_bar + s, sa + h * 8192, m_blk * BM + h * 64, ak + kb * BK);
@@ -357,9 +396,41 @@ static int make_map_mn(CUtensorMap* map, const void* base, int rows, int K) {
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// im2col map over a bf16 NHWC tensor [N, H, W, C]: boxes of `pixels` anchor pixels × 64 channels, 128B swizzle; the bounding
+// box of anchors is the set of output positions of an R×S filter with symmetric padding, walked with the conv stride
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn get_encode_im2col() {
+    static EncodeIm2colFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+    }
+    return fn;
+}
+static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int R, int S, int pad_h, int pad_w, int stride,
+                           int pixels) {
+    EncodeIm2colFn enc = get_encode_im2col();
+    if (!enc) return -1;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    int lower[2] = {-pad_w, -pad_h};
+    int upper[2] = {pad_w - (S - 1), pad_h - (R - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper, 64u, (cuuint32_t)pixels,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
-                       int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream, GemmBatch gb = GemmBatch{1, 0, 0, 0, 0}) {
+                       int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream, GemmBatch gb = GemmBatch{1, 0, 0, 0, 0},
+                       ConvIm ci = ConvIm{0, 0, 0, 0, 0, 0, 0, 0, 0, 0}) {
     CUtensorMap md;
     int tma_out = 0;
     if (make_out_map(&md, D, M * gb.batch, N, out_fp32, &tma_out) != 0) return -7;
@@ -372,7 +443,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * gb.batch;
     dim3 grid(min(tiles, max(1, sms / splits)), 1, splits);
-    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out, a_mn, b_mn, gb);
+    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out, a_mn, b_mn, gb, ci);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -449,6 +520,73 @@ int gemm_batched_mn_launch(const void* A, const void* B, float* D, int M, int N,
     GemmBatch gb{batch, a_k0, a_kstride, b_k0, b_kstride};
     return (bn == 256) ? launch_gemm<256>(ma, mb, D, nullptr, M, N, K, 0, 1, 1, sms, 1, 1, stream, gb)
                        : launch_gemm<128>(ma, mb, D, nullptr, M, N, K, 0, 1, 1, sms, 1, 1, stream, gb);
+}
+
+static int launch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
+                     int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream, const ConvIm& ci) {
+    const GemmBatch gb{1, 0, 0, 0, 0};
+    if (bn == 256) return launch_gemm<256>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci);
+    if (bn == 128) return launch_gemm<128>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci);
+    return launch_gemm<64>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci);
+}
+
+// Implicit-GEMM convolution on the GEMM mainloop (TMA im2col producer).  xb: bf16 NHWC [N, H, W, C] (C % 64 == 0), wq: packed bf16
+// weights [Cout, R·S·C], y: fp32 NHWC [N, P, Q, Cout].  flip = 1 addresses the taps of wq in reverse order (stride-1 data gradient:
+// xb = dY, wq = the [Cin][R][S][Cout] pack, pad = R-1-pad_fwd).  Square filters, symmetric padding.
+int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* bias, int N, int H, int W, int C, int Cout, int R, int S, int P,
+                        int Q, int pad, int stride, int flip, int relu, cudaStream_t stream) {
+    if (C % 64 != 0 || Cout % 8 != 0 || R != S || N <= 0) return -5;
+    if ((reinterpret_cast<uintptr_t>(xb) & 15) || (reinterpret_cast<uintptr_t>(wq) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return -6;
+    const long long Mll = (long long)N * P * Q;
+    if (Mll >= (1LL << 31) - 256) return -5;
+    const int M = (int)Mll, K = R * S * C;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int m_tiles = (M + BM - 1) / BM;
+    // widest N tile that still gives every SM a tile; otherwise the narrowest and split K over the taps
+    int bn = Cout <= 64 ? 64 : 128;
+    if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) bn = 256;
+    const int tiles = m_tiles * ((Cout + bn - 1) / bn), kb_total = K / BK;
+    int splits = 1;
+    if (tiles * 2 <= sms && kb_total >= 8) splits = std::max(1, std::min(std::min(sms / tiles, kb_total / 4), 16));
+    CUtensorMap ma, mb;
+    if (make_im2col_map(&ma, xb, N, H, W, C, R, S, pad, pad, stride, BM) != 0) return -7;
+    if (make_map(&mb, wq, Cout, K, bn) != 0) return -7;
+    const ConvIm ci{1, S, C / 64, R * S, Q, P * Q, stride, pad, pad, flip};
+    if (splits > 1) {
+        cudaMemsetAsync(y, 0, (size_t)M * Cout * sizeof(float), stream);
+        int rc = launch_bn(bn, ma, mb, y, nullptr, M, Cout, K, 0, 1, splits, sms, 0, 0, stream, ci);
+        if (rc != 0) return rc;
+        if (bias || relu) {
+            const long long MN = (long long)M * Cout;
+            bias_act_kernel<<<(int)std::min<long long>((MN + 255) / 256, 148LL * 8), 256, 0, stream>>>(y, y, bias, MN, Cout, relu, 1);
+        }
+        return cudaGetLastError() == cudaSuccess ? 0 : -4;
+    }
+    return launch_bn(bn, ma, mb, y, bias, M, Cout, K, relu, 1, 1, sms, 0, 0, stream, ci);
+}
+
+// Weight gradient: dw_ohwi[Cout, (r, s, c)] (fp32, ZEROED by the caller when the return value says split > 1 … always zero it)
+// = Σ_pixels dY[pixel, Cout] · X[gather(pixel, r, s), c].  xb: bf16 NHWC activations, dyb: bf16 [N·P·Q, Cout].
+int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N, int H, int W, int C, int Cout, int R, int S, int P, int Q,
+                          int pad, int stride, cudaStream_t stream) {
+    if (C % 64 != 0 || Cout % 8 != 0 || R != S || N <= 0) return -5;
+    if ((reinterpret_cast<uintptr_t>(xb) & 15) || (reinterpret_cast<uintptr_t>(dyb) & 15) || (reinterpret_cast<uintptr_t>(dw_ohwi) & 15)) return -6;
+    const long long Kll = (long long)N * P * Q;
+    if (Kll >= (1LL << 31) - 256) return -5;
+    const int Kpix = (int)Kll, RSC = R * S * C;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int bn = 128;
+    const int tiles = ((Cout + BM - 1) / BM) * ((RSC + bn - 1) / bn), kb_total = (Kpix + BK - 1) / BK;
+    int splits = std::max(1, std::min(std::min(sms / tiles, kb_total / 2), 64));
+    CUtensorMap ma, mb;
+    if (make_map_mn(&ma, dyb, Cout, Kpix) != 0) return -7;
+    if (make_im2col_map(&mb, xb, N, H, W, C, R, S, pad, pad, stride, BK) != 0) return -7;
+    const ConvIm ci{2, S, C / 64, R * S, Q, P * Q, stride, pad, pad, 0};
+    return launch_bn(bn, ma, mb, dw_ohwi, nullptr, Cout, RSC, Kpix, 0, 1, splits, sms, 1, 1, stream, ci);
 }
 
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,

@@ -72,6 +72,13 @@ int conv_igemm_launch(const ConvArgs& a, cudaStream_t stream);
 int conv_wgrad_launch(const ConvArgs& a, cudaStream_t stream);
 int conv_pack_weights_both_launch(const float* w, void* out0, void* out1, int K, int C, int R, int S, cudaStream_t stream);
 int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream);
+int conv_cast_bf16_launch(const float* x, const float* gate, void* out, long long n, cudaStream_t stream);
+int conv_ohwi_to_oihw_launch(const float* src, float* dst, int K, int C, int RS, int accumulate, cudaStream_t stream);
+// gemm_tc.cu: implicit-GEMM convolution on the GEMM mainloop with a TMA-im2col producer (bf16 NHWC operands)
+int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* bias, int N, int H, int W, int C, int Cout, int R, int S, int P,
+                        int Q, int pad, int stride, int flip, int relu, cudaStream_t stream);
+int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N, int H, int W, int C, int Cout, int R, int S, int P, int Q,
+                          int pad, int stride, cudaStream_t stream);
 // lstm_tc.cu : persistent cluster-resident 2-layer LSTM(256) forward / BPTT over many (client, model) pairs per launch
 struct LstmArgs {
     const float* params;          // parameter arena base

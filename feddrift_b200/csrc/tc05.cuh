@@ -38,6 +38,12 @@ FDB_DEVICE void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, in
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
+// TMA im2col load of an NHWC tensor (dims {C, W, H, N}): `pixelsPerColumn` consecutive anchor pixels of the map's bounding box
+// starting at (w, h, n), each displaced by the filter-tap offset (off_w, off_h); out-of-image pixels are zero-filled
+FDB_DEVICE void tma_load_im2col_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
 // TMA tile store / reduce-add (smem → global through the D tensor map; rows ≥ M and columns ≥ N are clipped by the hardware)
 FDB_DEVICE void tma_store_2d(const CUtensorMap* map, const void* src, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -1,18 +1,21 @@
-"""``TcConv2d`` — nn.Conv2d-compatible layer whose CUDA path is the hand-written IMPLICIT-GEMM convolution on tcgen05
-(``csrc/conv_igemm.cu``): forward, data gradient and weight gradient, NHWC activations end to end.
+"""``TcConv2d`` — nn.Conv2d-compatible layer whose CUDA path is the hand-written IMPLICIT-GEMM convolution on tcgen05:
+forward, data gradient and weight gradient, NHWC activations end to end.  Two kernel families, picked per direction by shape:
 
-* forward : the producer warps gather each output pixel's (tap, channel) slice straight from the NHWC input into the
-            tensor-core operand tile (no im2col matrix in memory), bias(+ReLU) fused in the epilogue; the result is
-            returned as an NCHW *view* with channels_last strides, so a chain of convolutions never transposes;
-* dgrad   : the same kernel gathers from dY with the transposed weight pack (strided convolutions skip non-integer taps);
-* wgrad   : a GEMM whose reduction runs over the output pixels, both operands MN-major straight from the NHWC tensors,
-            split over pixel ranges with coalesced ``red.global.add`` into the fp32 gradient.
+* **TMA-im2col path** (``csrc/gemm_tc.cu`` conv modes; Cin % 64 == 0, square filter, symmetric padding — every body layer of
+  the ResNets): activations are cast once to bf16 NHWC and the persistent GEMM mainloop's producer thread fetches the operand
+  tiles with ``cp.async.bulk.tensor.4d…im2col`` — the TMA unit walks the output pixels (conv stride = traversal stride), applies
+  the filter-tap offset and zero-fills the halo; no gather code runs on the SMs.  Forward = A[pixel,(tap,c)]·Wᵀ with the
+  bias(+ReLU) epilogue; stride-1 data gradient = the same kernel on dY with the tap-flipped transposed weight pack; weight
+  gradient = a GEMM over the pixels whose B operand is an MN-major im2col box and whose A operand is dY as it lies in memory,
+  split over pixel ranges with ``cp.reduce.async.bulk`` adds.
+* **software-gather path** (``csrc/conv_igemm.cu``; Cin, Cout % 32 == 0): producer warps gather each pixel's (tap, channel)
+  slice from the fp32 NHWC tensor into no-swizzle operand tiles; used for 32-channel layers and strided data gradients.
 
-fp32 activations / master weights, bf16 tensor-core operands, fp32 accumulation in TMEM.  Shapes the kernels do not cover
-(groups / dilation ≠ 1, Cin or Cout not a multiple of 32 — e.g. the 1- or 3-channel stems) and CPU
-tensors use ``F.conv2d``.  ``FDB_CONV_IM2COL=1`` selects the round-1 explicit-im2col + GEMM formulation (kept for A/B
-measurements).  State-dict keys and the init law equal ``nn.Conv2d``'s.  Reference: cuDNN fp32 ``nn.Conv2d``
-(``fedml_api/model/cv/cnn.py:110-117``).
+fp32 activations / master weights, bf16 tensor-core operands, fp32 accumulation in TMEM; results are NCHW *views* with
+channels_last strides, so a chain of convolutions never transposes.  Shapes neither family covers (groups / dilation ≠ 1,
+1- or 3-channel stems) and CPU tensors use ``F.conv2d``.  ``FDB_CONV_IM2COL=1`` selects the round-1 explicit-im2col + GEMM
+formulation and ``FDB_NO_TMA_CONV=1`` the gather kernels everywhere (A/B measurements).  State-dict keys and the init law
+equal ``nn.Conv2d``'s.  Reference: cuDNN fp32 ``nn.Conv2d`` (``fedml_api/model/cv/cnn.py:110-117``).
 """
 from __future__ import annotations
 
@@ -26,7 +29,7 @@ from torch import nn
 from . import _ext
 
 TC_CONV_CALLS = 0
-IGEMM_CALLS = {"fwd": 0, "dgrad": 0, "wgrad": 0}
+IGEMM_CALLS = {"fwd": 0, "dgrad": 0, "wgrad": 0, "tma_fwd": 0, "tma_dgrad": 0, "tma_wgrad": 0}
 
 
 def _pair(v):
@@ -43,34 +46,74 @@ def igemm_eligible(cin: int, cout: int, stride, dilation, groups: int) -> bool:
     return groups == 1 and tuple(dilation) == (1, 1) and stride[0] == stride[1] and cin % 32 == 0 and cout % 32 == 0
 
 
+def tma_eligible(cin: int, stride, padding, ksize) -> bool:
+    """The GEMM-mainloop path with the TMA-im2col producer: 64-channel K chunks, square filter, symmetric padding."""
+    return (cin % 64 == 0 and ksize[0] == ksize[1] and padding[0] == padding[1] and stride[0] == stride[1] and 1 <= stride[0] <= 8
+            and padding[0] < 128 and os.environ.get("FDB_NO_TMA_CONV") != "1")
+
+
+def _nhwc_bf16(ext, t: torch.Tensor, gate=None) -> torch.Tensor:
+    """bf16 NHWC copy of an NCHW-logical fp32 tensor: our cast kernel when the memory already is channels_last (optionally
+    fused with the ReLU-backward gate), one fused layout+dtype copy otherwise."""
+    if t.dtype == torch.float32 and t.is_contiguous(memory_format=torch.channels_last):
+        return ext.conv_cast_bf16(t.permute(0, 2, 3, 1), gate)
+    tb = t.to(dtype=torch.bfloat16, memory_format=torch.channels_last).permute(0, 2, 3, 1)
+    return tb if gate is None else tb * (gate > 0)
+
+
 class _ConvIgemmFn(torch.autograd.Function):
+    """Implicit-GEMM convolution.  Per direction the kernel is picked by shape: the GEMM mainloop with a TMA-im2col producer
+    (``gemm_tc.cu`` conv modes; bf16 NHWC operands, Cin % 64 == 0 — every body layer of the ResNets) or the software-gather
+    kernels of ``conv_igemm.cu`` (Cin % 32, strided data gradients)."""
+
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, relu: bool):
         global TC_CONV_CALLS
         TC_CONV_CALLS += 1
         IGEMM_CALLS["fwd"] += 1
         ext = _ext.load(required=True)
-        xh = _nhwc(x)
+        Co, Ci, kh, kw = weight.shape
         wq, wq_t = ext.conv_pack_weights(weight.detach().float().contiguous())     # both tensor-core packs, one launch
-        y = ext.conv_igemm_fwd(xh, wq, bias.detach() if bias is not None else None, stride[0], padding[0], padding[1], bool(relu))
-        ctx.save_for_backward(xh, wq_t, y if relu else None)
+        bdet = bias.detach() if bias is not None else None
+        tma_in = tma_eligible(Ci, stride, padding, (kh, kw))          # forward and weight gradient gather from x
+        xh = xb = None
+        if tma_in:
+            IGEMM_CALLS["tma_fwd"] += 1
+            xb = _nhwc_bf16(ext, x)
+            y = ext.conv_tma_fwd(xb, wq, bdet, stride[0], padding[0], bool(relu), False)
+        else:
+            xh = _nhwc(x)
+            y = ext.conv_igemm_fwd(xh, wq, bdet, stride[0], padding[0], padding[1], bool(relu))
+        ctx.save_for_backward(xb if tma_in else xh, wq_t, y if relu else None)
         ctx.weight_ref = weight if isinstance(weight, torch.nn.Parameter) else None
-        ctx.geom = (stride, padding, tuple(weight.shape))
-        ctx.relu, ctx.has_bias = relu, bias is not None
+        ctx.geom = (stride, padding, tuple(weight.shape), tuple(x.shape[2:]))
+        ctx.relu, ctx.has_bias, ctx.tma_in = relu, bias is not None, tma_in
         return y.permute(0, 3, 1, 2)                                          # NCHW view, channels_last strides
 
     @staticmethod
     def backward(ctx, gy):
         ext = _ext.load(required=True)
-        xh, wq_t, y = ctx.saved_tensors
-        stride, padding, (Co, Ci, kh, kw) = ctx.geom
-        g = _nhwc(gy)
-        if ctx.relu:
-            g = g * (y > 0)
+        xs, wq_t, y = ctx.saved_tensors
+        stride, padding, (Co, Ci, kh, kw), (H, W) = ctx.geom
+        tma_dgrad = (ctx.needs_input_grad[0] and stride[0] == 1 and padding[0] <= kh - 1
+                     and tma_eligible(Co, stride, padding, (kh, kw)))
+        tma_wgrad = ctx.needs_input_grad[1] and ctx.tma_in
+        need_f32 = (ctx.needs_input_grad[0] and not tma_dgrad) or (ctx.has_bias and ctx.needs_input_grad[2])
+        g = gb = None
+        if need_f32:
+            g = _nhwc(gy)
+            if ctx.relu:
+                g = g * (y > 0)
+        if tma_dgrad or tma_wgrad:
+            gb = ext.conv_cast_bf16(g, None) if g is not None else _nhwc_bf16(ext, gy, y if ctx.relu else None)
         gx = gw = gbias = None
         if ctx.needs_input_grad[0]:
             IGEMM_CALLS["dgrad"] += 1
-            gx = ext.conv_igemm_dgrad(g, wq_t, xh.shape[1], xh.shape[2], stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
+            if tma_dgrad:      # stride-1 data gradient = forward convolution of dY with the tap-flipped [Cin][R][S][Cout] pack
+                IGEMM_CALLS["tma_dgrad"] += 1
+                gx = ext.conv_tma_fwd(gb, wq_t, None, 1, kh - 1 - padding[0], False, True).permute(0, 3, 1, 2)
+            else:
+                gx = ext.conv_igemm_dgrad(g, wq_t, H, W, stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             IGEMM_CALLS["wgrad"] += 1
             wp = ctx.weight_ref
@@ -78,7 +121,17 @@ class _ConvIgemmFn(torch.autograd.Function):
                               and wp.grad.shape == wp.shape and wp.grad.is_cuda) else None
             # with a preallocated .grad (the federated executor binds every parameter's .grad to its slice of the flat, zeroed
             # gradient row) the kernel adds straight into it: no zero-fill launch, no AccumulateGrad add launch
-            gw = ext.conv_igemm_wgrad(xh, g, kh, kw, stride[0], padding[0], padding[1], acc)           # OIHW
+            if tma_wgrad:
+                IGEMM_CALLS["tma_wgrad"] += 1
+                gw = ext.conv_tma_wgrad(xs, gb, kh, kw, stride[0], padding[0], acc)                    # OIHW
+            else:
+                if ctx.tma_in:                          # forward ran on the TMA path but this shape's wgrad cannot: fp32 x again
+                    xs = xs.float()
+                if g is None:
+                    g = _nhwc(gy)
+                    if ctx.relu:
+                        g = g * (y > 0)
+                gw = ext.conv_igemm_wgrad(xs, g, kh, kw, stride[0], padding[0], padding[1], acc)       # OIHW
             if acc is not None:
                 gw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -152,10 +205,10 @@ class TcConv2d(nn.Module):
                 and os.environ.get("FDB_NO_TC_CONV") != "1" and hasattr(_ext.load(), "conv_igemm_fwd")
                 and igemm_eligible(self.in_channels, self.out_channels, self.stride, self.dilation, self.groups)):
             return False
-        # FDB_CONV_POLICY: "igemm" = every eligible layer on the hand-written kernels (default); "auto" = leave layers with
-        # fewer than 2048 output pixels to the library (a 128-pixel-row tile grid cannot fill 148 SMs there; measured
-        # in profiles/conv_probe_r2.jsonl the deep 7×7 / 4×4 stages are 1.5–2.6× slower than cuDNN)
-        if os.environ.get("FDB_CONV_POLICY", "igemm") == "auto":
+        # FDB_CONV_POLICY: "igemm" = every eligible layer on the hand-written kernels (default); "auto" = leave layers with fewer
+        # than 2048 output pixels that only the gather kernels cover to the library (a 128-pixel-row tile grid cannot fill 148
+        # SMs there: profiles/conv_probe_r2.jsonl)
+        if os.environ.get("FDB_CONV_POLICY", "igemm") == "auto" and not tma_eligible(self.in_channels, self.stride, self.padding, self.kernel_size):
             ho = (x.shape[2] + 2 * self.padding[0] - self.kernel_size[0]) // self.stride[0] + 1
             wo = (x.shape[3] + 2 * self.padding[1] - self.kernel_size[1]) // self.stride[1] + 1
             return x.shape[0] * ho * wo >= 2048

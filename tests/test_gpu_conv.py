@@ -16,7 +16,43 @@ GEOMS = [
     (5, 32, 9, 11, 32, 5, 1, 2),       # odd sizes, 5x5, small channels
     (2, 96, 7, 7, 96, 3, 1, 1),        # Cout multiple of 32 only
     (2, 512, 4, 4, 512, 3, 1, 1),      # deep layer, 32 output pixels: split-K forward / dgrad
+    (3, 128, 9, 11, 192, 3, 1, 1),     # TMA path, odd sizes, partial pixel tile, Cout = 1.5 N tiles
+    (2, 64, 13, 13, 64, 3, 1, 0),      # TMA path, no padding
+    (2, 64, 15, 15, 64, 3, 2, 1),      # TMA forward / wgrad with traversal stride 2 on an odd image
+    (2, 64, 12, 12, 64, 5, 1, 2),      # 5x5 taps
 ]
+
+
+def test_conv_tma_ops_direct_and_gated_cast():
+    """conv_cast_bf16 (+ ReLU gate) and the three TMA-im2col GEMM modes against F.conv2d on the same bf16-rounded operands."""
+    from feddrift_b200.ops import _ext
+    ext = _ext.load(required=True)
+    torch.manual_seed(1)
+    N, Ci, H, W, Co, k, st, pad = 3, 128, 10, 7, 64, 3, 1, 1
+    x = torch.randn(N, H, W, Ci, device="cuda")
+    gate = torch.randn(N, H, W, Ci, device="cuda")
+    assert torch.equal(ext.conv_cast_bf16(x, None), x.bfloat16())
+    assert torch.equal(ext.conv_cast_bf16(x, gate), (x * (gate > 0)).bfloat16())
+    odd = torch.randn(1003, device="cuda")
+    assert torch.equal(ext.conv_cast_bf16(odd, None), odd.bfloat16())
+    w = torch.randn(Co, Ci, k, k, device="cuda") / (Ci * k * k) ** 0.5
+    xb = ext.conv_cast_bf16(x, None)
+    wq, wq_t = ext.conv_pack_weights(w)
+    xr = xb.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.bfloat16().float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, st, pad)
+    y = ext.conv_tma_fwd(xb, wq, None, st, pad, True, False)
+    assert (y.permute(0, 3, 1, 2) - F.relu(ref)).abs().max().item() < 1e-3
+    dy = torch.randn_like(y)
+    dyb = ext.conv_cast_bf16(dy, None)
+    gx, gw = torch.autograd.grad(ref, (xr, wr), dyb.float().permute(0, 3, 1, 2))
+    dx = ext.conv_tma_fwd(dyb, wq_t, None, 1, k - 1 - pad, False, True)
+    assert (dx.permute(0, 3, 1, 2) - gx).abs().max().item() < 1e-3 * gx.abs().max().item() + 1e-4
+    dw = ext.conv_tma_wgrad(xb, dyb, k, k, st, pad, None)
+    assert (dw - gw).abs().max().item() < 1e-3 * gw.abs().max().item() + 1e-4
+    acc = torch.full_like(dw, 2.0)
+    ext.conv_tma_wgrad(xb, dyb, k, k, st, pad, acc)
+    assert (acc - 2.0 - gw).abs().max().item() < 1e-3 * gw.abs().max().item() + 1e-4
 
 
 @pytest.mark.parametrize("geom", GEOMS)
@@ -36,6 +72,10 @@ def test_conv_igemm_matches_conv2d(geom):
     torch.cuda.synchronize()
     assert C.IGEMM_CALLS["fwd"] == n0["fwd"] + 1 and C.IGEMM_CALLS["dgrad"] == n0["dgrad"] + 1 and C.IGEMM_CALLS["wgrad"] == n0["wgrad"] + 1
     assert got.shape == ref.shape
+    # the GEMM-mainloop path with the TMA-im2col producer must be the one that ran wherever the shape allows it
+    exp_tma = (int(Ci % 64 == 0), int(Co % 64 == 0 and st == 1), int(Ci % 64 == 0))
+    assert (C.IGEMM_CALLS["tma_fwd"] - n0["tma_fwd"], C.IGEMM_CALLS["tma_dgrad"] - n0["tma_dgrad"],
+            C.IGEMM_CALLS["tma_wgrad"] - n0["tma_wgrad"]) == exp_tma
 
     def rel(a, b_):
         return (a - b_).abs().max().item() / (b_.abs().max().item() + 1e-6)

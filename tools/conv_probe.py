@@ -1,4 +1,4 @@
-"""Implicit-GEMM conv kernels (csrc/conv_igemm.cu) vs cuDNN on the conv shapes of the model zoo (CNN_DropOut conv2, ResNet-18
+"""Implicit-GEMM conv kernels (TMA-im2col GEMM modes of csrc/gemm_tc.cu, gather kernels of csrc/conv_igemm.cu) vs cuDNN on the conv shapes of the model zoo (CNN_DropOut conv2, ResNet-18
 stages): per-direction kernel time (forward / dgrad / wgrad, CUDA events, L2-flushing 256 MiB write between timed launches) and
 module-level forward+backward time (TcConv2d vs nn.Conv2d fp32 NCHW vs nn.Conv2d bf16-autocast channels_last).  Clocks recorded."""
 import json
@@ -55,9 +55,22 @@ for B, cin, cout, k, stride, pad, hw in ((50, 32, 64, 3, 1, 0, 26), (32, 64, 64,
     xb, wb, dyb = xcl.bfloat16(), wcl.bfloat16(), dy_cl.bfloat16()
     mask = [True, True, False]
     r = {"shape": f"B{B} {cin}->{cout} k{k} s{stride} p{pad} {hw}x{hw}", "GFLOP_per_dir": 2.0 * B * Ho * Ho * cout * cin * k * k / 1e9}
-    r["ours_fwd_us"] = timeit(lambda: ext.conv_igemm_fwd(xh, ext.conv_pack_weights(w)[0], tc.bias.detach(), stride, pad, pad, False))
-    r["ours_dgrad_us"] = timeit(lambda: ext.conv_igemm_dgrad(dyh, wpk[1], hw, hw, stride, pad, pad))
-    r["ours_wgrad_us"] = timeit(lambda: ext.conv_igemm_wgrad(xh, dyh, k, k, stride, pad, pad, None))
+    r["gather_fwd_us"] = timeit(lambda: ext.conv_igemm_fwd(xh, ext.conv_pack_weights(w)[0], tc.bias.detach(), stride, pad, pad, False))
+    r["gather_dgrad_us"] = timeit(lambda: ext.conv_igemm_dgrad(dyh, wpk[1], hw, hw, stride, pad, pad))
+    r["gather_wgrad_us"] = timeit(lambda: ext.conv_igemm_wgrad(xh, dyh, k, k, stride, pad, pad, None))
+    r["ours_fwd_us"], r["ours_dgrad_us"], r["ours_wgrad_us"] = r["gather_fwd_us"], r["gather_dgrad_us"], r["gather_wgrad_us"]
+    if cin % 64 == 0:      # TMA-im2col GEMM path: bf16 NHWC operands; the casts are charged to the directions that need them
+        xh_c = xh.contiguous()
+        xbh, dybh = ext.conv_cast_bf16(xh_c, None), ext.conv_cast_bf16(dyh, None)
+        r["cast_x_us"] = timeit(lambda: ext.conv_cast_bf16(xh_c, None))
+        r["cast_dy_us"] = timeit(lambda: ext.conv_cast_bf16(dyh, None))
+        r["tma_fwd_us"] = timeit(lambda: ext.conv_tma_fwd(xbh, ext.conv_pack_weights(w)[0], tc.bias.detach(), stride, pad, False, False))
+        r["tma_wgrad_us"] = timeit(lambda: ext.conv_tma_wgrad(xbh, dybh, k, k, stride, pad, None))
+        r["ours_fwd_us"] = r["tma_fwd_us"] + r["cast_x_us"]
+        r["ours_wgrad_us"] = r["tma_wgrad_us"] + r["cast_dy_us"]
+        if stride == 1 and cout % 64 == 0:
+            r["tma_dgrad_us"] = timeit(lambda: ext.conv_tma_fwd(dybh, wpk[1], None, 1, k - 1 - pad, False, True))
+            r["ours_dgrad_us"] = r["tma_dgrad_us"]
     r["cudnn_fp32_fwd_us"] = timeit(lambda: F.conv2d(x, w, tc.bias.detach(), stride, pad))
     r["cudnn_fp32_bwd_us"] = timeit(lambda: torch.ops.aten.convolution_backward(dy_nchw, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, mask))
     r["cudnn_bf16cl_fwd_us"] = timeit(lambda: F.conv2d(xb, wb, None, stride, pad))

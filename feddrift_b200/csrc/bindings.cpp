@@ -623,7 +623,8 @@ Tensor conv_igemm_dgrad(Tensor dy, Tensor wq_t, int64_t H, int64_t W, int64_t st
 // x: NHWC fp32 [N, H, W, C]; dy: NHWC fp32 [N, P, Q, K]; -> dW fp32 OIHW [K, C, R, S]
 // `accum_into`: an existing fp32 OIHW gradient buffer to ADD into (no zero-fill, no extra accumulate kernel) — the federated
 // executor's parameters already own a zeroed `.grad` view of the flat gradient row
-Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t stride, int64_t pad_h, int64_t pad_w, c10::optional<Tensor> accum_into) {
+Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t stride, int64_t pad_h, int64_t pad_w, c10::optional<Tensor> accum_into,
+                        bool ohwi) {
     CHECK_CUDA_F32(x); CHECK_CUDA_F32(dy);
     TORCH_CHECK(x.is_contiguous() && dy.is_contiguous() && x.dim() == 4 && dy.dim() == 4, "conv_igemm_wgrad: contiguous NHWC tensors");
     TORCH_CHECK(x.size(3) % 8 == 0 && dy.size(3) % 32 == 0, "conv_igemm wgrad needs Cin % 8 == 0 and Cout % 32 == 0");
@@ -636,10 +637,11 @@ Tensor conv_igemm_wgrad(Tensor x, Tensor dy, int64_t R, int64_t S, int64_t strid
         CHECK_CUDA_F32(dw);
         TORCH_CHECK(dw.is_contiguous() && dw.numel() == (int64_t)K * C * R * S, "conv_igemm_wgrad: accum_into must be a contiguous OIHW buffer");
     } else {
-        dw = torch::empty({K, C, R, S}, x.options());
+        dw = ohwi ? torch::empty({K, R, S, C}, x.options()) : torch::empty({K, C, R, S}, x.options());
         cudaMemsetAsync(dw.data_ptr<float>(), 0, (size_t)dw.numel() * sizeof(float), cur_stream());
     }
     fdb::ConvArgs a{};
+    a.mode = ohwi ? 1 : 0;       // layout of dw: [K][R][S][C] (channels_last storage of the parameter) or OIHW
     a.x = x.data_ptr<float>(); a.dy = dy.data_ptr<float>(); a.dw = dw.data_ptr<float>();
     a.N = N; a.H = H; a.W = W; a.C = C; a.Kout = K; a.R = (int)R; a.S = (int)S; a.P = P; a.Q = Q;
     a.pad_h = (int)pad_h; a.pad_w = (int)pad_w; a.stride = (int)stride;
@@ -652,21 +654,22 @@ Tensor conv_cast_bf16(Tensor x, c10::optional<Tensor> gate) {
     CHECK_CUDA_F32(x);
     TORCH_CHECK(x.is_contiguous(), "conv_cast_bf16: contiguous input");
     c10::cuda::CUDAGuard guard(x.device());
-    auto out = torch::empty(x.sizes(), x.options().dtype(torch::kBFloat16));
     const float* g = nullptr;
     if (gate.has_value() && gate->defined()) {
         CHECK_CUDA_F32((*gate));
         TORCH_CHECK(gate->is_contiguous() && gate->numel() == x.numel(), "conv_cast_bf16: gate shape");
         g = gate->data_ptr<float>();
     }
+    if ((reinterpret_cast<uintptr_t>(x.data_ptr<float>()) & 15) || (reinterpret_cast<uintptr_t>(g) & 15))   // 128-bit loads need 16-byte bases
+        return g ? (x * gate->gt(0).view_as(x)).to(torch::kBFloat16) : x.to(torch::kBFloat16);
+    auto out = torch::empty(x.sizes(), x.options().dtype(torch::kBFloat16));
     CHECK_OK(fdb::conv_cast_bf16_launch(x.data_ptr<float>(), g, out.data_ptr(), x.numel(), cur_stream()), "conv_cast_bf16");
     return out;
 }
-// xb: bf16 NHWC [N, H, W, C]; wq: packed bf16 [Cout][R][S][C]; -> fp32 NHWC [N, P, Q, Cout].  flip = taps of wq in reverse order
-// (stride-1 data gradient: xb = dY, wq = the [Cin][R][S][Cout] pack, pad = R - 1 - pad_fwd)
-Tensor conv_tma_fwd(Tensor xb, Tensor wq, c10::optional<Tensor> bias, int64_t stride, int64_t pad, bool relu, bool flip) {
+// xb: bf16 NHWC [N, H, W, C]; wq: bf16 [Cout][R][S][C]; -> fp32 NHWC [N, P, Q, Cout] = act(conv(x, w) + bias)
+Tensor conv_tma_fwd(Tensor xb, Tensor wq, c10::optional<Tensor> bias, int64_t stride, int64_t pad, bool relu) {
     TORCH_CHECK(xb.is_cuda() && xb.scalar_type() == torch::kBFloat16 && xb.dim() == 4 && xb.is_contiguous(), "conv_tma_fwd: xb must be contiguous bf16 NHWC");
-    TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kBFloat16 && wq.dim() == 4 && wq.is_contiguous(), "conv_tma_fwd: wq must be packed bf16 [K,R,S,C]");
+    TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kBFloat16 && wq.dim() == 4 && wq.is_contiguous(), "conv_tma_fwd: wq must be bf16 [K,R,S,C]");
     const int N = (int)xb.size(0), H = (int)xb.size(1), W = (int)xb.size(2), C = (int)xb.size(3);
     const int K = (int)wq.size(0), R = (int)wq.size(1), S = (int)wq.size(2);
     TORCH_CHECK(wq.size(3) == C && C % 64 == 0 && K % 8 == 0 && R == S, "conv_tma_fwd: needs Cin % 64 == 0, Cout % 8 == 0, square filter");
@@ -678,34 +681,47 @@ Tensor conv_tma_fwd(Tensor xb, Tensor wq, c10::optional<Tensor> bias, int64_t st
     const float* bp = nullptr;
     if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
     CHECK_OK(fdb::conv_tma_fwd_launch(xb.data_ptr(), wq.data_ptr(), y.data_ptr<float>(), bp, N, H, W, C, K, R, S, P, Q, (int)pad, (int)stride,
-                                      flip ? 1 : 0, relu ? 1 : 0, cur_stream()), "conv_tma_fwd (tcgen05 + TMA im2col)");
+                                      0, relu ? 1 : 0, cur_stream()), "conv_tma_fwd (tcgen05 + TMA im2col)");
     return y;
 }
-// xb: bf16 NHWC [N, H, W, C]; dyb: bf16 NHWC [N, P, Q, K]; -> dW fp32 OIHW (added into `accum_into` when given)
-Tensor conv_tma_wgrad(Tensor xb, Tensor dyb, int64_t R, int64_t S, int64_t stride, int64_t pad, c10::optional<Tensor> accum_into) {
+// stride-1 data gradient.  dyb: bf16 NHWC [N, P, Q, Cout]; wq: THE FORWARD pack bf16 [Cout][R][S][Cin] (read as an MN-major operand
+// with flipped taps); pad = the forward padding; -> dx fp32 NHWC [N, P + R - 1 - 2·pad, Q + S - 1 - 2·pad, Cin]
+Tensor conv_tma_dgrad(Tensor dyb, Tensor wq, int64_t pad) {
+    TORCH_CHECK(dyb.is_cuda() && dyb.scalar_type() == torch::kBFloat16 && dyb.dim() == 4 && dyb.is_contiguous(), "conv_tma_dgrad: dyb must be contiguous bf16 NHWC");
+    TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kBFloat16 && wq.dim() == 4 && wq.is_contiguous(), "conv_tma_dgrad: wq must be bf16 [K,R,S,C]");
+    const int N = (int)dyb.size(0), P = (int)dyb.size(1), Q = (int)dyb.size(2), K = (int)dyb.size(3);
+    const int R = (int)wq.size(1), S = (int)wq.size(2), C = (int)wq.size(3);
+    TORCH_CHECK(wq.size(0) == K && K % 64 == 0 && C % 8 == 0 && R == S && pad >= 0 && pad <= R - 1, "conv_tma_dgrad: needs Cout % 64 == 0, Cin % 8 == 0, square filter, pad <= R-1");
+    const int pd = R - 1 - (int)pad, H = P + 2 * pd - R + 1, W = Q + 2 * pd - S + 1;
+    c10::cuda::CUDAGuard guard(dyb.device());
+    auto dx = torch::empty({N, H, W, C}, dyb.options().dtype(torch::kFloat32));
+    CHECK_OK(fdb::conv_tma_fwd_launch(dyb.data_ptr(), wq.data_ptr(), dx.data_ptr<float>(), nullptr, N, P, Q, K, C, R, S, H, W, pd, 1, 1, 0,
+                                      cur_stream()), "conv_tma_dgrad (tcgen05 + TMA im2col)");
+    return dx;
+}
+// xb: bf16 NHWC [N, H, W, C]; dyb: bf16 NHWC [N, P, Q, K]; dw_ohwi: fp32 [K, R, S, C] — the gradient is ADDED into it
+void conv_tma_wgrad(Tensor xb, Tensor dyb, Tensor dw_ohwi, int64_t stride, int64_t pad) {
     TORCH_CHECK(xb.is_cuda() && xb.scalar_type() == torch::kBFloat16 && xb.dim() == 4 && xb.is_contiguous(), "conv_tma_wgrad: xb must be contiguous bf16 NHWC");
     TORCH_CHECK(dyb.is_cuda() && dyb.scalar_type() == torch::kBFloat16 && dyb.dim() == 4 && dyb.is_contiguous(), "conv_tma_wgrad: dyb must be contiguous bf16 NHWC");
+    CHECK_CUDA_F32(dw_ohwi);
+    TORCH_CHECK(dw_ohwi.dim() == 4 && dw_ohwi.is_contiguous(), "conv_tma_wgrad: dw must be a contiguous fp32 [K,R,S,C] buffer");
     const int N = (int)xb.size(0), H = (int)xb.size(1), W = (int)xb.size(2), C = (int)xb.size(3);
     const int P = (int)dyb.size(1), Q = (int)dyb.size(2), K = (int)dyb.size(3);
-    TORCH_CHECK(C % 64 == 0 && K % 8 == 0 && R == S && dyb.size(0) == N, "conv_tma_wgrad: needs Cin % 64 == 0, Cout % 8 == 0, square filter");
+    const int R = (int)dw_ohwi.size(1), S = (int)dw_ohwi.size(2);
+    TORCH_CHECK(dw_ohwi.size(0) == K && dw_ohwi.size(3) == C && C % 64 == 0 && K % 8 == 0 && R == S && dyb.size(0) == N,
+                "conv_tma_wgrad: needs Cin % 64 == 0, Cout % 8 == 0, square filter");
     c10::cuda::CUDAGuard guard(xb.device());
-    auto o = xb.options().dtype(torch::kFloat32);
-    auto tmp = torch::empty({K, R, S, C}, o);
-    cudaMemsetAsync(tmp.data_ptr<float>(), 0, (size_t)tmp.numel() * sizeof(float), cur_stream());
-    CHECK_OK(fdb::conv_tma_wgrad_launch(xb.data_ptr(), dyb.data_ptr(), tmp.data_ptr<float>(), N, H, W, C, K, (int)R, (int)S, P, Q, (int)pad,
+    CHECK_OK(fdb::conv_tma_wgrad_launch(xb.data_ptr(), dyb.data_ptr(), dw_ohwi.data_ptr<float>(), N, H, W, C, K, R, S, P, Q, (int)pad,
                                         (int)stride, cur_stream()), "conv_tma_wgrad (tcgen05 + TMA im2col)");
-    Tensor dw;
-    int accumulate = 0;
-    if (accum_into.has_value() && accum_into->defined()) {
-        dw = *accum_into;
-        CHECK_CUDA_F32(dw);
-        TORCH_CHECK(dw.is_contiguous() && dw.numel() == (int64_t)K * C * R * S, "conv_tma_wgrad: accum_into must be a contiguous OIHW buffer");
-        accumulate = 1;
-    } else {
-        dw = torch::empty({K, C, R, S}, o);
-    }
-    CHECK_OK(fdb::conv_ohwi_to_oihw_launch(tmp.data_ptr<float>(), dw.data_ptr<float>(), K, C, (int)(R * S), accumulate, cur_stream()), "conv_ohwi_to_oihw");
-    return dw;
+}
+// bf16 [K][R][S][C] (the cast channels_last weight) -> bf16 [C][R][S][K] for the software-gather data-gradient kernel
+Tensor conv_pack_t(Tensor wq) {
+    TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kBFloat16 && wq.dim() == 4 && wq.is_contiguous(), "conv_pack_t: wq must be bf16 [K,R,S,C]");
+    c10::cuda::CUDAGuard guard(wq.device());
+    const int K = (int)wq.size(0), R = (int)wq.size(1), S = (int)wq.size(2), C = (int)wq.size(3);
+    auto out = torch::empty({C, R, S, K}, wq.options());
+    CHECK_OK(fdb::conv_pack_t_launch(wq.data_ptr(), out.data_ptr(), K, C, R * S, cur_stream()), "conv_pack_t");
+    return out;
 }
 
 // bias / W_ih1 / embedding gradients of every chunk from the gate-gradient histories (lstm_tc.cu::lstm_small_grads_kernel)
@@ -776,6 +792,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("conv_cast_bf16", &conv_cast_bf16);
     m.def("conv_tma_fwd", &conv_tma_fwd);
     m.def("conv_tma_wgrad", &conv_tma_wgrad);
+    m.def("conv_tma_dgrad", &conv_tma_dgrad);
+    m.def("conv_pack_t", &conv_pack_t);
     m.def("conv_igemm_dgrad", &conv_igemm_dgrad);
     m.def("conv_igemm_wgrad", &conv_igemm_wgrad);
 }

@@ -296,8 +296,41 @@ __global__ void conv_pack_weights_both_kernel(const float* __restrict__ w, __nv_
         out1[(((size_t)c * R + r) * S + s) * K + k] = v;
     }
 }
+// tiled variant (R·S ≤ 11): one block per (32 k × 32 c) tile — coalesced reads of the OIHW rows, the two transposes go through
+// shared memory, both outputs are written in 64-byte runs.  The pack runs once per optimizer step on every conv layer, i.e. its
+// cost is proportional to the parameter count, not to the batch.
+__global__ void conv_pack_weights_tiled_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out0, __nv_bfloat16* __restrict__ out1,
+                                               int K, int C, int RS) {
+    extern __shared__ float tile[];                         // [32 k][32·RS + 1]
+    const int pitch = 32 * RS + 1, kt = (K + 31) / 32, ct = (C + 31) / 32;
+    for (int blk = blockIdx.x; blk < kt * ct; blk += gridDim.x) {
+        const int k0 = (blk / ct) * 32, c0 = (blk % ct) * 32, kw = min(32, K - k0), cw = min(32, C - c0);
+        const int seg = cw * RS;
+        for (int i = threadIdx.x; i < 32 * seg; i += blockDim.x) {
+            const int kk = i / seg, t = i - kk * seg;
+            if (kk < kw) tile[kk * pitch + t] = __ldg(w + ((size_t)(k0 + kk) * C + c0) * RS + t);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * RS * 32; i += blockDim.x) {
+            const int c = i & 31, rs = (i >> 5) % RS, kk = i / (32 * RS);
+            if (kk < kw && c < cw) out0[((size_t)(k0 + kk) * RS + rs) * C + c0 + c] = __float2bfloat16(tile[kk * pitch + c * RS + rs]);
+        }
+        for (int i = threadIdx.x; i < 32 * RS * 32; i += blockDim.x) {
+            const int kk = i & 31, rs = (i >> 5) % RS, c = i / (32 * RS);
+            if (kk < kw && c < cw) out1[((size_t)(c0 + c) * RS + rs) * K + k0 + kk] = __float2bfloat16(tile[kk * pitch + c * RS + rs]);
+        }
+        __syncthreads();
+    }
+}
 int conv_pack_weights_both_launch(const float* w, void* out0, void* out1, int K, int C, int R, int S, cudaStream_t stream) {
     const long long total = (long long)K * C * R * S;
+    if (R * S <= 11) {
+        const int tiles = ((K + 31) / 32) * ((C + 31) / 32);
+        const size_t smem = (size_t)32 * (32 * R * S + 1) * sizeof(float);
+        conv_pack_weights_tiled_kernel<<<std::min(tiles, 148 * 8), 256, smem, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out0),
+                                                                                      reinterpret_cast<__nv_bfloat16*>(out1), K, C, R * S);
+        return cudaGetLastError() == cudaSuccess ? 0 : -4;
+    }
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
     conv_pack_weights_both_kernel<<<blocks, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out0), reinterpret_cast<__nv_bfloat16*>(out1), K, C, R, S);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
@@ -338,22 +371,56 @@ int conv_cast_bf16_launch(const float* x, const float* gate, void* out, long lon
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
-// dW[k][c][r][s] (+)= src[k][r][s][c]: the TMA wgrad GEMM produces the gradient in the packed (O, H, W, I) order
+// dW[k][c][r][s] (+)= src[k][r][s][c]: the TMA wgrad GEMM produces the gradient in the packed (O, H, W, I) order.  One block per
+// (k, 64-channel chunk): both the source rows and the destination range are contiguous, the transpose happens in shared memory.
 __global__ void conv_ohwi_to_oihw_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int C, int RS, int accumulate) {
-    const long long total = (long long)K * C * RS;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long t = i;                                  // i indexes the OIHW destination
-        const int rs = (int)(t % RS); t /= RS;
-        const int c = (int)(t % C);
-        const int k = (int)(t / C);
-        const float v = __ldg(src + ((size_t)k * RS + rs) * C + c);
-        dst[i] = accumulate ? dst[i] + v : v;
+    extern __shared__ float tile[];                         // [RS][65]
+    const int cchunks = (C + 63) / 64;
+    for (int blk = blockIdx.x; blk < K * cchunks; blk += gridDim.x) {
+        const int k = blk / cchunks, c0 = (blk - k * cchunks) * 64, cw = min(64, C - c0);
+        for (int i = threadIdx.x; i < RS * 64; i += blockDim.x) {
+            const int rs = i >> 6, c = i & 63;
+            if (c < cw) tile[rs * 65 + c] = __ldg(src + ((size_t)k * RS + rs) * C + c0 + c);
+        }
+        __syncthreads();
+        float* out = dst + ((size_t)k * C + c0) * RS;
+        for (int j = threadIdx.x; j < cw * RS; j += blockDim.x) {
+            const int c = j / RS, rs = j - c * RS;
+            const float v = tile[rs * 65 + c];
+            out[j] = accumulate ? out[j] + v : v;
+        }
+        __syncthreads();
     }
 }
 int conv_ohwi_to_oihw_launch(const float* src, float* dst, int K, int C, int RS, int accumulate, cudaStream_t stream) {
-    const long long total = (long long)K * C * RS;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-    conv_ohwi_to_oihw_kernel<<<blocks, 256, 0, stream>>>(src, dst, K, C, RS, accumulate);
+    const int blocks = std::min(K * ((C + 63) / 64), 148 * 16);
+    const size_t smem = (size_t)RS * 65 * sizeof(float);
+    if (smem > 48 * 1024) return -5;
+    conv_ohwi_to_oihw_kernel<<<blocks, 256, smem, stream>>>(src, dst, K, C, RS, accumulate);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// bf16 [K][RS][C] → bf16 [C][RS][K] (32×32 tiles through shared memory), for the strided layers' software-gather data gradient
+__global__ void conv_pack_t_kernel(const __nv_bfloat16* __restrict__ wq, __nv_bfloat16* __restrict__ out, int K, int C, int RS) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int kt = (K + 31) / 32, ct = (C + 31) / 32;
+    for (int blk = blockIdx.x; blk < kt * ct * RS; blk += gridDim.x) {
+        const int rs = blk % RS, t = blk / RS, k0 = (t / ct) * 32, c0 = (t % ct) * 32;
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            const int kk = i >> 5, c = i & 31;
+            if (k0 + kk < K && c0 + c < C) tile[kk][c] = wq[((size_t)(k0 + kk) * RS + rs) * C + c0 + c];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            const int c = i >> 5, kk = i & 31;
+            if (k0 + kk < K && c0 + c < C) out[((size_t)(c0 + c) * RS + rs) * K + k0 + kk] = tile[kk][c];
+        }
+        __syncthreads();
+    }
+}
+int conv_pack_t_launch(const void* wq, void* out, int K, int C, int RS, cudaStream_t stream) {
+    const int tiles = ((K + 31) / 32) * ((C + 31) / 32) * RS;
+    conv_pack_t_kernel<<<std::min(tiles, 148 * 16), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(wq), reinterpret_cast<__nv_bfloat16*>(out), K, C, RS);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -509,7 +576,11 @@ __global__ void __launch_bounds__(cv::kFwdThreads, 1) conv_wgrad_kernel(const __
             if (j < RSC) {   // dW is written in the framework's OIHW layout: [k][c][r][s]
                 const int tap = j / a.C, c = j - tap * a.C, RS = a.R * a.S;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(a.dw + ((size_t)(n_blk * BN + c0 + i) * a.C + c) * RS + tap, __uint_as_float(v[i]));
+                for (int i = 0; i < 32; ++i) {
+                    float* dst = a.mode == 1 ? a.dw + (size_t)(n_blk * BN + c0 + i) * RSC + j      // [k][r][s][c]: lanes = consecutive j
+                                             : a.dw + ((size_t)(n_blk * BN + c0 + i) * a.C + c) * RS + tap;
+                    atomicAdd(dst, __uint_as_float(v[i]));
+                }
             }
         }
     }

@@ -37,10 +37,12 @@ constexpr uint32_t kStageBytesA = BM * BK * 2;
 struct GemmBatch { int batch, a_k0, a_kstride, b_k0, b_kstride; };
 // Implicit-GEMM convolution modes: one operand is fetched with TMA *im2col* loads straight from the bf16 NHWC tensor.
 //   mode 1 (forward / stride-1 data gradient): A[pixel, (tap, c)] — K-major 128-pixel × 64-channel boxes, one per k-block
-//           (k-block kb = tap·cchunks + c-chunk); B = packed weights [Cout, R·S·C] (dgrad: taps addressed in flipped order);
+//           (k-block kb = tap·cchunks + c-chunk); B = packed weights [Cout, R·S·C], K-major for the forward; the data gradient
+//           reads THE SAME pack as an MN-major operand (b_mn: 64(cin) × 64(cout) boxes at column tap'·Cin, taps flipped), so
+//           no transposed copy of the weights is ever made;
 //   mode 2 (weight gradient): reduction over output pixels; A = dY [pixels, Cout] (MN-major tiled loads), B[(tap, c), pixel] —
 //           MN-major 64-pixel × 64-channel im2col boxes, one per 64-wide column group of the N tile.
-struct ConvIm { int mode, S, cchunks, ntaps, Q, PQ, stride, pad_h, pad_w, flip; };
+struct ConvIm { int mode, S, cchunks, ntaps, Q, PQ, stride, pad_h, pad_w, flip, bcols; };
 
 template <int BN> struct GemmCfg {
     static constexpr uint32_t kStageBytesB = BN * BK * 2;
@@ -127,8 +129,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const int tap = kb / ci.cchunks, cc = kb - tap * ci.cchunks;
                         const int r = tap / ci.S, sx = tap - r * ci.S;
                         tma_load_im2col_4d(&map_a, full_bar + s, sa, cc * 64, cw, chh, cn, (uint16_t)sx, (uint16_t)r);
-                        const int wkb = ci.flip ? (ci.ntaps - 1 - tap) * ci.cchunks + cc : kb;
-                        tma_load_2d(&map_b, full_bar + s, sb, wkb * BK, n_blk * BN);
+                        const int wtap = ci.flip ? ci.ntaps - 1 - tap : tap;
+                        if (b_mn) {
+#pragma unroll
+                            for (int h = 0; h < BN / 64; ++h)
+                                tma_load_2d(&map_b, full_bar + s, sb + h * 8192, wtap * ci.bcols + n_blk * BN + h * 64, cc * BK);
+                        } else {
+                            tma_load_2d(&map_b, full_bar + s, sb, (wtap * ci.cchunks + cc) * BK, n_blk * BN);
+                        }
                         continue;
                     }
                     if (ci.mode == 2) {
@@ -256,7 +264,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (splits > 1) tma_reduce_add_2d(&map_d, buf, col0, row0);
+                        if (splits > 1 || ci.mode == 2) tma_reduce_add_2d(&map_d, buf, col0, row0);   // wgrad always accumulates
                         else tma_store_2d(&map_d, buf, col0, row0);
                         tma_store_commit();
                     }
@@ -430,7 +438,7 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int
 template <int BN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
                        int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream, GemmBatch gb = GemmBatch{1, 0, 0, 0, 0},
-                       ConvIm ci = ConvIm{0, 0, 0, 0, 0, 0, 0, 0, 0, 0}) {
+                       ConvIm ci = ConvIm{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}) {
     CUtensorMap md;
     int tma_out = 0;
     if (make_out_map(&md, D, M * gb.batch, N, out_fp32, &tma_out) != 0) return -7;
@@ -530,11 +538,14 @@ static int launch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, void*
     return launch_gemm<64>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci);
 }
 
-// Implicit-GEMM convolution on the GEMM mainloop (TMA im2col producer).  xb: bf16 NHWC [N, H, W, C] (C % 64 == 0), wq: packed bf16
-// weights [Cout, R·S·C], y: fp32 NHWC [N, P, Q, Cout].  flip = 1 addresses the taps of wq in reverse order (stride-1 data gradient:
-// xb = dY, wq = the [Cin][R][S][Cout] pack, pad = R-1-pad_fwd).  Square filters, symmetric padding.
+// Implicit-GEMM convolution on the GEMM mainloop (TMA im2col producer).  xb: bf16 NHWC [N, H, W, C] (C % 64 == 0), wq: bf16
+// weights [Cout, R·S·C] (the channels_last storage of the parameter, cast), y: fp32 NHWC [N, P, Q, Cout].  Square filters,
+// symmetric padding.
+//   dgrad = 0: forward, y = act(conv(x, w) + bias).
+//   dgrad = 1: stride-1 data gradient: xb = dY [N, P, Q, C = Cout_fwd], wq = the SAME forward pack [Cout_fwd, R·S·Cin_fwd],
+//              `Cout` = Cin_fwd, pad = R-1-pad_fwd; the pack is read as an MN-major B operand with flipped taps.
 int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* bias, int N, int H, int W, int C, int Cout, int R, int S, int P,
-                        int Q, int pad, int stride, int flip, int relu, cudaStream_t stream) {
+                        int Q, int pad, int stride, int dgrad, int relu, cudaStream_t stream) {
     if (C % 64 != 0 || Cout % 8 != 0 || R != S || N <= 0) return -5;
     if ((reinterpret_cast<uintptr_t>(xb) & 15) || (reinterpret_cast<uintptr_t>(wq) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return -6;
     const long long Mll = (long long)N * P * Q;
@@ -552,11 +563,12 @@ int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* b
     if (tiles * 2 <= sms && kb_total >= 8) splits = std::max(1, std::min(std::min(sms / tiles, kb_total / 4), 16));
     CUtensorMap ma, mb;
     if (make_im2col_map(&ma, xb, N, H, W, C, R, S, pad, pad, stride, BM) != 0) return -7;
-    if (make_map(&mb, wq, Cout, K, bn) != 0) return -7;
-    const ConvIm ci{1, S, C / 64, R * S, Q, P * Q, stride, pad, pad, flip};
+    if (dgrad) { if (make_map_mn(&mb, wq, R * S * Cout, C) != 0) return -7; }      // [C = Cout_fwd rows (K), R·S·Cin_fwd contiguous]
+    else if (make_map(&mb, wq, Cout, K, bn) != 0) return -7;
+    const ConvIm ci{1, S, C / 64, R * S, Q, P * Q, stride, pad, pad, dgrad, Cout};
     if (splits > 1) {
         cudaMemsetAsync(y, 0, (size_t)M * Cout * sizeof(float), stream);
-        int rc = launch_bn(bn, ma, mb, y, nullptr, M, Cout, K, 0, 1, splits, sms, 0, 0, stream, ci);
+        int rc = launch_bn(bn, ma, mb, y, nullptr, M, Cout, K, 0, 1, splits, sms, 0, dgrad, stream, ci);
         if (rc != 0) return rc;
         if (bias || relu) {
             const long long MN = (long long)M * Cout;
@@ -564,11 +576,12 @@ int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* b
         }
         return cudaGetLastError() == cudaSuccess ? 0 : -4;
     }
-    return launch_bn(bn, ma, mb, y, bias, M, Cout, K, relu, 1, 1, sms, 0, 0, stream, ci);
+    return launch_bn(bn, ma, mb, y, bias, M, Cout, K, relu, 1, 1, sms, 0, dgrad, stream, ci);
 }
 
-// Weight gradient: dw_ohwi[Cout, (r, s, c)] (fp32, ZEROED by the caller when the return value says split > 1 … always zero it)
-// = Σ_pixels dY[pixel, Cout] · X[gather(pixel, r, s), c].  xb: bf16 NHWC activations, dyb: bf16 [N·P·Q, Cout].
+// Weight gradient: dw_ohwi[Cout, (r, s, c)] (fp32) += Σ_pixels dY[pixel, Cout] · X[gather(pixel, r, s), c] — the tiles are
+// REDUCE-ADDED (cp.reduce.async.bulk) into the buffer, which is the channels_last storage of the parameter's gradient: the
+// flat gradient row of the federated executor, or a zeroed tensor.  xb: bf16 NHWC activations, dyb: bf16 [N·P·Q, Cout].
 int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N, int H, int W, int C, int Cout, int R, int S, int P, int Q,
                           int pad, int stride, cudaStream_t stream) {
     if (C % 64 != 0 || Cout % 8 != 0 || R != S || N <= 0) return -5;
@@ -585,7 +598,7 @@ int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N
     CUtensorMap ma, mb;
     if (make_map_mn(&ma, dyb, Cout, Kpix) != 0) return -7;
     if (make_im2col_map(&mb, xb, N, H, W, C, R, S, pad, pad, stride, BK) != 0) return -7;
-    const ConvIm ci{2, S, C / 64, R * S, Q, P * Q, stride, pad, pad, 0};
+    const ConvIm ci{2, S, C / 64, R * S, Q, P * Q, stride, pad, pad, 0, 0};
     return launch_bn(bn, ma, mb, dw_ohwi, nullptr, Cout, RSC, Kpix, 0, 1, splits, sms, 1, 1, stream, ci);
 }
 

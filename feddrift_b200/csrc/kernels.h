@@ -64,7 +64,7 @@ struct ConvArgs {
     const float* bias;     // [Kout] or nullptr (forward)
     float* y;              // [N, P, Q, Kout] output of forward / dgrad
     const float* dy;       // wgrad: [N·P·Q, Kout]
-    float* dw;             // wgrad: zeroed fp32 gradient in OIHW layout [Kout][C][R][S]
+    float* dw;             // wgrad: fp32 gradient to add into — OIHW [Kout][C][R][S] (mode 0) or [Kout][R][S][C] (mode 1)
     int N, H, W, C, Kout, R, S, P, Q, pad_h, pad_w, stride, mode, relu;
 };
 int make_kmajor_sw128_map(void* map_out /* CUtensorMap* */, const void* base, int rows, int cols, int box_rows);   // gemm_tc.cu
@@ -74,9 +74,10 @@ int conv_pack_weights_both_launch(const float* w, void* out0, void* out1, int K,
 int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream);
 int conv_cast_bf16_launch(const float* x, const float* gate, void* out, long long n, cudaStream_t stream);
 int conv_ohwi_to_oihw_launch(const float* src, float* dst, int K, int C, int RS, int accumulate, cudaStream_t stream);
+int conv_pack_t_launch(const void* wq, void* out, int K, int C, int RS, cudaStream_t stream);
 // gemm_tc.cu: implicit-GEMM convolution on the GEMM mainloop with a TMA-im2col producer (bf16 NHWC operands)
 int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* bias, int N, int H, int W, int C, int Cout, int R, int S, int P,
-                        int Q, int pad, int stride, int flip, int relu, cudaStream_t stream);
+                        int Q, int pad, int stride, int dgrad, int relu, cudaStream_t stream);
 int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N, int H, int W, int C, int Cout, int R, int S, int P, int Q,
                           int pad, int stride, cudaStream_t stream);
 // lstm_tc.cu : persistent cluster-resident 2-layer LSTM(256) forward / BPTT over many (client, model) pairs per launch

@@ -62,6 +62,16 @@ def flat_spec(module_or_sd) -> List[Tuple[str, torch.Size, torch.dtype, int, int
     return out
 
 
+def flat_view(t: torch.Tensor) -> torch.Tensor:
+    """The tensor's elements in FLAT-ROW ORDER.  4-D tensors (convolution weights ``[O, I, kh, kw]``) are stored in the row in
+    (O, kh, kw, I) order — the ``channels_last`` memory format, which is the K-major operand layout of the implicit-GEMM
+    convolution kernels: the forward / data-gradient weight operand is then a plain bf16 cast of the row segment and the
+    weight-gradient GEMM reduce-adds straight into the flat gradient row (no per-step transposing pack, no un-permute).
+    Everything else is stored in logical (row-major) order.  Row operations (aggregation, optimizer, norms, distances) are
+    elementwise over rows and therefore layout-agnostic."""
+    return t.permute(0, 2, 3, 1).reshape(-1) if t.dim() == 4 else t.reshape(-1)
+
+
 def flat_size(module_or_sd) -> int:
     """Row length: end of the last tensor, rounded up to 4 floats for models with aligned (big) tensors so that every
     row of a dense ``[C, M, P]`` arena starts on a 16-byte boundary too."""
@@ -82,11 +92,11 @@ def flatten_state_dict(sd: Dict[str, torch.Tensor], out: torch.Tensor = None) ->
     dev = vals[0].device if vals else "cpu"
     dense = all(spec[i][3] + spec[i][4] == spec[i + 1][3] for i in range(len(spec) - 1))
     if dense and (not spec or spec[-1][3] + spec[-1][4] == total):   # dense layout: one cat
-        flat = torch.cat([v.reshape(-1).to(torch.float32) for v in vals]) if vals else torch.zeros(0)
+        flat = torch.cat([flat_view(v).to(torch.float32) for v in vals]) if vals else torch.zeros(0)
     else:
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
         for (_, _, _, off, n), v in zip(spec, vals):
-            flat[off:off + n] = v.reshape(-1).to(torch.float32)
+            flat[off:off + n] = flat_view(v).to(torch.float32)
     if out is not None:
         out.copy_(flat)
         return out
@@ -96,7 +106,12 @@ def flatten_state_dict(sd: Dict[str, torch.Tensor], out: torch.Tensor = None) ->
 def unflatten_to_state_dict(flat: torch.Tensor, spec) -> "OrderedDict[str, torch.Tensor]":
     sd = OrderedDict()
     for k, shape, dtype, off, n in spec:
-        sd[k] = flat[off:off + n].reshape(shape).to(dtype)
+        seg = flat[off:off + n]
+        if len(shape) == 4:     # stored (O, kh, kw, I): a logical [O, I, kh, kw] VIEW with channels_last strides (see flat_view)
+            v = seg.reshape(shape[0], shape[2], shape[3], shape[1]).permute(0, 3, 1, 2)
+        else:
+            v = seg.reshape(shape)
+        sd[k] = v.to(dtype)
     return sd
 
 

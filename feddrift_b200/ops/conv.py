@@ -61,10 +61,20 @@ def _nhwc_bf16(ext, t: torch.Tensor, gate=None) -> torch.Tensor:
     return tb if gate is None else tb * (gate > 0)
 
 
+def _weight_ohwi(weight: torch.Tensor) -> torch.Tensor:
+    """fp32 [Cout, kh, kw, Cin] contiguous: a free view when the parameter is stored channels_last (the flat-row layout of
+    ``models.utils.flat_view`` and the layout ``TcConv2d`` allocates), one transposing copy otherwise."""
+    w = weight.detach()
+    if w.dtype != torch.float32:
+        w = w.float()
+    return w.permute(0, 2, 3, 1).contiguous()       # no-op for channels_last storage
+
+
 class _ConvIgemmFn(torch.autograd.Function):
     """Implicit-GEMM convolution.  Per direction the kernel is picked by shape: the GEMM mainloop with a TMA-im2col producer
     (``gemm_tc.cu`` conv modes; bf16 NHWC operands, Cin % 64 == 0 — every body layer of the ResNets) or the software-gather
-    kernels of ``conv_igemm.cu`` (Cin % 32, strided data gradients)."""
+    kernels of ``conv_igemm.cu`` (Cin % 32, strided data gradients).  The weight operand of forward AND data gradient is one
+    bf16 cast of the channels_last parameter; the weight gradient is reduce-added into the channels_last ``.grad`` in place."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, relu: bool):
@@ -73,18 +83,17 @@ class _ConvIgemmFn(torch.autograd.Function):
         IGEMM_CALLS["fwd"] += 1
         ext = _ext.load(required=True)
         Co, Ci, kh, kw = weight.shape
-        wq, wq_t = ext.conv_pack_weights(weight.detach().float().contiguous())     # both tensor-core packs, one launch
+        wq = ext.conv_cast_bf16(_weight_ohwi(weight), None)            # bf16 [Cout][kh][kw][Cin]
         bdet = bias.detach() if bias is not None else None
         tma_in = tma_eligible(Ci, stride, padding, (kh, kw))          # forward and weight gradient gather from x
-        xh = xb = None
         if tma_in:
             IGEMM_CALLS["tma_fwd"] += 1
-            xb = _nhwc_bf16(ext, x)
-            y = ext.conv_tma_fwd(xb, wq, bdet, stride[0], padding[0], bool(relu), False)
+            xs = _nhwc_bf16(ext, x)
+            y = ext.conv_tma_fwd(xs, wq, bdet, stride[0], padding[0], bool(relu))
         else:
-            xh = _nhwc(x)
-            y = ext.conv_igemm_fwd(xh, wq, bdet, stride[0], padding[0], padding[1], bool(relu))
-        ctx.save_for_backward(xb if tma_in else xh, wq_t, y if relu else None)
+            xs = _nhwc(x)
+            y = ext.conv_igemm_fwd(xs, wq, bdet, stride[0], padding[0], padding[1], bool(relu))
+        ctx.save_for_backward(xs, wq, y if relu else None)
         ctx.weight_ref = weight if isinstance(weight, torch.nn.Parameter) else None
         ctx.geom = (stride, padding, tuple(weight.shape), tuple(x.shape[2:]))
         ctx.relu, ctx.has_bias, ctx.tma_in = relu, bias is not None, tma_in
@@ -93,12 +102,13 @@ class _ConvIgemmFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         ext = _ext.load(required=True)
-        xs, wq_t, y = ctx.saved_tensors
+        xs, wq, y = ctx.saved_tensors
         stride, padding, (Co, Ci, kh, kw), (H, W) = ctx.geom
         tma_dgrad = (ctx.needs_input_grad[0] and stride[0] == 1 and padding[0] <= kh - 1
                      and tma_eligible(Co, stride, padding, (kh, kw)))
         tma_wgrad = ctx.needs_input_grad[1] and ctx.tma_in
-        need_f32 = (ctx.needs_input_grad[0] and not tma_dgrad) or (ctx.has_bias and ctx.needs_input_grad[2])
+        need_f32 = ((ctx.needs_input_grad[0] and not tma_dgrad) or (ctx.needs_input_grad[1] and not tma_wgrad)
+                    or (ctx.has_bias and ctx.needs_input_grad[2]))
         g = gb = None
         if need_f32:
             g = _nhwc(gy)
@@ -109,31 +119,27 @@ class _ConvIgemmFn(torch.autograd.Function):
         gx = gw = gbias = None
         if ctx.needs_input_grad[0]:
             IGEMM_CALLS["dgrad"] += 1
-            if tma_dgrad:      # stride-1 data gradient = forward convolution of dY with the tap-flipped [Cin][R][S][Cout] pack
+            if tma_dgrad:      # stride-1 data gradient = forward convolution of dY; the forward pack is read MN-major, taps flipped
                 IGEMM_CALLS["tma_dgrad"] += 1
-                gx = ext.conv_tma_fwd(gb, wq_t, None, 1, kh - 1 - padding[0], False, True).permute(0, 3, 1, 2)
+                gx = ext.conv_tma_dgrad(gb, wq, padding[0]).permute(0, 3, 1, 2)
             else:
-                gx = ext.conv_igemm_dgrad(g, wq_t, H, W, stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
+                gx = ext.conv_igemm_dgrad(g, ext.conv_pack_t(wq), H, W, stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             IGEMM_CALLS["wgrad"] += 1
             wp = ctx.weight_ref
-            acc = wp.grad if (wp is not None and wp.grad is not None and wp.grad.is_contiguous() and wp.grad.dtype == torch.float32
-                              and wp.grad.shape == wp.shape and wp.grad.is_cuda) else None
-            # with a preallocated .grad (the federated executor binds every parameter's .grad to its slice of the flat, zeroed
-            # gradient row) the kernel adds straight into it: no zero-fill launch, no AccumulateGrad add launch
+            acc = None
+            if (wp is not None and wp.grad is not None and wp.grad.is_cuda and wp.grad.dtype == torch.float32 and wp.grad.shape == wp.shape
+                    and wp.grad.is_contiguous(memory_format=torch.channels_last)):
+                # a preallocated channels_last .grad (the federated executor binds every parameter's .grad to its segment of the
+                # flat, zeroed gradient row): the kernel reduce-adds straight into it — no zero-fill, no AccumulateGrad launch
+                acc = wp.grad.permute(0, 2, 3, 1)
+            buf = acc if acc is not None else torch.zeros(Co, kh, kw, Ci, dtype=torch.float32, device=xs.device)
             if tma_wgrad:
                 IGEMM_CALLS["tma_wgrad"] += 1
-                gw = ext.conv_tma_wgrad(xs, gb, kh, kw, stride[0], padding[0], acc)                    # OIHW
+                ext.conv_tma_wgrad(xs, gb, buf, stride[0], padding[0])
             else:
-                if ctx.tma_in:                          # forward ran on the TMA path but this shape's wgrad cannot: fp32 x again
-                    xs = xs.float()
-                if g is None:
-                    g = _nhwc(gy)
-                    if ctx.relu:
-                        g = g * (y > 0)
-                gw = ext.conv_igemm_wgrad(xs, g, kh, kw, stride[0], padding[0], padding[1], acc)       # OIHW
-            if acc is not None:
-                gw = None
+                ext.conv_igemm_wgrad(xs, g, kh, kw, stride[0], padding[0], padding[1], buf, True)
+            gw = None if acc is not None else buf.permute(0, 3, 1, 2)          # logical OIHW view of the channels_last buffer
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gbias = g.sum((0, 1, 2))
         return gx, gw, gbias, None, None, None
@@ -184,12 +190,16 @@ class TcConv2d(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.stride, self.padding = _pair(kernel_size), _pair(stride), _pair(padding)
         self.dilation, self.groups, self.activation = _pair(dilation), groups, activation
-        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size))
+        # channels_last storage ([Cout][kh][kw][Cin]) = the K-major operand layout of the implicit-GEMM kernels
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size).contiguous(memory_format=torch.channels_last))
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
         self.reset_parameters()
 
     def reset_parameters(self) -> None:  # identical init law to nn.Conv2d
-        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        w = torch.empty(self.weight.shape)                    # drawn in logical order: same values as nn.Conv2d for a given seed
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        with torch.no_grad():
+            self.weight.copy_(w)
         if self.bias is not None:
             fan_in = self.weight.shape[1] * self.kernel_size[0] * self.kernel_size[1]
             bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
@@ -229,15 +239,15 @@ class TcConv2d(nn.Module):
 
 
 def convert_convs_(module: nn.Module) -> nn.Module:
-    """Replace every eligible ``nn.Conv2d`` of ``module`` (in place) by a :class:`TcConv2d` sharing the same parameters —
-    state-dict keys, shapes and values are unchanged.  Used for the torchvision / model-zoo networks so that their 3×3 and
+    """Replace every eligible ``nn.Conv2d`` of ``module`` (in place) by a :class:`TcConv2d` with the same parameter values (the
+    weight is re-laid-out channels_last) — state-dict keys, shapes and values are unchanged.  Used for the torchvision / model-zoo networks so that their 3×3 and
     1×1 body convolutions run on the implicit-GEMM tcgen05 kernels (stems with 1 or 3 input channels stay library convs)."""
     for name, child in list(module.named_children()):
         if type(child) is nn.Conv2d and child.padding_mode == "zeros" and not isinstance(child.padding, str) and \
                 igemm_eligible(child.in_channels, child.out_channels, _pair(child.stride), _pair(child.dilation), child.groups):
             tc = TcConv2d(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding, child.dilation,
                           child.groups, bias=child.bias is not None)
-            tc.weight = child.weight
+            tc.weight = nn.Parameter(child.weight.detach().contiguous(memory_format=torch.channels_last), requires_grad=child.weight.requires_grad)
             tc.bias = child.bias
             setattr(module, name, tc)
         else:

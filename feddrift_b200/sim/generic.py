@@ -416,12 +416,13 @@ def _bind(mod, bank, row):
 
 
 def _flat_grads(mod, bank, row):
+    from ..models.utils import flat_view
     g = torch.zeros_like(row)
     grads = dict(mod.named_parameters())
     for k, shape, dtype, off, n in bank.spec:
         p = grads.get(k)
         if p is not None and p.grad is not None:
-            g[off:off + n] = p.grad.reshape(-1)
+            g[off:off + n] = flat_view(p.grad)
     return g
 
 

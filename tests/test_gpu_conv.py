@@ -37,22 +37,59 @@ def test_conv_tma_ops_direct_and_gated_cast():
     assert torch.equal(ext.conv_cast_bf16(odd, None), odd.bfloat16())
     w = torch.randn(Co, Ci, k, k, device="cuda") / (Ci * k * k) ** 0.5
     xb = ext.conv_cast_bf16(x, None)
-    wq, wq_t = ext.conv_pack_weights(w)
+    wq = ext.conv_cast_bf16(w.permute(0, 2, 3, 1).contiguous(), None)            # bf16 [Cout][kh][kw][Cin]
     xr = xb.float().permute(0, 3, 1, 2).requires_grad_(True)
     wr = w.bfloat16().float().requires_grad_(True)
     ref = F.conv2d(xr, wr, None, st, pad)
-    y = ext.conv_tma_fwd(xb, wq, None, st, pad, True, False)
+    y = ext.conv_tma_fwd(xb, wq, None, st, pad, True)
     assert (y.permute(0, 3, 1, 2) - F.relu(ref)).abs().max().item() < 1e-3
     dy = torch.randn_like(y)
     dyb = ext.conv_cast_bf16(dy, None)
     gx, gw = torch.autograd.grad(ref, (xr, wr), dyb.float().permute(0, 3, 1, 2))
-    dx = ext.conv_tma_fwd(dyb, wq_t, None, 1, k - 1 - pad, False, True)
+    dx = ext.conv_tma_dgrad(dyb, wq, pad)                                          # reads the forward pack MN-major
+    assert dx.shape == (N, H, W, Ci)
     assert (dx.permute(0, 3, 1, 2) - gx).abs().max().item() < 1e-3 * gx.abs().max().item() + 1e-4
-    dw = ext.conv_tma_wgrad(xb, dyb, k, k, st, pad, None)
-    assert (dw - gw).abs().max().item() < 1e-3 * gw.abs().max().item() + 1e-4
-    acc = torch.full_like(dw, 2.0)
-    ext.conv_tma_wgrad(xb, dyb, k, k, st, pad, acc)
-    assert (acc - 2.0 - gw).abs().max().item() < 1e-3 * gw.abs().max().item() + 1e-4
+    dw = torch.full((Co, k, k, Ci), 2.0, device="cuda")                            # the kernel ADDS into the channels_last buffer
+    ext.conv_tma_wgrad(xb, dyb, dw, st, pad)
+    assert (dw.permute(0, 3, 1, 2) - 2.0 - gw).abs().max().item() < 1e-3 * gw.abs().max().item() + 1e-4
+    # software-gather kernels with the same operand conventions
+    wq_t = ext.conv_pack_t(wq)
+    assert torch.equal(wq_t, wq.permute(3, 1, 2, 0).contiguous())
+    dw2 = torch.zeros(Co, k, k, Ci, device="cuda")
+    ext.conv_igemm_wgrad(xb.float(), dyb.float(), k, k, st, pad, pad, dw2, True)
+    assert (dw2.permute(0, 3, 1, 2) - gw).abs().max().item() < 1e-3 * gw.abs().max().item() + 1e-4
+
+
+def test_channels_last_parameter_grad_is_accumulated_in_place():
+    """TcConv2d stores its weight channels_last; a preset channels_last .grad (the executor's flat gradient row) is the
+    buffer the wgrad kernel reduce-adds into; a contiguous OIHW weight (plain tensor) still works through one transposing copy."""
+    from feddrift_b200.ops import conv as C
+    from feddrift_b200.ops.conv import TcConv2d
+    torch.manual_seed(0)
+    m = TcConv2d(64, 64, 3, padding=1, bias=False).cuda()
+    assert m.weight.is_contiguous(memory_format=torch.channels_last)
+    ref = torch.nn.Conv2d(64, 64, 3, padding=1, bias=False)
+    torch.manual_seed(0)
+    ref.reset_parameters()
+    torch.manual_seed(0)
+    m2 = TcConv2d(64, 64, 3, padding=1, bias=False)
+    assert torch.equal(m2.weight.detach(), ref.weight.detach())                    # same values as nn.Conv2d for a given seed
+    x = torch.randn(2, 64, 9, 9, device="cuda", requires_grad=True)
+    g0 = torch.full_like(m.weight, 0.5)                                            # preserves channels_last
+    m.weight.grad = g0
+    y = m(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    assert m.weight.grad is g0
+    xr = x.detach().bfloat16().float()
+    wr = m.weight.detach().bfloat16().float().contiguous().requires_grad_(True)
+    gw, = torch.autograd.grad(F.conv2d(xr, wr, None, 1, 1), wr, dy.bfloat16().float())
+    assert (g0 - 0.5 - gw).abs().max().item() < 2e-3 * gw.abs().max().item() + 1e-4
+    wc = m.weight.detach().contiguous().clone().requires_grad_(True)               # contiguous OIHW weight
+    y2 = C._ConvIgemmFn.apply(x, wc, None, (1, 1), (1, 1), False)
+    assert (y2 - y).abs().max().item() < 1e-5
+    gwc, = torch.autograd.grad(y2, wc, dy)
+    assert (gwc - gw).abs().max().item() < 2e-3 * gw.abs().max().item() + 1e-4
 
 
 @pytest.mark.parametrize("geom", GEOMS)

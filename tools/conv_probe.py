@@ -46,7 +46,10 @@ for B, cin, cout, k, stride, pad, hw in ((50, 32, 64, 3, 1, 0, 26), (32, 64, 64,
     xcl = x.contiguous(memory_format=torch.channels_last)
     xh = xcl.permute(0, 2, 3, 1)                                   # NHWC view
     w = tc.weight.detach().contiguous()
-    wpk = ext.conv_pack_weights(w)
+    w_ohwi = tc.weight.detach().permute(0, 2, 3, 1).contiguous()        # free view: TcConv2d stores its weight channels_last
+    wq = ext.conv_cast_bf16(w_ohwi, None)
+    wq_t = ext.conv_pack_t(wq)
+    dwbuf = torch.zeros(cout, k, k, cin, device="cuda")
     Ho = (hw + 2 * pad - k) // stride + 1
     dyh = torch.randn(B, Ho, Ho, cout, device="cuda")
     dy_nchw = dyh.permute(0, 3, 1, 2).contiguous()
@@ -55,21 +58,21 @@ for B, cin, cout, k, stride, pad, hw in ((50, 32, 64, 3, 1, 0, 26), (32, 64, 64,
     xb, wb, dyb = xcl.bfloat16(), wcl.bfloat16(), dy_cl.bfloat16()
     mask = [True, True, False]
     r = {"shape": f"B{B} {cin}->{cout} k{k} s{stride} p{pad} {hw}x{hw}", "GFLOP_per_dir": 2.0 * B * Ho * Ho * cout * cin * k * k / 1e9}
-    r["gather_fwd_us"] = timeit(lambda: ext.conv_igemm_fwd(xh, ext.conv_pack_weights(w)[0], tc.bias.detach(), stride, pad, pad, False))
-    r["gather_dgrad_us"] = timeit(lambda: ext.conv_igemm_dgrad(dyh, wpk[1], hw, hw, stride, pad, pad))
-    r["gather_wgrad_us"] = timeit(lambda: ext.conv_igemm_wgrad(xh, dyh, k, k, stride, pad, pad, None))
+    r["gather_fwd_us"] = timeit(lambda: ext.conv_igemm_fwd(xh, ext.conv_cast_bf16(w_ohwi, None), tc.bias.detach(), stride, pad, pad, False))
+    r["gather_dgrad_us"] = timeit(lambda: ext.conv_igemm_dgrad(dyh, wq_t, hw, hw, stride, pad, pad))
+    r["gather_wgrad_us"] = timeit(lambda: ext.conv_igemm_wgrad(xh, dyh, k, k, stride, pad, pad, dwbuf, True))
     r["ours_fwd_us"], r["ours_dgrad_us"], r["ours_wgrad_us"] = r["gather_fwd_us"], r["gather_dgrad_us"], r["gather_wgrad_us"]
     if cin % 64 == 0:      # TMA-im2col GEMM path: bf16 NHWC operands; the casts are charged to the directions that need them
         xh_c = xh.contiguous()
         xbh, dybh = ext.conv_cast_bf16(xh_c, None), ext.conv_cast_bf16(dyh, None)
         r["cast_x_us"] = timeit(lambda: ext.conv_cast_bf16(xh_c, None))
         r["cast_dy_us"] = timeit(lambda: ext.conv_cast_bf16(dyh, None))
-        r["tma_fwd_us"] = timeit(lambda: ext.conv_tma_fwd(xbh, ext.conv_pack_weights(w)[0], tc.bias.detach(), stride, pad, False, False))
-        r["tma_wgrad_us"] = timeit(lambda: ext.conv_tma_wgrad(xbh, dybh, k, k, stride, pad, None))
+        r["tma_fwd_us"] = timeit(lambda: ext.conv_tma_fwd(xbh, ext.conv_cast_bf16(w_ohwi, None), tc.bias.detach(), stride, pad, False))
+        r["tma_wgrad_us"] = timeit(lambda: ext.conv_tma_wgrad(xbh, dybh, dwbuf, stride, pad))
         r["ours_fwd_us"] = r["tma_fwd_us"] + r["cast_x_us"]
         r["ours_wgrad_us"] = r["tma_wgrad_us"] + r["cast_dy_us"]
         if stride == 1 and cout % 64 == 0:
-            r["tma_dgrad_us"] = timeit(lambda: ext.conv_tma_fwd(dybh, wpk[1], None, 1, k - 1 - pad, False, True))
+            r["tma_dgrad_us"] = timeit(lambda: ext.conv_tma_dgrad(dybh, wq, pad))
             r["ours_dgrad_us"] = r["tma_dgrad_us"]
     r["cudnn_fp32_fwd_us"] = timeit(lambda: F.conv2d(x, w, tc.bias.detach(), stride, pad))
     r["cudnn_fp32_bwd_us"] = timeit(lambda: torch.ops.aten.convolution_backward(dy_nchw, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, mask))

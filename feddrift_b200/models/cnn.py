@@ -36,6 +36,10 @@ class CNN_OriginalFedAvg(nn.Module):
         self.linear_2 = TcLinear(512, 10 if only_digits else 62)
         self.softmax = nn.Softmax(dim=1)
 
+    @staticmethod
+    def stack_input(x):                     # [npairs, B, 784 | 28, 28] → [npairs, B, 1, 28, 28] (sim/stacked.py)
+        return x.reshape(x.shape[0], x.shape[1], 1, 28, 28)
+
     def forward(self, x):
         if x.dim() == 2:
             x = x.reshape(x.shape[0], 28, 28)
@@ -59,8 +63,12 @@ class CNN_DropOut(nn.Module):
         self.linear_2 = TcLinear(128, 10 if only_digits else 62)
         self.softmax = nn.Softmax(dim=1)
 
+    @staticmethod
+    def stack_input(x):                     # [npairs, B, 784 | 28, 28] → [npairs, B, 1, 28, 28] (sim/stacked.py)
+        return x.reshape(x.shape[0], x.shape[1], 1, 28, 28)
+
     def forward(self, x):
-        x = x.reshape(x.shape[0], 1, 28, 28)
+        x = x.reshape(x.shape[0], -1, 28, 28)     # 1 channel — or one per stacked (client, model) pair
         x = self.conv2d_2(self.conv2d_1(x))
         x = self.dropout_1(self.max_pooling(x))
         x = self.linear_1(self.flatten(x))

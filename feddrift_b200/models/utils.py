@@ -62,14 +62,22 @@ def flat_spec(module_or_sd) -> List[Tuple[str, torch.Size, torch.dtype, int, int
     return out
 
 
+def ohwi_stored(shape) -> bool:
+    """Which 4-D tensors live in the flat rows in (O, kh, kw, I) order: the convolution weights the implicit-GEMM tensor-core
+    kernels can take (channel counts multiples of 32, square filter > 1×1).  A pure function of the shape, so every flatten /
+    unflatten of a state_dict agrees.  (1×1 filters have the same memory order either way; stems and depthwise filters stay
+    in logical order and on the library path.)"""
+    return len(shape) == 4 and shape[0] % 32 == 0 and shape[1] % 32 == 0 and shape[2] == shape[3] and shape[2] > 1
+
+
 def flat_view(t: torch.Tensor) -> torch.Tensor:
-    """The tensor's elements in FLAT-ROW ORDER.  4-D tensors (convolution weights ``[O, I, kh, kw]``) are stored in the row in
-    (O, kh, kw, I) order — the ``channels_last`` memory format, which is the K-major operand layout of the implicit-GEMM
+    """The tensor's elements in FLAT-ROW ORDER.  Tensor-core-eligible convolution weights ``[O, I, kh, kw]`` (:func:`ohwi_stored`)
+    are stored in the row in (O, kh, kw, I) order — the ``channels_last`` memory format, which is the K-major operand layout of the implicit-GEMM
     convolution kernels: the forward / data-gradient weight operand is then a plain bf16 cast of the row segment and the
     weight-gradient GEMM reduce-adds straight into the flat gradient row (no per-step transposing pack, no un-permute).
     Everything else is stored in logical (row-major) order.  Row operations (aggregation, optimizer, norms, distances) are
     elementwise over rows and therefore layout-agnostic."""
-    return t.permute(0, 2, 3, 1).reshape(-1) if t.dim() == 4 else t.reshape(-1)
+    return t.permute(0, 2, 3, 1).reshape(-1) if ohwi_stored(t.shape) else t.reshape(-1)
 
 
 def flat_size(module_or_sd) -> int:
@@ -107,7 +115,10 @@ def unflatten_to_state_dict(flat: torch.Tensor, spec) -> "OrderedDict[str, torch
     sd = OrderedDict()
     for k, shape, dtype, off, n in spec:
         seg = flat[off:off + n]
-        if len(shape) == 4:     # stored (O, kh, kw, I): a logical [O, I, kh, kw] VIEW with channels_last strides (see flat_view)
+        if ohwi_stored(shape):
+            # stored (O, kh, kw, I): a logical [O, I, kh, kw] VIEW with channels_last strides (see flat_view); such tensors must
+            # be consumed by TcConv2d, whose CPU path canonicalises memory formats (oneDNN's convolution backward corrupts the
+            # heap for channels_last inputs of 1×1 stride-2 filters) — ModelBank converts its template accordingly
             v = seg.reshape(shape[0], shape[2], shape[3], shape[1]).permute(0, 3, 1, 2)
         else:
             v = seg.reshape(shape)

@@ -27,6 +27,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _ext
+from ..models.utils import ohwi_stored as _ohwi
 
 TC_CONV_CALLS = 0
 IGEMM_CALLS = {"fwd": 0, "dgrad": 0, "wgrad": 0, "tma_fwd": 0, "tma_dgrad": 0, "tma_wgrad": 0}
@@ -183,6 +184,11 @@ class _TcConvFn(torch.autograd.Function):
         return gx, gw, gbias, None, None, None
 
 
+def stacked_eligible(layer, x: torch.Tensor) -> bool:
+    """Grouped (one group per stacked pair) implicit-GEMM path of ``sim/stacked.py::StackedConv2d``."""
+    return False
+
+
 class TcConv2d(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, kernel_size, stride=1, padding=0, dilation=1, groups: int = 1,
                  bias: bool = True, activation: str = "none"):
@@ -190,8 +196,10 @@ class TcConv2d(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.stride, self.padding = _pair(kernel_size), _pair(stride), _pair(padding)
         self.dilation, self.groups, self.activation = _pair(dilation), groups, activation
-        # channels_last storage ([Cout][kh][kw][Cin]) = the K-major operand layout of the implicit-GEMM kernels
-        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size).contiguous(memory_format=torch.channels_last))
+        # channels_last storage ([Cout][kh][kw][Cin]) = the K-major operand layout of the implicit-GEMM kernels = the layout of
+        # the flat parameter rows for these shapes (models.utils.ohwi_stored)
+        w = torch.empty(out_channels, in_channels // groups, *self.kernel_size)
+        self.weight = nn.Parameter(w.contiguous(memory_format=torch.channels_last) if _ohwi(w.shape) else w)
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
         self.reset_parameters()
 
@@ -230,7 +238,10 @@ class TcConv2d(nn.Module):
             return _ConvIgemmFn.apply(x, self.weight, self.bias, self.stride, self.padding, relu)
         if self._eligible(x) and os.environ.get("FDB_CONV_IM2COL") == "1":
             return _TcConvFn.apply(x, self.weight, self.bias, self.stride, self.padding, relu)
-        y = F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        w = self.weight
+        if not x.is_cuda:       # CPU: canonical (contiguous NCHW) formats only — see models.utils.unflatten_to_state_dict
+            x, w = x.contiguous(), w.contiguous()
+        y = F.conv2d(x, w, self.bias, self.stride, self.padding, self.dilation, self.groups)
         return F.relu(y) if relu else y
 
     def extra_repr(self) -> str:
@@ -239,15 +250,19 @@ class TcConv2d(nn.Module):
 
 
 def convert_convs_(module: nn.Module) -> nn.Module:
-    """Replace every eligible ``nn.Conv2d`` of ``module`` (in place) by a :class:`TcConv2d` with the same parameter values (the
-    weight is re-laid-out channels_last) — state-dict keys, shapes and values are unchanged.  Used for the torchvision / model-zoo networks so that their 3×3 and
+    """Replace every ``nn.Conv2d`` of ``module`` whose shape the tensor-core kernels take — or whose weight the flat rows store
+    channels_last (``models.utils.ohwi_stored``; ``TcConv2d`` is the layer that consumes that layout safely on CPU too) — in place
+    by a :class:`TcConv2d` with the same parameter values; state-dict keys, shapes and values are unchanged.  Used for the torchvision / model-zoo networks so that their 3×3 and
     1×1 body convolutions run on the implicit-GEMM tcgen05 kernels (stems with 1 or 3 input channels stay library convs)."""
     for name, child in list(module.named_children()):
         if type(child) is nn.Conv2d and child.padding_mode == "zeros" and not isinstance(child.padding, str) and \
-                igemm_eligible(child.in_channels, child.out_channels, _pair(child.stride), _pair(child.dilation), child.groups):
+                (igemm_eligible(child.in_channels, child.out_channels, _pair(child.stride), _pair(child.dilation), child.groups)
+                 or _ohwi(child.weight.shape)):
             tc = TcConv2d(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding, child.dilation,
                           child.groups, bias=child.bias is not None)
-            tc.weight = nn.Parameter(child.weight.detach().contiguous(memory_format=torch.channels_last), requires_grad=child.weight.requires_grad)
+            wd = child.weight.detach()
+            tc.weight = nn.Parameter(wd.contiguous(memory_format=torch.channels_last) if _ohwi(wd.shape) else wd,
+                                     requires_grad=child.weight.requires_grad)
             tc.bias = child.bias
             setattr(module, name, tc)
         else:

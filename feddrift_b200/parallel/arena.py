@@ -36,6 +36,8 @@ class ModelBank:
 
     def __init__(self, template: nn.Module, num_models: int, device="cpu", storage: Optional[torch.Tensor] = None):
         self.template = copy.deepcopy(template).to("cpu")
+        from ..ops.conv import convert_convs_
+        convert_convs_(self.template)    # conv weights the rows store channels_last are consumed through TcConv2d (same state-dict keys)
         self.spec = mutils.flat_spec(self.template)
         self.P = mutils.flat_size(self.template)
         self.stride = padded(self.P)

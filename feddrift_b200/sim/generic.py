@@ -63,8 +63,10 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
         active = (st["train_count"] > 0).any(dim=1) if st["sample_mode"] == "index" else (Wt != 0).any(dim=1)
         cl.n.zero_()
         world, rank = _world_rank(sim)
-        from . import lstm_exec
-        batched = lstm_exec.applicable(sim, feat_mask)   # LSTM federations: all pairs advance in the same few launches
+        from . import lstm_exec, stacked
+        lstm_b = lstm_exec.applicable(sim, feat_mask)    # LSTM federations: all pairs advance in the same few launches
+        stack_b = not lstm_b and stacked.applicable(sim, feat_mask)   # conv nets: all pairs in one channel-stacked network
+        batched = lstm_b or stack_b
         bpairs, n_host = [], np.zeros((C, M), dtype=np.float32)
         slots = [] if batched else _stream_slots(sim)    # K side streams: independent (client, model) pairs replay concurrently
         pair_i = 0
@@ -93,7 +95,12 @@ def run_rounds_generic(sim, rounds: int) -> Dict[str, torch.Tensor]:
                 cl.n[c, m] = n_cm
         _join_slots(sim, slots)
         if batched:
-            lstm_exec.train_pairs(sim, bpairs, seed, rnd, E, use_adam, lr, a.wd)
+            if lstm_b:
+                lstm_exec.train_pairs(sim, bpairs, seed, rnd, E, use_adam, lr, a.wd)
+            elif not stacked.train_pairs(sim, bpairs, seed, rnd, E, use_adam, lr, a.wd):
+                for (c, m, sampler) in bpairs:            # unequal batch sizes: the per-pair path
+                    cl.params[c, m].copy_(bank.theta[m])
+                    _local_steps(sim, c, m, _lazy_client_xy(Xc_all, data, c, T1, S), sampler, seed, rnd, E, use_adam, lr, a.wd, feat_mask)
             cl.n.copy_(torch.from_numpy(n_host), non_blocking=True)
         # raw-update hooks (CFL family) may veto the aggregation of this round
         skip = False

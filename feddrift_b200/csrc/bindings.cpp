@@ -666,53 +666,82 @@ Tensor conv_cast_bf16(Tensor x, c10::optional<Tensor> gate) {
     CHECK_OK(fdb::conv_cast_bf16_launch(x.data_ptr<float>(), g, out.data_ptr(), x.numel(), cur_stream()), "conv_cast_bf16");
     return out;
 }
-// xb: bf16 NHWC [N, H, W, C]; wq: bf16 [Cout][R][S][C]; -> fp32 NHWC [N, P, Q, Cout] = act(conv(x, w) + bias)
-Tensor conv_tma_fwd(Tensor xb, Tensor wq, c10::optional<Tensor> bias, int64_t stride, int64_t pad, bool relu) {
+// strided rows [n, numel] fp32 (stride(1) == 1; the staged parameter rows of the stacked pairs) -> contiguous bf16 [n, numel]
+Tensor conv_cast_rows_bf16(Tensor x) {
+    CHECK_CUDA_F32(x);
+    TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.size(1) % 8 == 0 && x.stride(0) % 4 == 0 &&
+                (reinterpret_cast<uintptr_t>(x.data_ptr<float>()) & 15) == 0, "conv_cast_rows_bf16: [n, numel] rows, 16-byte aligned, numel % 8 == 0");
+    c10::cuda::CUDAGuard guard(x.device());
+    auto out = torch::empty({x.size(0), x.size(1)}, x.options().dtype(torch::kBFloat16));
+    CHECK_OK(fdb::conv_cast_rows_bf16_launch(x.data_ptr<float>(), x.stride(0), out.data_ptr(), (int)x.size(0), x.size(1), cur_stream()), "conv_cast_rows_bf16");
+    return out;
+}
+// xb: bf16 NHWC [N, H, W, G·C]; wq: bf16 [G·Cout][R][S][C]; -> fp32 NHWC [N, P, Q, G·Cout] = act(conv(x, w) + bias), G groups
+Tensor conv_tma_fwd(Tensor xb, Tensor wq, c10::optional<Tensor> bias, int64_t stride, int64_t pad, bool relu, int64_t groups) {
     TORCH_CHECK(xb.is_cuda() && xb.scalar_type() == torch::kBFloat16 && xb.dim() == 4 && xb.is_contiguous(), "conv_tma_fwd: xb must be contiguous bf16 NHWC");
     TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kBFloat16 && wq.dim() == 4 && wq.is_contiguous(), "conv_tma_fwd: wq must be bf16 [K,R,S,C]");
-    const int N = (int)xb.size(0), H = (int)xb.size(1), W = (int)xb.size(2), C = (int)xb.size(3);
-    const int K = (int)wq.size(0), R = (int)wq.size(1), S = (int)wq.size(2);
-    TORCH_CHECK(wq.size(3) == C && C % 64 == 0 && K % 8 == 0 && R == S, "conv_tma_fwd: needs Cin % 64 == 0, Cout % 8 == 0, square filter");
+    const int G = (int)groups;
+    const int N = (int)xb.size(0), H = (int)xb.size(1), W = (int)xb.size(2), C = (int)wq.size(3);
+    const int R = (int)wq.size(1), S = (int)wq.size(2);
+    TORCH_CHECK(G >= 1 && wq.size(0) % G == 0 && xb.size(3) == (int64_t)G * C, "conv_tma_fwd: group shapes");
+    const int K = (int)(wq.size(0) / G);
+    TORCH_CHECK(C % 64 == 0 && K % 8 == 0 && R == S && (G == 1 || K % 32 == 0), "conv_tma_fwd: needs Cin % 64 == 0, Cout % 8 == 0 (% 32 grouped), square filter");
     const int P = (H + 2 * (int)pad - R) / (int)stride + 1, Q = (W + 2 * (int)pad - S) / (int)stride + 1;
     TORCH_CHECK(P > 0 && Q > 0 && pad >= 0 && pad < 128 && stride >= 1 && stride <= 8, "conv_tma_fwd: geometry");
     c10::cuda::CUDAGuard guard(xb.device());
-    auto y = torch::empty({N, P, Q, K}, xb.options().dtype(torch::kFloat32));
+    auto y = torch::empty({N, P, Q, (int64_t)G * K}, xb.options().dtype(torch::kFloat32));
     Tensor bias_f;
     const float* bp = nullptr;
-    if (bias.has_value() && bias->defined()) { bias_f = bias->to(torch::kFloat32).contiguous(); bp = bias_f.data_ptr<float>(); }
+    if (bias.has_value() && bias->defined()) {
+        bias_f = bias->to(torch::kFloat32).contiguous();
+        TORCH_CHECK(bias_f.numel() == (int64_t)G * K, "conv_tma_fwd: bias size");
+        bp = bias_f.data_ptr<float>();
+    }
     CHECK_OK(fdb::conv_tma_fwd_launch(xb.data_ptr(), wq.data_ptr(), y.data_ptr<float>(), bp, N, H, W, C, K, R, S, P, Q, (int)pad, (int)stride,
-                                      0, relu ? 1 : 0, cur_stream()), "conv_tma_fwd (tcgen05 + TMA im2col)");
+                                      0, relu ? 1 : 0, G, cur_stream()), "conv_tma_fwd (tcgen05 + TMA im2col)");
     return y;
 }
-// stride-1 data gradient.  dyb: bf16 NHWC [N, P, Q, Cout]; wq: THE FORWARD pack bf16 [Cout][R][S][Cin] (read as an MN-major operand
-// with flipped taps); pad = the forward padding; -> dx fp32 NHWC [N, P + R - 1 - 2·pad, Q + S - 1 - 2·pad, Cin]
-Tensor conv_tma_dgrad(Tensor dyb, Tensor wq, int64_t pad) {
+// stride-1 data gradient.  dyb: bf16 NHWC [N, P, Q, G·Cout]; wq: THE FORWARD pack bf16 [G·Cout][R][S][Cin] (read as an MN-major operand
+// with flipped taps); pad = the forward padding; -> dx fp32 NHWC [N, P + R - 1 - 2·pad, Q + S - 1 - 2·pad, G·Cin]
+Tensor conv_tma_dgrad(Tensor dyb, Tensor wq, int64_t pad, int64_t groups) {
     TORCH_CHECK(dyb.is_cuda() && dyb.scalar_type() == torch::kBFloat16 && dyb.dim() == 4 && dyb.is_contiguous(), "conv_tma_dgrad: dyb must be contiguous bf16 NHWC");
     TORCH_CHECK(wq.is_cuda() && wq.scalar_type() == torch::kBFloat16 && wq.dim() == 4 && wq.is_contiguous(), "conv_tma_dgrad: wq must be bf16 [K,R,S,C]");
-    const int N = (int)dyb.size(0), P = (int)dyb.size(1), Q = (int)dyb.size(2), K = (int)dyb.size(3);
+    const int G = (int)groups;
+    const int N = (int)dyb.size(0), P = (int)dyb.size(1), Q = (int)dyb.size(2);
     const int R = (int)wq.size(1), S = (int)wq.size(2), C = (int)wq.size(3);
-    TORCH_CHECK(wq.size(0) == K && K % 64 == 0 && C % 8 == 0 && R == S && pad >= 0 && pad <= R - 1, "conv_tma_dgrad: needs Cout % 64 == 0, Cin % 8 == 0, square filter, pad <= R-1");
+    TORCH_CHECK(G >= 1 && wq.size(0) % G == 0 && dyb.size(3) == wq.size(0), "conv_tma_dgrad: group shapes");
+    const int K = (int)(wq.size(0) / G);
+    TORCH_CHECK(K % 64 == 0 && C % 8 == 0 && R == S && pad >= 0 && pad <= R - 1 && (G == 1 || C % 32 == 0),
+                "conv_tma_dgrad: needs Cout % 64 == 0, Cin % 8 == 0 (% 32 grouped), square filter, pad <= R-1");
     const int pd = R - 1 - (int)pad, H = P + 2 * pd - R + 1, W = Q + 2 * pd - S + 1;
     c10::cuda::CUDAGuard guard(dyb.device());
-    auto dx = torch::empty({N, H, W, C}, dyb.options().dtype(torch::kFloat32));
-    CHECK_OK(fdb::conv_tma_fwd_launch(dyb.data_ptr(), wq.data_ptr(), dx.data_ptr<float>(), nullptr, N, P, Q, K, C, R, S, H, W, pd, 1, 1, 0,
+    auto dx = torch::empty({N, H, W, (int64_t)G * C}, dyb.options().dtype(torch::kFloat32));
+    CHECK_OK(fdb::conv_tma_fwd_launch(dyb.data_ptr(), wq.data_ptr(), dx.data_ptr<float>(), nullptr, N, P, Q, K, C, R, S, H, W, pd, 1, 1, 0, G,
                                       cur_stream()), "conv_tma_dgrad (tcgen05 + TMA im2col)");
     return dx;
 }
-// xb: bf16 NHWC [N, H, W, C]; dyb: bf16 NHWC [N, P, Q, K]; dw_ohwi: fp32 [K, R, S, C] — the gradient is ADDED into it
-void conv_tma_wgrad(Tensor xb, Tensor dyb, Tensor dw_ohwi, int64_t stride, int64_t pad) {
+// xb: bf16 NHWC [N, H, W, G·C]; dyb: bf16 NHWC [N, P, Q, G·K]; dw: fp32 — [K, R, S, C] contiguous (G = 1) or rows [G, K·R·S·C] with
+// stride(1) == 1 and any 16-byte-multiple row stride (the flat gradient rows of the stacked pairs); the gradient is ADDED into it
+void conv_tma_wgrad(Tensor xb, Tensor dyb, Tensor dw, int64_t R, int64_t stride, int64_t pad, int64_t groups) {
     TORCH_CHECK(xb.is_cuda() && xb.scalar_type() == torch::kBFloat16 && xb.dim() == 4 && xb.is_contiguous(), "conv_tma_wgrad: xb must be contiguous bf16 NHWC");
     TORCH_CHECK(dyb.is_cuda() && dyb.scalar_type() == torch::kBFloat16 && dyb.dim() == 4 && dyb.is_contiguous(), "conv_tma_wgrad: dyb must be contiguous bf16 NHWC");
-    CHECK_CUDA_F32(dw_ohwi);
-    TORCH_CHECK(dw_ohwi.dim() == 4 && dw_ohwi.is_contiguous(), "conv_tma_wgrad: dw must be a contiguous fp32 [K,R,S,C] buffer");
-    const int N = (int)xb.size(0), H = (int)xb.size(1), W = (int)xb.size(2), C = (int)xb.size(3);
-    const int P = (int)dyb.size(1), Q = (int)dyb.size(2), K = (int)dyb.size(3);
-    const int R = (int)dw_ohwi.size(1), S = (int)dw_ohwi.size(2);
-    TORCH_CHECK(dw_ohwi.size(0) == K && dw_ohwi.size(3) == C && C % 64 == 0 && K % 8 == 0 && R == S && dyb.size(0) == N,
-                "conv_tma_wgrad: needs Cin % 64 == 0, Cout % 8 == 0, square filter");
+    CHECK_CUDA_F32(dw);
+    const int G = (int)groups;
+    TORCH_CHECK(G >= 1 && xb.size(3) % G == 0 && dyb.size(3) % G == 0 && dyb.size(0) == xb.size(0), "conv_tma_wgrad: group shapes");
+    const int N = (int)xb.size(0), H = (int)xb.size(1), W = (int)xb.size(2), C = (int)(xb.size(3) / G);
+    const int P = (int)dyb.size(1), Q = (int)dyb.size(2), K = (int)(dyb.size(3) / G);
+    const int64_t numel = (int64_t)K * R * R * C;
+    long long gstride = numel;
+    if (G == 1) {
+        TORCH_CHECK(dw.is_contiguous() && dw.numel() == numel, "conv_tma_wgrad: dw must be a contiguous fp32 [K,R,S,C] buffer");
+    } else {
+        TORCH_CHECK(dw.dim() == 2 && dw.size(0) == G && dw.size(1) == numel && dw.stride(1) == 1, "conv_tma_wgrad: dw must be rows [G, K·R·S·C]");
+        gstride = dw.stride(0);
+    }
+    TORCH_CHECK(C % 64 == 0 && K % 8 == 0, "conv_tma_wgrad: needs Cin % 64 == 0, Cout % 8 == 0");
     c10::cuda::CUDAGuard guard(xb.device());
-    CHECK_OK(fdb::conv_tma_wgrad_launch(xb.data_ptr(), dyb.data_ptr(), dw_ohwi.data_ptr<float>(), N, H, W, C, K, R, S, P, Q, (int)pad,
-                                        (int)stride, cur_stream()), "conv_tma_wgrad (tcgen05 + TMA im2col)");
+    CHECK_OK(fdb::conv_tma_wgrad_launch(xb.data_ptr(), dyb.data_ptr(), dw.data_ptr<float>(), N, H, W, C, K, (int)R, (int)R, P, Q, (int)pad,
+                                        (int)stride, G, gstride, cur_stream()), "conv_tma_wgrad (tcgen05 + TMA im2col)");
 }
 // bf16 [K][R][S][C] (the cast channels_last weight) -> bf16 [C][R][S][K] for the software-gather data-gradient kernel
 Tensor conv_pack_t(Tensor wq) {
@@ -793,6 +822,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("conv_tma_fwd", &conv_tma_fwd);
     m.def("conv_tma_wgrad", &conv_tma_wgrad);
     m.def("conv_tma_dgrad", &conv_tma_dgrad);
+    m.def("conv_cast_rows_bf16", &conv_cast_rows_bf16);
     m.def("conv_pack_t", &conv_pack_t);
     m.def("conv_igemm_dgrad", &conv_igemm_dgrad);
     m.def("conv_igemm_wgrad", &conv_igemm_wgrad);

@@ -371,6 +371,31 @@ int conv_cast_bf16_launch(const float* x, const float* gate, void* out, long lon
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
+// rows variant: x is [rows][n] with `row_stride` floats between rows (the staged parameter rows of the stacked pairs), out is
+// contiguous bf16 [rows][n]; n % 8 == 0, 16-byte aligned rows
+__global__ void conv_cast_rows_bf16_kernel(const float* __restrict__ x, long long row_stride, __nv_bfloat16* __restrict__ out, int rows, long long n8) {
+    const long long total = (long long)rows * n8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / n8, j = i - r * n8;
+        const float4* src = reinterpret_cast<const float4*>(x + r * row_stride) + 2 * j;
+        const float4 a = __ldg(src), b = __ldg(src + 1);
+        uint4 o;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(a.x, a.y); o.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(a.z, a.w); o.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(b.x, b.y); o.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(b.z, b.w); o.w = *reinterpret_cast<uint32_t*>(&t);
+        reinterpret_cast<uint4*>(out)[i] = o;
+    }
+}
+int conv_cast_rows_bf16_launch(const float* x, long long row_stride, void* out, int rows, long long n, cudaStream_t stream) {
+    if (n % 8 != 0 || row_stride % 4 != 0) return -5;
+    const long long total = (long long)rows * (n / 8);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 148 * 16));
+    conv_cast_rows_bf16_kernel<<<blocks, 256, 0, stream>>>(x, row_stride, reinterpret_cast<__nv_bfloat16*>(out), rows, n / 8);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
 // dW[k][c][r][s] (+)= src[k][r][s][c]: the TMA wgrad GEMM produces the gradient in the packed (O, H, W, I) order.  One block per
 // (k, 64-channel chunk): both the source rows and the destination range are contiguous, the transpose happens in shared memory.
 __global__ void conv_ohwi_to_oihw_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int C, int RS, int accumulate) {

@@ -40,6 +40,9 @@ struct GemmBatch { int batch, a_k0, a_kstride, b_k0, b_kstride; };
 //           (k-block kb = tap·cchunks + c-chunk); B = packed weights [Cout, R·S·C], K-major for the forward; the data gradient
 //           reads THE SAME pack as an MN-major operand (b_mn: 64(cin) × 64(cout) boxes at column tap'·Cin, taps flipped), so
 //           no transposed copy of the weights is ever made;
+//   GROUPED convolution (one group per stacked (client, model) pair, sim/stacked.py): gb.batch = groups, M / N are per-group
+//   sizes; group g reads channel chunk g·Cg + c of the NHWC tensor, weight rows g·N + n, and writes output columns g·N + n
+//   (mode 1) or slice g of the 3-D gradient map [groups][Cout][R·S·C] (mode 2, which therefore clips rows ≥ Cout);
 //   mode 2 (weight gradient): reduction over output pixels; A = dY [pixels, Cout] (MN-major tiled loads), B[(tap, c), pixel] —
 //           MN-major 64-pixel × 64-channel im2col boxes, one per 64-wide column group of the N tile.
 struct ConvIm { int mode, S, cchunks, ntaps, Q, PQ, stride, pad_h, pad_w, flip, bcols; };
@@ -128,27 +131,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         mbar_expect_tx(full_bar + s, kStageBytesA + Cfg::kStageBytesB);
                         const int tap = kb / ci.cchunks, cc = kb - tap * ci.cchunks;
                         const int r = tap / ci.S, sx = tap - r * ci.S;
-                        tma_load_im2col_4d(&map_a, full_bar + s, sa, cc * 64, cw, chh, cn, (uint16_t)sx, (uint16_t)r);
+                        const int cg = bt * ci.cchunks * 64;        // first channel of this group in the NHWC tensor / first K row
+                        tma_load_im2col_4d(&map_a, full_bar + s, sa, cg + cc * 64, cw, chh, cn, (uint16_t)sx, (uint16_t)r);
                         const int wtap = ci.flip ? ci.ntaps - 1 - tap : tap;
                         if (b_mn) {
 #pragma unroll
                             for (int h = 0; h < BN / 64; ++h)
-                                tma_load_2d(&map_b, full_bar + s, sb + h * 8192, wtap * ci.bcols + n_blk * BN + h * 64, cc * BK);
+                                tma_load_2d(&map_b, full_bar + s, sb + h * 8192, wtap * ci.bcols + n_blk * BN + h * 64, cg + cc * BK);
                         } else {
-                            tma_load_2d(&map_b, full_bar + s, sb, (wtap * ci.cchunks + cc) * BK, n_blk * BN);
+                            tma_load_2d(&map_b, full_bar + s, sb, (wtap * ci.cchunks + cc) * BK, bt * N + n_blk * BN);
                         }
                         continue;
                     }
                     if (ci.mode == 2) {
                         mbar_expect_tx(full_bar + s, kStageBytesA + (uint32_t)nvalid * 8192u);
 #pragma unroll
-                        for (int h = 0; h < BM / 64; ++h) tma_load_2d(&map_a, full_bar + s, sa + h * 8192, m_blk * BM + h * 64, kb * BK);
+                        for (int h = 0; h < BM / 64; ++h) tma_load_2d(&map_a, full_bar + s, sa + h * 8192, bt * M + m_blk * BM + h * 64, kb * BK);
                         const int p0 = kb * BK, pn = p0 / ci.PQ, prem = p0 - pn * ci.PQ, pp = prem / ci.Q, pq = prem - pp * ci.Q;
                         for (int h = 0; h < nvalid; ++h) {
                             const int j = n_blk * (BN / 64) + h, tap = j / ci.cchunks, cc = j - tap * ci.cchunks;
                             const int r = tap / ci.S, sx = tap - r * ci.S;
-                            tma_load_im2col_4d(&map_b, full_bar + s, sb + h * 8192, cc * 64, pq * ci.stride - ci.pad_w, pp * ci.stride - ci.pad_h,
-                                               pn, (uint16_t)sx, (uint16_t)r);
+                            tma_load_im2col_4d(&map_b, full_bar + s, sb + h * 8192, bt * ci.cchunks * 64 + cc * 64, pq * ci.stride - ci.pad_w,
+                                               pp * ci.stride - ci.pad_h, pn, (uint16_t)sx, (uint16_t)r);
                         }
                         continue;
                     }
@@ -213,11 +217,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // staging (conflict-free 16-byte stores) → ONE TMA tile store (or fp32 reduce-add for split-K) per
                 // 128-byte column chunk.  Staging is double-buffered per warp; TMA clips the M/N edges.
                 const int cols_per_chunk = out_fp32 ? 32 : 64;
-                const int row0 = bt * M + m_blk * BM + q * 32;   // batched outputs are stacked along the rows of D
+                // batched GEMM outputs are stacked along the rows of D; grouped convolutions write column block g·N (mode 1) or
+                // slice g of the 3-D gradient map (mode 2)
+                const int row0 = (ci.mode ? 0 : bt * M) + m_blk * BM + q * 32;
+                const int colg = ci.mode == 1 ? bt * N : 0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += cols_per_chunk, ++chunk_it) {
-                    const int col0 = n_blk * BN + c0;
-                    if (col0 >= N) break;   // warp-uniform
+                    if (n_blk * BN + c0 >= N) break;   // warp-uniform
+                    const int col0 = colg + n_blk * BN + c0;
                     uint8_t* buf = staging + (q * 2 + (chunk_it & 1)) * 4096;
                     if (lane == 0 && chunk_it >= 2) tma_store_wait_read<1>();   // the store that last read this buffer is done
                     __syncwarp();
@@ -230,7 +237,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 float x = __uint_as_float(v[j]);
-                                if (bias) x += (col0 + j < N) ? __ldg(bias + col0 + j) : 0.f;
+                                if (bias) x += (col0 - colg + j < N) ? __ldg(bias + col0 + j) : 0.f;
                                 if (relu) x = fmaxf(x, 0.f);
                                 v[j] = __float_as_uint(x);
                             }
@@ -264,7 +271,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (splits > 1 || ci.mode == 2) tma_reduce_add_2d(&map_d, buf, col0, row0);   // wgrad always accumulates
+                        if (ci.mode == 2) tma_reduce_add_3d(&map_d, buf, col0, row0, bt);   // wgrad always accumulates into slice g
+                        else if (splits > 1) tma_reduce_add_2d(&map_d, buf, col0, row0);
                         else tma_store_2d(&map_d, buf, col0, row0);
                         tma_store_commit();
                     }
@@ -438,10 +446,11 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int
 template <int BN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
                        int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream, GemmBatch gb = GemmBatch{1, 0, 0, 0, 0},
-                       ConvIm ci = ConvIm{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}) {
+                       ConvIm ci = ConvIm{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, const CUtensorMap* md_conv = nullptr) {
     CUtensorMap md;
     int tma_out = 0;
-    if (make_out_map(&md, D, M * gb.batch, N, out_fp32, &tma_out) != 0) return -7;
+    if (md_conv) { md = *md_conv; tma_out = 1; }     // convolution modes bring their own output map (grouped columns / 3-D gradient)
+    else if (make_out_map(&md, D, M * gb.batch, N, out_fp32, &tma_out) != 0) return -7;
     if (gb.batch > 1 && !tma_out) return -9;
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
@@ -531,25 +540,42 @@ int gemm_batched_mn_launch(const void* A, const void* B, float* D, int M, int N,
 }
 
 static int launch_bn(int bn, const CUtensorMap& ma, const CUtensorMap& mb, void* D, const float* bias, int M, int N, int K, int relu,
-                     int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream, const ConvIm& ci) {
-    const GemmBatch gb{1, 0, 0, 0, 0};
-    if (bn == 256) return launch_gemm<256>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci);
-    if (bn == 128) return launch_gemm<128>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci);
-    return launch_gemm<64>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci);
+                     int out_fp32, int splits, int sms, int a_mn, int b_mn, cudaStream_t stream, const ConvIm& ci, int groups,
+                     const CUtensorMap& md) {
+    const GemmBatch gb{groups, 0, 0, 0, 0};
+    if (bn == 256) return launch_gemm<256>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci, &md);
+    if (bn == 128) return launch_gemm<128>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci, &md);
+    return launch_gemm<64>(ma, mb, D, bias, M, N, K, relu, out_fp32, splits, sms, a_mn, b_mn, stream, gb, ci, &md);
 }
 
-// Implicit-GEMM convolution on the GEMM mainloop (TMA im2col producer).  xb: bf16 NHWC [N, H, W, C] (C % 64 == 0), wq: bf16
-// weights [Cout, R·S·C] (the channels_last storage of the parameter, cast), y: fp32 NHWC [N, P, Q, Cout].  Square filters,
-// symmetric padding.
+// 3-D fp32 output map of the weight-gradient GEMM: [groups][Cout][R·S·C] with `gstride` floats between the groups' gradients
+// (the flat gradient rows of the stacked pairs); 32-row × 32-column × 1 boxes, rows ≥ Cout are clipped
+static int make_wgrad_map(CUtensorMap* map, float* base, int groups, int cout, int rsc, long long gstride) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[3] = {(cuuint64_t)rsc, (cuuint64_t)cout, (cuuint64_t)groups};
+    cuuint64_t strides[2] = {(cuuint64_t)rsc * 4, (cuuint64_t)(groups > 1 ? gstride : (long long)rsc * cout) * 4};
+    cuuint32_t box[3] = {32u, 32u, 1u};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// Implicit-GEMM convolution on the GEMM mainloop (TMA im2col producer), optionally GROUPED (groups > 1: one group per stacked
+// (client, model) pair; C and Cout are PER-GROUP channel counts, the tensors hold groups·C / groups·Cout channels).
+// xb: bf16 NHWC [N, H, W, groups·C] (C % 64 == 0), wq: bf16 weights [groups·Cout, R·S·C] (the channels_last storage of the
+// parameters, cast), y: fp32 NHWC [N, P, Q, groups·Cout].  Square filters, symmetric padding.
 //   dgrad = 0: forward, y = act(conv(x, w) + bias).
-//   dgrad = 1: stride-1 data gradient: xb = dY [N, P, Q, C = Cout_fwd], wq = the SAME forward pack [Cout_fwd, R·S·Cin_fwd],
-//              `Cout` = Cin_fwd, pad = R-1-pad_fwd; the pack is read as an MN-major B operand with flipped taps.
+//   dgrad = 1: stride-1 data gradient: xb = dY [N, P, Q, groups·Cout_fwd] (C = Cout_fwd), wq = the SAME forward pack
+//              [groups·Cout_fwd, R·S·Cin_fwd], `Cout` = Cin_fwd, pad = R-1-pad_fwd; the pack is read MN-major with flipped taps.
 int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* bias, int N, int H, int W, int C, int Cout, int R, int S, int P,
-                        int Q, int pad, int stride, int dgrad, int relu, cudaStream_t stream) {
-    if (C % 64 != 0 || Cout % 8 != 0 || R != S || N <= 0) return -5;
+                        int Q, int pad, int stride, int dgrad, int relu, int groups, cudaStream_t stream) {
+    if (C % 64 != 0 || Cout % 8 != 0 || R != S || N <= 0 || groups < 1) return -5;
+    if (groups > 1 && Cout % 32 != 0) return -5;       // a 32-column output chunk must not straddle two groups
     if ((reinterpret_cast<uintptr_t>(xb) & 15) || (reinterpret_cast<uintptr_t>(wq) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return -6;
     const long long Mll = (long long)N * P * Q;
-    if (Mll >= (1LL << 31) - 256) return -5;
+    if (Mll >= (1LL << 31) - 256 || (long long)groups * C >= (1LL << 31)) return -5;
     const int M = (int)Mll, K = R * S * C;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -557,35 +583,40 @@ int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* b
     const int m_tiles = (M + BM - 1) / BM;
     // widest N tile that still gives every SM a tile; otherwise the narrowest and split K over the taps
     int bn = Cout <= 64 ? 64 : 128;
-    if (Cout >= 256 && m_tiles * ((Cout + 255) / 256) >= sms) bn = 256;
-    const int tiles = m_tiles * ((Cout + bn - 1) / bn), kb_total = K / BK;
+    if (Cout >= 256 && (long long)m_tiles * ((Cout + 255) / 256) * groups >= sms) bn = 256;
+    const long long tiles = (long long)m_tiles * ((Cout + bn - 1) / bn) * groups;
+    const int kb_total = K / BK;
     int splits = 1;
-    if (tiles * 2 <= sms && kb_total >= 8) splits = std::max(1, std::min(std::min(sms / tiles, kb_total / 4), 16));
-    CUtensorMap ma, mb;
-    if (make_im2col_map(&ma, xb, N, H, W, C, R, S, pad, pad, stride, BM) != 0) return -7;
-    if (dgrad) { if (make_map_mn(&mb, wq, R * S * Cout, C) != 0) return -7; }      // [C = Cout_fwd rows (K), R·S·Cin_fwd contiguous]
-    else if (make_map(&mb, wq, Cout, K, bn) != 0) return -7;
+    if (tiles * 2 <= sms && kb_total >= 8) splits = std::max(1, std::min(std::min(sms / (int)tiles, kb_total / 4), 16));
+    CUtensorMap ma, mb, md;
+    int ok = 0;
+    if (make_im2col_map(&ma, xb, N, H, W, groups * C, R, S, pad, pad, stride, BM) != 0) return -7;
+    if (dgrad) { if (make_map_mn(&mb, wq, R * S * Cout, groups * C) != 0) return -7; }   // [groups·Cout_fwd rows (K), R·S·Cin_fwd contiguous]
+    else if (make_map(&mb, wq, groups * Cout, K, bn) != 0) return -7;
+    if (make_out_map(&md, y, M, groups * Cout, 1, &ok) != 0 || !ok) return -7;
     const ConvIm ci{1, S, C / 64, R * S, Q, P * Q, stride, pad, pad, dgrad, Cout};
     if (splits > 1) {
-        cudaMemsetAsync(y, 0, (size_t)M * Cout * sizeof(float), stream);
-        int rc = launch_bn(bn, ma, mb, y, nullptr, M, Cout, K, 0, 1, splits, sms, 0, dgrad, stream, ci);
+        cudaMemsetAsync(y, 0, (size_t)M * groups * Cout * sizeof(float), stream);
+        int rc = launch_bn(bn, ma, mb, y, nullptr, M, Cout, K, 0, 1, splits, sms, 0, dgrad, stream, ci, groups, md);
         if (rc != 0) return rc;
         if (bias || relu) {
-            const long long MN = (long long)M * Cout;
-            bias_act_kernel<<<(int)std::min<long long>((MN + 255) / 256, 148LL * 8), 256, 0, stream>>>(y, y, bias, MN, Cout, relu, 1);
+            const long long MN = (long long)M * groups * Cout;
+            bias_act_kernel<<<(int)std::min<long long>((MN + 255) / 256, 148LL * 8), 256, 0, stream>>>(y, y, bias, MN, groups * Cout, relu, 1);
         }
         return cudaGetLastError() == cudaSuccess ? 0 : -4;
     }
-    return launch_bn(bn, ma, mb, y, bias, M, Cout, K, relu, 1, 1, sms, 0, dgrad, stream, ci);
+    return launch_bn(bn, ma, mb, y, bias, M, Cout, K, relu, 1, 1, sms, 0, dgrad, stream, ci, groups, md);
 }
 
-// Weight gradient: dw_ohwi[Cout, (r, s, c)] (fp32) += Σ_pixels dY[pixel, Cout] · X[gather(pixel, r, s), c] — the tiles are
-// REDUCE-ADDED (cp.reduce.async.bulk) into the buffer, which is the channels_last storage of the parameter's gradient: the
-// flat gradient row of the federated executor, or a zeroed tensor.  xb: bf16 NHWC activations, dyb: bf16 [N·P·Q, Cout].
+// Weight gradient: dw[g][Cout, (r, s, c)] (fp32) += Σ_pixels dY[pixel, g·Cout + k] · X[gather(pixel, r, s), g·C + c] — the tiles are
+// REDUCE-ADDED (cp.reduce.async.bulk) into the buffer, which is the channels_last storage of the parameters' gradients: the
+// flat gradient rows of the federated executors (`gstride` floats between the groups' segments), or a zeroed tensor.
+// xb: bf16 NHWC activations [N, H, W, groups·C], dyb: bf16 [N·P·Q, groups·Cout].
 int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N, int H, int W, int C, int Cout, int R, int S, int P, int Q,
-                          int pad, int stride, cudaStream_t stream) {
-    if (C % 64 != 0 || Cout % 8 != 0 || R != S || N <= 0) return -5;
+                          int pad, int stride, int groups, long long gstride, cudaStream_t stream) {
+    if (C % 64 != 0 || Cout % 8 != 0 || R != S || N <= 0 || groups < 1) return -5;
     if ((reinterpret_cast<uintptr_t>(xb) & 15) || (reinterpret_cast<uintptr_t>(dyb) & 15) || (reinterpret_cast<uintptr_t>(dw_ohwi) & 15)) return -6;
+    if (groups > 1 && (gstride % 4 != 0 || gstride < (long long)Cout * R * S * C)) return -6;
     const long long Kll = (long long)N * P * Q;
     if (Kll >= (1LL << 31) - 256) return -5;
     const int Kpix = (int)Kll, RSC = R * S * C;
@@ -593,13 +624,15 @@ int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int bn = 128;
-    const int tiles = ((Cout + BM - 1) / BM) * ((RSC + bn - 1) / bn), kb_total = (Kpix + BK - 1) / BK;
-    int splits = std::max(1, std::min(std::min(sms / tiles, kb_total / 2), 64));
-    CUtensorMap ma, mb;
-    if (make_map_mn(&ma, dyb, Cout, Kpix) != 0) return -7;
-    if (make_im2col_map(&mb, xb, N, H, W, C, R, S, pad, pad, stride, BK) != 0) return -7;
+    const long long tiles = (long long)((Cout + BM - 1) / BM) * ((RSC + bn - 1) / bn) * groups;
+    const int kb_total = (Kpix + BK - 1) / BK;
+    int splits = tiles >= sms ? 1 : std::max(1, std::min(std::min(sms / (int)tiles, kb_total / 2), 64));
+    CUtensorMap ma, mb, md;
+    if (make_map_mn(&ma, dyb, groups * Cout, Kpix) != 0) return -7;
+    if (make_im2col_map(&mb, xb, N, H, W, groups * C, R, S, pad, pad, stride, BK) != 0) return -7;
+    if (make_wgrad_map(&md, dw_ohwi, groups, Cout, RSC, gstride) != 0) return -7;
     const ConvIm ci{2, S, C / 64, R * S, Q, P * Q, stride, pad, pad, 0, 0};
-    return launch_bn(bn, ma, mb, dw_ohwi, nullptr, Cout, RSC, Kpix, 0, 1, splits, sms, 1, 1, stream, ci);
+    return launch_bn(bn, ma, mb, dw_ohwi, nullptr, Cout, RSC, Kpix, 0, 1, splits, sms, 1, 1, stream, ci, groups, md);
 }
 
 int gemm_tn_launch(const void* A, const void* B, void* D, const float* bias, int M, int N, int K, int relu, int out_fp32,

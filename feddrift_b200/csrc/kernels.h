@@ -77,9 +77,10 @@ int conv_ohwi_to_oihw_launch(const float* src, float* dst, int K, int C, int RS,
 int conv_pack_t_launch(const void* wq, void* out, int K, int C, int RS, cudaStream_t stream);
 // gemm_tc.cu: implicit-GEMM convolution on the GEMM mainloop with a TMA-im2col producer (bf16 NHWC operands)
 int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* bias, int N, int H, int W, int C, int Cout, int R, int S, int P,
-                        int Q, int pad, int stride, int dgrad, int relu, cudaStream_t stream);
+                        int Q, int pad, int stride, int dgrad, int relu, int groups, cudaStream_t stream);
 int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N, int H, int W, int C, int Cout, int R, int S, int P, int Q,
-                          int pad, int stride, cudaStream_t stream);
+                          int pad, int stride, int groups, long long gstride, cudaStream_t stream);
+int conv_cast_rows_bf16_launch(const float* x, long long row_stride, void* out, int rows, long long n, cudaStream_t stream);
 // lstm_tc.cu : persistent cluster-resident 2-layer LSTM(256) forward / BPTT over many (client, model) pairs per launch
 struct LstmArgs {
     const float* params;          // parameter arena base

@@ -71,6 +71,18 @@ def _weight_ohwi(weight: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).contiguous()       # no-op for channels_last storage
 
 
+def _dilate(gb: torch.Tensor, stride: int, H: int, W: int, k: int, pad: int) -> torch.Tensor:
+    """Strided layers: dY (bf16 NHWC) with ``stride-1`` zeros between the pixels, sized so that the stride-1 data-gradient
+    convolution returns exactly ``[H, W]`` — the strided data gradient then runs on the same TMA-im2col kernel (3/4 of its
+    multiply-adds hit zeros, which is still several times faster than the software gather it replaces)."""
+    if stride == 1:
+        return gb
+    N, P, Q, C = gb.shape
+    out = gb.new_zeros(N, H - k + 1 + 2 * pad, W - k + 1 + 2 * pad, C)
+    out[:, 0:(P - 1) * stride + 1:stride, 0:(Q - 1) * stride + 1:stride] = gb
+    return out
+
+
 class _ConvIgemmFn(torch.autograd.Function):
     """Implicit-GEMM convolution.  Per direction the kernel is picked by shape: the GEMM mainloop with a TMA-im2col producer
     (``gemm_tc.cu`` conv modes; bf16 NHWC operands, Cin % 64 == 0 — every body layer of the ResNets) or the software-gather
@@ -90,7 +102,7 @@ class _ConvIgemmFn(torch.autograd.Function):
         if tma_in:
             IGEMM_CALLS["tma_fwd"] += 1
             xs = _nhwc_bf16(ext, x)
-            y = ext.conv_tma_fwd(xs, wq, bdet, stride[0], padding[0], bool(relu))
+            y = ext.conv_tma_fwd(xs, wq, bdet, stride[0], padding[0], bool(relu), 1)
         else:
             xs = _nhwc(x)
             y = ext.conv_igemm_fwd(xs, wq, bdet, stride[0], padding[0], padding[1], bool(relu))
@@ -105,8 +117,7 @@ class _ConvIgemmFn(torch.autograd.Function):
         ext = _ext.load(required=True)
         xs, wq, y = ctx.saved_tensors
         stride, padding, (Co, Ci, kh, kw), (H, W) = ctx.geom
-        tma_dgrad = (ctx.needs_input_grad[0] and stride[0] == 1 and padding[0] <= kh - 1
-                     and tma_eligible(Co, stride, padding, (kh, kw)))
+        tma_dgrad = ctx.needs_input_grad[0] and padding[0] <= kh - 1 and tma_eligible(Co, stride, padding, (kh, kw))
         tma_wgrad = ctx.needs_input_grad[1] and ctx.tma_in
         need_f32 = ((ctx.needs_input_grad[0] and not tma_dgrad) or (ctx.needs_input_grad[1] and not tma_wgrad)
                     or (ctx.has_bias and ctx.needs_input_grad[2]))
@@ -120,9 +131,9 @@ class _ConvIgemmFn(torch.autograd.Function):
         gx = gw = gbias = None
         if ctx.needs_input_grad[0]:
             IGEMM_CALLS["dgrad"] += 1
-            if tma_dgrad:      # stride-1 data gradient = forward convolution of dY; the forward pack is read MN-major, taps flipped
+            if tma_dgrad:      # data gradient = stride-1 convolution of (zero-dilated) dY; the forward pack is read MN-major, taps flipped
                 IGEMM_CALLS["tma_dgrad"] += 1
-                gx = ext.conv_tma_dgrad(gb, wq, padding[0]).permute(0, 3, 1, 2)
+                gx = ext.conv_tma_dgrad(_dilate(gb, stride[0], H, W, kh, padding[0]), wq, padding[0], 1).permute(0, 3, 1, 2)
             else:
                 gx = ext.conv_igemm_dgrad(g, ext.conv_pack_t(wq), H, W, stride[0], padding[0], padding[1]).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
@@ -137,7 +148,7 @@ class _ConvIgemmFn(torch.autograd.Function):
             buf = acc if acc is not None else torch.zeros(Co, kh, kw, Ci, dtype=torch.float32, device=xs.device)
             if tma_wgrad:
                 IGEMM_CALLS["tma_wgrad"] += 1
-                ext.conv_tma_wgrad(xs, gb, buf, stride[0], padding[0])
+                ext.conv_tma_wgrad(xs, gb, buf, kh, stride[0], padding[0], 1)
             else:
                 ext.conv_igemm_wgrad(xs, g, kh, kw, stride[0], padding[0], padding[1], buf, True)
             gw = None if acc is not None else buf.permute(0, 3, 1, 2)          # logical OIHW view of the channels_last buffer
@@ -185,8 +196,74 @@ class _TcConvFn(torch.autograd.Function):
 
 
 def stacked_eligible(layer, x: torch.Tensor) -> bool:
-    """Grouped (one group per stacked pair) implicit-GEMM path of ``sim/stacked.py::StackedConv2d``."""
-    return False
+    """Grouped (one group per stacked pair) implicit-GEMM path of ``sim/stacked.py::StackedConv2d``: all three directions on the
+    TMA-im2col GEMM kernels, which needs 64-channel chunks on both sides."""
+    return (x.is_cuda and x.dim() == 4 and layer.groups == 1 and layer.dilation == (1, 1) and layer.in_channels % 64 == 0
+            and layer.out_channels % 64 == 0 and layer.padding[0] <= layer.kernel_size[0] - 1
+            and tma_eligible(layer.in_channels, layer.stride, layer.padding, layer.kernel_size)
+            and os.environ.get("FDB_NO_TC_CONV") != "1" and _ext.available() and hasattr(_ext.load(), "conv_cast_rows_bf16"))
+
+
+def _rows2d(w: torch.Tensor):
+    """[n, Co, Ci, kh, kw] strided view of the staged rows (each pair's weight channels_last) → the [n, Co·kh·kw·Ci] rows view."""
+    n = w.shape[0]
+    v = w.permute(0, 1, 3, 4, 2)
+    r = v.reshape(n, -1)
+    return r if r.stride(1) == 1 and r.data_ptr() == w.data_ptr() else None
+
+
+class _StackedConvFn(torch.autograd.Function):
+    """Grouped implicit-GEMM convolution over ``n`` stacked (client, model) pairs: ``x`` is ``[B, n·Ci, H, W]``, ``weight`` the
+    strided view ``[n, Co, Ci, kh, kw]`` of the staged parameter rows.  One cast kernel turns all pairs' weights into the bf16
+    operand, forward / data gradient are ONE launch each for all pairs, and the weight gradients are reduce-added straight into
+    the pairs' gradient rows through a 3-D tensor map (``weight.grad`` is the matching strided view)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, relu: bool, n: int):
+        global TC_CONV_CALLS
+        TC_CONV_CALLS += 1
+        IGEMM_CALLS["stacked_fwd"] = IGEMM_CALLS.get("stacked_fwd", 0) + 1
+        ext = _ext.load(required=True)
+        _, Co, Ci, kh, kw = weight.shape
+        w2 = _rows2d(weight.detach())
+        if w2 is None:
+            w2 = weight.detach().permute(0, 1, 3, 4, 2).reshape(n, -1).contiguous()
+        wq = ext.conv_cast_rows_bf16(w2).view(n * Co, kh, kw, Ci)
+        xb = _nhwc_bf16(ext, x)
+        b = bias.detach().reshape(-1) if bias is not None else None
+        y = ext.conv_tma_fwd(xb, wq, b, stride[0], padding[0], bool(relu), n)
+        ctx.save_for_backward(xb, wq, y if relu else None)
+        ctx.weight_ref = weight if isinstance(weight, torch.nn.Parameter) else None
+        ctx.geom = (stride, padding, (n, Co, Ci, kh, kw), tuple(x.shape[2:]))
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        ext = _ext.load(required=True)
+        xb, wq, y = ctx.saved_tensors
+        stride, padding, (n, Co, Ci, kh, kw), (H, W) = ctx.geom
+        g = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            g = _nhwc(gy)
+            if ctx.relu:
+                g = g * (y > 0)
+        gb = ext.conv_cast_bf16(g, None) if g is not None else _nhwc_bf16(ext, gy, y if ctx.relu else None)
+        gx = gw = gbias = None
+        if ctx.needs_input_grad[0]:
+            gx = ext.conv_tma_dgrad(_dilate(gb, stride[0], H, W, kh, padding[0]), wq, padding[0], n).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            wp = ctx.weight_ref
+            acc = _rows2d(wp.grad) if (wp is not None and wp.grad is not None and wp.grad.shape == wp.shape and wp.grad.dtype == torch.float32) else None
+            buf = acc if acc is not None else torch.zeros(n, Co * kh * kw * Ci, dtype=torch.float32, device=xb.device)
+            if n == 1:
+                ext.conv_tma_wgrad(xb, gb, buf.view(Co, kh, kw, Ci), kh, stride[0], padding[0], 1)
+            else:
+                ext.conv_tma_wgrad(xb, gb, buf, kh, stride[0], padding[0], n)
+            gw = None if acc is not None else buf.view(n, Co, kh, kw, Ci).permute(0, 1, 4, 2, 3)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gbias = g.sum((0, 1, 2)).view(n, Co)
+        return gx, gw, gbias, None, None, None, None
 
 
 class TcConv2d(nn.Module):

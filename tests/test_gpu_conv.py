@@ -41,16 +41,16 @@ def test_conv_tma_ops_direct_and_gated_cast():
     xr = xb.float().permute(0, 3, 1, 2).requires_grad_(True)
     wr = w.bfloat16().float().requires_grad_(True)
     ref = F.conv2d(xr, wr, None, st, pad)
-    y = ext.conv_tma_fwd(xb, wq, None, st, pad, True)
+    y = ext.conv_tma_fwd(xb, wq, None, st, pad, True, 1)
     assert (y.permute(0, 3, 1, 2) - F.relu(ref)).abs().max().item() < 1e-3
     dy = torch.randn_like(y)
     dyb = ext.conv_cast_bf16(dy, None)
     gx, gw = torch.autograd.grad(ref, (xr, wr), dyb.float().permute(0, 3, 1, 2))
-    dx = ext.conv_tma_dgrad(dyb, wq, pad)                                          # reads the forward pack MN-major
+    dx = ext.conv_tma_dgrad(dyb, wq, pad, 1)                                          # reads the forward pack MN-major
     assert dx.shape == (N, H, W, Ci)
     assert (dx.permute(0, 3, 1, 2) - gx).abs().max().item() < 1e-3 * gx.abs().max().item() + 1e-4
     dw = torch.full((Co, k, k, Ci), 2.0, device="cuda")                            # the kernel ADDS into the channels_last buffer
-    ext.conv_tma_wgrad(xb, dyb, dw, st, pad)
+    ext.conv_tma_wgrad(xb, dyb, dw, k, st, pad, 1)
     assert (dw.permute(0, 3, 1, 2) - 2.0 - gw).abs().max().item() < 1e-3 * gw.abs().max().item() + 1e-4
     # software-gather kernels with the same operand conventions
     wq_t = ext.conv_pack_t(wq)
@@ -110,7 +110,7 @@ def test_conv_igemm_matches_conv2d(geom):
     assert C.IGEMM_CALLS["fwd"] == n0["fwd"] + 1 and C.IGEMM_CALLS["dgrad"] == n0["dgrad"] + 1 and C.IGEMM_CALLS["wgrad"] == n0["wgrad"] + 1
     assert got.shape == ref.shape
     # the GEMM-mainloop path with the TMA-im2col producer must be the one that ran wherever the shape allows it
-    exp_tma = (int(Ci % 64 == 0), int(Co % 64 == 0 and st == 1), int(Ci % 64 == 0))
+    exp_tma = (int(Ci % 64 == 0), int(Co % 64 == 0), int(Ci % 64 == 0))      # strided data gradients run on zero-dilated dY
     assert (C.IGEMM_CALLS["tma_fwd"] - n0["tma_fwd"], C.IGEMM_CALLS["tma_dgrad"] - n0["tma_dgrad"],
             C.IGEMM_CALLS["tma_wgrad"] - n0["tma_wgrad"]) == exp_tma
 
@@ -177,3 +177,89 @@ def test_torchvision_resnet18_body_runs_on_igemm_and_matches_library_convs():
     assert cos(y, y2) > 0.99, cos(y, y2)
     k = "layer1.0.conv1.weight"
     assert cos(g_ours[k], m.get_parameter(k).grad) > 0.9, cos(g_ours[k], m.get_parameter(k).grad)
+
+
+
+@pytest.mark.parametrize("geom", [(3, 4, 64, 9, 9, 64, 3, 1, 1), (2, 3, 64, 8, 8, 128, 3, 2, 1), (4, 2, 128, 6, 6, 64, 1, 2, 0),
+                                  (5, 2, 64, 7, 5, 192, 3, 1, 1)])
+def test_grouped_tma_conv_matches_per_group(geom):
+    """Grouped mode (one group per stacked pair): forward, data gradient (incl. zero-dilated strided layers) and the weight
+    gradient written through the 3-D tensor map into strided gradient rows, against per-group F.conv2d."""
+    from feddrift_b200.ops import _ext
+    from feddrift_b200.ops import conv as C
+    ext = _ext.load(required=True)
+    G, N, Ci, H, W, Co, k, st, pad = geom
+    torch.manual_seed(2)
+    x = torch.randn(N, H, W, G * Ci, device="cuda")
+    w = torch.randn(G, Co, k, k, Ci, device="cuda") / (Ci * k * k) ** 0.5           # per-group (O, kh, kw, I)
+    bias = torch.randn(G * Co, device="cuda")
+    stage = torch.zeros(G, Co * k * k * Ci + 40, device="cuda")                       # rows with a stride ≠ numel, like the parameter rows
+    stage[:, :Co * k * k * Ci] = w.reshape(G, -1)
+    wq = ext.conv_cast_rows_bf16(stage[:, :Co * k * k * Ci]).view(G * Co, k, k, Ci)
+    assert torch.equal(wq.view(G, -1), w.reshape(G, -1).bfloat16())
+    xb = ext.conv_cast_bf16(x, None)
+    y = ext.conv_tma_fwd(xb, wq, bias, st, pad, False, G)
+    xr = xb.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.bfloat16().float().permute(0, 1, 4, 2, 3).reshape(G * Co, Ci, k, k).requires_grad_(True)
+    ref = F.conv2d(xr, wr, bias, st, pad, 1, G)
+    assert (y.permute(0, 3, 1, 2) - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+    dy = torch.randn_like(y)
+    dyb = ext.conv_cast_bf16(dy, None)
+    gx, gw = torch.autograd.grad(ref, (xr, wr), dyb.float().permute(0, 3, 1, 2))
+    dx = ext.conv_tma_dgrad(C._dilate(dyb, st, H, W, k, pad), wq, pad, G)
+    assert dx.shape == (N, H, W, G * Ci)
+    assert (dx.permute(0, 3, 1, 2) - gx).abs().max().item() < 2e-3 * gx.abs().max().item()
+    grows = torch.full((G, Co * k * k * Ci + 40), 0.25, device="cuda")
+    ext.conv_tma_wgrad(xb, dyb, grows[:, :Co * k * k * Ci], k, st, pad, G)
+    got = (grows[:, :Co * k * k * Ci] - 0.25).view(G, Co, k, k, Ci).permute(0, 1, 4, 2, 3).reshape(G * Co, Ci, k, k)
+    assert (got - gw).abs().max().item() < 2e-3 * gw.abs().max().item()
+    assert torch.all(grows[:, Co * k * k * Ci:] == 0.25)                               # nothing spilled past a group's segment
+
+
+def test_stacked_resnet_on_gpu_uses_grouped_kernels_and_matches_per_pair():
+    import copy
+    from feddrift_b200.models import resnet
+    from feddrift_b200.models.utils import flat_size, flat_spec, flat_view, flatten_state_dict, unflatten_to_state_dict
+    from feddrift_b200.ops import conv as C
+    from feddrift_b200.sim import stacked as S
+    torch.manual_seed(0)
+    tmpl = resnet.ResNet(resnet.BasicBlock, [1, 1], 10, widths=(64, 128))
+    n, B = 3, 4
+    spec, P = flat_spec(tmpl), flat_size(tmpl)
+    rows = []
+    for i in range(n):
+        m = copy.deepcopy(tmpl)
+        torch.manual_seed(10 + i)
+        for layer in m.modules():
+            if layer is not m and hasattr(layer, "reset_parameters"):
+                layer.reset_parameters()
+        rows.append(flatten_state_dict(m.state_dict()))
+    rows = torch.stack(rows).cuda()
+    x, y = torch.randn(n, B, 3, 12, 12, device="cuda"), torch.randint(0, 10, (n, B), device="cuda")
+    gref, outs = torch.zeros(n, P, device="cuda"), []
+    for i in range(n):
+        mod = copy.deepcopy(tmpl).cuda()
+        mod.load_state_dict(unflatten_to_state_dict(rows[i].clone(), spec))
+        mod.train()
+        out = mod(x[i])
+        outs.append(out)
+        F.cross_entropy(out, y[i]).backward()
+        grads = {k: p.grad for k, p in mod.named_parameters()}
+        for k, _, _, off, numel in spec:
+            if grads.get(k) is not None:
+                gref[i, off:off + numel] = flat_view(grads[k])
+    net = S.stack_module(tmpl, n).cuda()
+    stage, G = rows.clone(), torch.zeros(n, P, device="cuda")
+    sp = {k: (tuple(shape), off, numel) for k, shape, _, off, numel in spec}
+    for name, mod in net.named_modules():
+        if isinstance(mod, S._Stacked):
+            mod.bind(name, sp, stage, G)
+    net.train()
+    n0 = C.IGEMM_CALLS.get("stacked_fwd", 0)
+    logits = net(S.stack_input(tmpl, x))
+    assert C.IGEMM_CALLS.get("stacked_fwd", 0) - n0 == 5          # every 64/128-channel body conv incl. the strided one + its 1×1 shortcut
+    ref = torch.stack(outs, 1).reshape(B, -1)
+    assert (logits - ref).abs().max().item() < 3e-2 * (1 + ref.abs().max().item())
+    (F.cross_entropy(logits.reshape(B * n, -1), y.t().reshape(-1), reduction="sum") / B).backward()
+    cos = F.cosine_similarity(G.flatten(), gref.flatten(), dim=0).item()
+    assert cos > 0.995, cos

@@ -24,8 +24,8 @@ for _ in range(2):
         ext.conv_igemm_wgrad(x, dy, k, k, stride, pad, pad, dw, True)
     else:
         xb, dyb = ext.conv_cast_bf16(x, None), ext.conv_cast_bf16(dy, None)
-        y = ext.conv_tma_fwd(xb, wq, None, stride, pad, False)
+        y = ext.conv_tma_fwd(xb, wq, None, stride, pad, False, 1)
         if stride == 1:
-            dx = ext.conv_tma_dgrad(dyb, wq, pad)
-        ext.conv_tma_wgrad(xb, dyb, dw, stride, pad)
+            dx = ext.conv_tma_dgrad(dyb, wq, pad, 1)
+        ext.conv_tma_wgrad(xb, dyb, dw, k, stride, pad, 1)
 torch.cuda.synchronize()

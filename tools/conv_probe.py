@@ -67,12 +67,12 @@ for B, cin, cout, k, stride, pad, hw in ((50, 32, 64, 3, 1, 0, 26), (32, 64, 64,
         xbh, dybh = ext.conv_cast_bf16(xh_c, None), ext.conv_cast_bf16(dyh, None)
         r["cast_x_us"] = timeit(lambda: ext.conv_cast_bf16(xh_c, None))
         r["cast_dy_us"] = timeit(lambda: ext.conv_cast_bf16(dyh, None))
-        r["tma_fwd_us"] = timeit(lambda: ext.conv_tma_fwd(xbh, ext.conv_cast_bf16(w_ohwi, None), tc.bias.detach(), stride, pad, False))
-        r["tma_wgrad_us"] = timeit(lambda: ext.conv_tma_wgrad(xbh, dybh, dwbuf, stride, pad))
+        r["tma_fwd_us"] = timeit(lambda: ext.conv_tma_fwd(xbh, ext.conv_cast_bf16(w_ohwi, None), tc.bias.detach(), stride, pad, False, 1))
+        r["tma_wgrad_us"] = timeit(lambda: ext.conv_tma_wgrad(xbh, dybh, dwbuf, k, stride, pad, 1))
         r["ours_fwd_us"] = r["tma_fwd_us"] + r["cast_x_us"]
         r["ours_wgrad_us"] = r["tma_wgrad_us"] + r["cast_dy_us"]
         if stride == 1 and cout % 64 == 0:
-            r["tma_dgrad_us"] = timeit(lambda: ext.conv_tma_dgrad(dybh, wq, pad))
+            r["tma_dgrad_us"] = timeit(lambda: ext.conv_tma_dgrad(dybh, wq, pad, 1))
             r["ours_dgrad_us"] = r["tma_dgrad_us"]
     r["cudnn_fp32_fwd_us"] = timeit(lambda: F.conv2d(x, w, tc.bias.detach(), stride, pad))
     r["cudnn_fp32_bwd_us"] = timeit(lambda: torch.ops.aten.convolution_backward(dy_nchw, x, w, None, [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, mask))

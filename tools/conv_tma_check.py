@@ -51,7 +51,7 @@ for (N, Ci, H, W, Co, k, st, pad) in GEOMS:
     wr = w.bfloat16().float()
     ref = F.conv2d(xr, wr, b, st, pad)
     r = {"geom": [N, Ci, H, W, Co, k, st, pad]}
-    y = ext.conv_tma_fwd(xb, wq, b, st, pad, False)
+    y = ext.conv_tma_fwd(xb, wq, b, st, pad, False, 1)
     torch.cuda.synchronize()
     r["fwd_err"] = rel(y.permute(0, 3, 1, 2), ref)
     dy = torch.randn_like(y)
@@ -59,19 +59,19 @@ for (N, Ci, H, W, Co, k, st, pad) in GEOMS:
     dyr = dyb.float().permute(0, 3, 1, 2)
     gx, gw = torch.autograd.grad(F.conv2d(xr.requires_grad_(True), wr.requires_grad_(True), None, st, pad), (xr, wr), dyr)
     if st == 1 and Co % 64 == 0:
-        dx = ext.conv_tma_dgrad(dyb, wq, pad)
+        dx = ext.conv_tma_dgrad(dyb, wq, pad, 1)
         torch.cuda.synchronize()
         r["dgrad_err"] = rel(dx.permute(0, 3, 1, 2), gx) if dx.shape[1:3] == (H, W) else f"shape {tuple(dx.shape)}"
     dw = torch.zeros(Co, k, k, Ci, device="cuda")
-    ext.conv_tma_wgrad(xb, dyb, dw, st, pad)
+    ext.conv_tma_wgrad(xb, dyb, dw, k, st, pad, 1)
     torch.cuda.synchronize()
     r["wgrad_err"] = rel(dw.permute(0, 3, 1, 2), gw)
     if N >= 32:
         r["cast_x_us"] = timeit(lambda: ext.conv_cast_bf16(x, None))
-        r["fwd_us"] = timeit(lambda: ext.conv_tma_fwd(xb, wq, b, st, pad, False))
+        r["fwd_us"] = timeit(lambda: ext.conv_tma_fwd(xb, wq, b, st, pad, False, 1))
         if st == 1:
-            r["dgrad_us"] = timeit(lambda: ext.conv_tma_dgrad(dyb, wq, pad))
-        r["wgrad_us"] = timeit(lambda: ext.conv_tma_wgrad(xb, dyb, dw, st, pad))
+            r["dgrad_us"] = timeit(lambda: ext.conv_tma_dgrad(dyb, wq, pad, 1))
+        r["wgrad_us"] = timeit(lambda: ext.conv_tma_wgrad(xb, dyb, dw, k, st, pad, 1))
         w_ohwi = w.permute(0, 2, 3, 1).contiguous()
         r["cast_w_us"] = timeit(lambda: ext.conv_cast_bf16(w_ohwi, None))
         xcl = xb.permute(0, 3, 1, 2)

@@ -3,7 +3,7 @@
 // Hand-written Blackwell GEMM used by TcLinear (fnn-MNIST 784→1568→10, CNN fc 9216→128, LSTM/classifier heads):
 //   * PERSISTENT, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles tile = blockIdx.x + i·gridDim.x
 //     (M-fastest rasterisation so concurrently running CTAs share the same B panel in L2);
-//   * warp 0 = TMA producer (cp.async.bulk.tensor.2d, 128B-swizzled 128×64 / BN×64 bf16 boxes) into a 4-stage smem ring
+//   * warp 0 = TMA producer (cp.async.bulk.tensor.2d, 128B-swizzled 128×64 / BN×64 bf16 boxes) into a 4 / 6 / 8-stage (BN 256 / 128 / 64) smem ring
 //     with full/empty mbarriers; warp 1 = single-thread tcgen05.mma issuer (UMMA 128×BN×16, BN ∈ {128, 256});
 //     warp 2 owns the TMEM allocation; warps 4-7 = epilogue;
 //   * the accumulator is DOUBLE-BUFFERED in TMEM (2 × BN fp32 columns): the epilogue of tile i (tcgen05.ld →
@@ -16,6 +16,12 @@
 //     K) and described to the tensor core with the MN-major canonical layout (LBO = 8 KB between 64-wide M/N groups,
 //     SBO = 1 KB between 8-row K groups, a_major/b_major bits of the instruction descriptor), so the backward GEMMs
 //     dX = dY·W and dW = dYᵀ·X run directly on the row-major tensors autograd hands us — no transpose kernels.
+//   * IMPLICIT-GEMM CONVOLUTION on the same mainloop (struct ConvIm below, ops/conv.py): the producer thread issues TMA *im2col*
+//     loads (cp.async.bulk.tensor.4d…im2col) from the bf16 NHWC activation tensor — the TMA unit walks the output pixels with the
+//     conv stride, applies the filter-tap offset and zero-fills the halo — for the forward, the data gradient (the forward
+//     weight pack read MN-major, taps flipped; strided layers on zero-dilated dY) and the weight gradient (reduction over
+//     pixels, im2col boxes as the MN-major B operand, cp.reduce.async.bulk adds into the channels_last gradient), optionally
+//     GROUPED with one group per stacked (client, model) pair (sim/stacked.py).
 // All waits are bounded (trap after 2 s) so a protocol bug faults the context instead of hanging the GPU.
 // The reference's equivalent is eager `nn.Linear` + separate bias/ReLU kernels in fp32 on cuBLAS
 // (fedml_api/model/fnn/fnn.py:11-15, cv/cnn.py:128-136).
@@ -31,7 +37,7 @@
 
 namespace fdb {
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int kGemmThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-7 epilogue
 constexpr uint32_t kStageBytesA = BM * BK * 2;
 struct GemmBatch { int batch, a_k0, a_kstride, b_k0, b_kstride; };
@@ -51,7 +57,10 @@ template <int BN> struct GemmCfg {
     static constexpr uint32_t kStageBytesB = BN * BK * 2;
     static constexpr uint32_t kTmemCols = 2 * BN;  // double-buffered accumulator (256 or 512 columns)
     static constexpr uint32_t kStagingBytes = 4 /*epilogue warps*/ * 2 /*double buffer*/ * 4096;   // 32 rows × 128 B per buffer
-    static constexpr uint32_t kSmemBytes = STAGES * (kStageBytesA + kStageBytesB) + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    // 192 KB of operand ring in every configuration: 4 × 48 KB (BN 256), 6 × 32 KB (BN 128), 8 × 24 KB (BN 64) — the narrow tiles
+    // of the convolution modes have short K loops, a deeper ring keeps their TMA (im2col) loads far enough ahead
+    static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr uint32_t kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     // c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
@@ -62,6 +71,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_d, void* __restrict__ D, const float* __restrict__ bias, int M, int N, int K,
                int relu, int out_fp32, int splits, int tma_out, int a_mn, int b_mn, GemmBatch gb, ConvIm ci) {
     using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;

@@ -53,9 +53,9 @@ FDB_DEVICE void grid_barrier(unsigned* counter, unsigned target, long long timeo
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
-        const long long t0 = globaltimer_ns();
+        SpinGuard g;
         while ((int)(*reinterpret_cast<volatile unsigned*>(counter) - target) < 0) {
-            if (globaltimer_ns() - t0 > timeout_ns) { if (err) atomicExch(err, 3); break; }
+            if (g.expired(timeout_ns)) { if (err) atomicExch(err, 3); break; }
         }
         __threadfence();
     }
@@ -71,9 +71,9 @@ FDB_DEVICE void peer_barrier(const PeerAggParams& p, int slot, unsigned epoch) {
     }
     if ((int)threadIdx.x < p.world) {
         const unsigned* f = p.flags[p.rank] + slot * p.world + threadIdx.x;
-        const long long t0 = globaltimer_ns();
+        SpinGuard g;
         while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-            if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 4); break; }
+            if (g.expired(p.spin_timeout_ns)) { if (p.error_flag) atomicExch(p.error_flag, 4); break; }
         }
     }
     __syncthreads();
@@ -189,9 +189,9 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
         const int ct = tid - kAggProd;
         if (ct < W) {   // weight totals of every rank
             const unsigned* f = p.flags[p.rank] + 0 * W + ct;
-            const long long t0 = globaltimer_ns();
+            SpinGuard g;
             while ((int)(ld_acquire_sys(f) - p.epoch) < 0) {
-                if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 4); break; }
+                if (g.expired(p.spin_timeout_ns)) { if (p.error_flag) atomicExch(p.error_flag, 4); break; }
             }
         }
         named_bar(2, kAggCons);
@@ -208,9 +208,9 @@ __global__ void __launch_bounds__(512) fedavg_reduce_apply_peer_kernel(const __g
             if (!(tot > 0.f)) continue;       // unused cluster: leave θ untouched everywhere (uniform)
             if (ct < W) {                     // chunk k of EVERY rank's partial buffer is complete
                 const unsigned* f = p.flags[p.rank] + (2 + ck) * W + ct;
-                const long long t0 = globaltimer_ns();
+                SpinGuard g;
                 while ((int)(ld_acquire_sys(f) - p.epoch) < 0) {
-                    if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 5); break; }
+                    if (g.expired(p.spin_timeout_ns)) { if (p.error_flag) atomicExch(p.error_flag, 5); break; }
                 }
             }
             named_bar(2, kAggCons);

@@ -39,12 +39,12 @@ FDB_DEVICE void gm_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 FDB_DEVICE void gm_mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
-    const long long t0 = globaltimer_ns();
+    SpinGuard g;
     while (true) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(gm_smem(bar)), "r"(parity) : "memory");
         if (ok) return;
-        if (globaltimer_ns() - t0 > 2000000000LL) __trap();   // a protocol bug must fault, never hang the GPU
+        if (g.expired(2000000000LL)) __trap();   // a protocol bug must fault, never hang the GPU
     }
 }
 FDB_DEVICE void gm_bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {

@@ -95,5 +95,19 @@ FDB_DEVICE long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Bounded spinning without a timer read on the fast path: %globaltimer is a slow, chip-level register — reading it before and
+// inside every wait put hundreds of cycles on each hop of the mbarrier / flag handshake chains (the pipeline skeleton of the
+// tcgen05 kernels alone cost ~0.4 µs per k-block).  The guard looks at the timer only every 256 failed polls; the first look
+// starts the clock.
+struct SpinGuard {
+    long long t0 = 0;
+    unsigned n = 0;
+    FDB_DEVICE bool expired(long long timeout_ns) {
+        if ((++n & 255u) != 0) return false;
+        const long long now = globaltimer_ns();
+        if (t0 == 0) { t0 = now; return false; }
+        return now - t0 > timeout_ns;
+    }
+};
 
 }  // namespace fdb

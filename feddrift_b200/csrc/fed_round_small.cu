@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                     st_ll(reinterpret_cast<uint2*>(p.inbox[gq]) + slot + e, v, epoch);
             }
             const uint2* inb = reinterpret_cast<const uint2*>(p.inbox[p.rank]) + (size_t)(xbuf * p.world) * MP;
-            const long long t0 = globaltimer_ns();
+            SpinGuard sg;
             for (int e = tid; e < MP; e += blockDim.x) {
                 uint2 w[kMaxPeers];
 #pragma unroll
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
                 for (int gq = 0; gq < kMaxPeers; ++gq) {
                     if (gq < p.world) {
                         while (ok && w[gq].y != epoch) {
-                            if (globaltimer_ns() - t0 > p.spin_timeout_ns) { ok = false; break; }
+                            if (sg.expired(p.spin_timeout_ns)) { ok = false; break; }
                             w[gq] = ld_ll(inb + (size_t)gq * MP + e);
                         }
                         v += __uint_as_float(w[gq].x);
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
     //      for the end-to-end graph, the pinned host mirror (posted PCIe writes).
     if (p.world > 1 && p.metrics_peer[0] && crank == 0) {
         const uint4* stg = reinterpret_cast<const uint4*>(p.metrics_peer[p.rank]);
-        const long long t0 = globaltimer_ns();
+        SpinGuard sg;
         for (int e = tid; e < p.rounds * C * 2; e += blockDim.x) {
             const int c = (e >> 1) % C, which = e & 1;
             if (t + which >= p.T1) continue;   // nobody evaluates a test split beyond the last time step
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(SmallCfg<Net>::kThreads, 1) fed_round_small_ke
             uint4 w = ld_ll2(stg + e);
             bool ok = true;
             while (w.y != epoch || w.w != epoch) {
-                if (globaltimer_ns() - t0 > p.spin_timeout_ns) { ok = false; break; }
+                if (sg.expired(p.spin_timeout_ns)) { ok = false; break; }
                 w = ld_ll2(stg + e);
             }
             if (!ok) { if (p.error_flag) atomicExch(p.error_flag, 2); continue; }

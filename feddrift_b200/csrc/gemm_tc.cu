@@ -28,6 +28,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
 
@@ -69,7 +70,7 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_d, void* __restrict__ D, const float* __restrict__ bias, int M, int N, int K,
-               int relu, int out_fp32, int splits, int tma_out, int a_mn, int b_mn, GemmBatch gb, ConvIm ci) {
+               int relu, int out_fp32, int splits, int tma_out, int a_mn, int b_mn, GemmBatch gb, ConvIm ci, int dbg) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -137,6 +138,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_wait(empty_bar + s, ph ^ 1);
                     uint8_t* sa = smem_a + s * kStageBytesA;
                     uint8_t* sb = smem_b + s * Cfg::kStageBytesB;
+                    if (dbg & 1) { mbar_arrive(full_bar + s); continue; }   // FDB_GEMM_DBG bit 0: pipeline without operand loads (timing study)
                     if (ci.mode == 1) {
                         mbar_expect_tx(full_bar + s, kStageBytesA + Cfg::kStageBytesB);
                         const int tap = kb / ci.cchunks, cc = kb - tap * ci.cchunks;
@@ -204,7 +206,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // K-major: 16 K-elements = 32 B along the row; MN-major: 16 K-rows = two 1024-B atoms
                         const uint64_t da = a_mn ? make_smem_desc_mn(a_addr + k * 2048) : make_smem_desc(a_addr + k * UMMA_K * 2);
                         const uint64_t db = b_mn ? make_smem_desc_mn(b_addr + k * 2048) : make_smem_desc(b_addr + k * UMMA_K * 2);
-                        umma_f16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(dbg & 2)) umma_f16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);   // bit 1: no MMAs
                     }
                     tcgen05_commit(empty_bar + s);  // frees the smem stage once these MMAs retire
                 }
@@ -280,7 +282,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (lane == 0 && !(dbg & 4)) {   // bit 2: no output stores
                         if (ci.mode == 2) tma_reduce_add_3d(&map_d, buf, col0, row0, bt);   // wgrad always accumulates into slice g
                         else if (splits > 1) tma_reduce_add_2d(&map_d, buf, col0, row0);
                         else tma_store_2d(&map_d, buf, col0, row0);
@@ -468,9 +470,10 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
         if (cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes) != cudaSuccess) return -3;
         attr_set = true;
     }
+    static const int dbg = getenv("FDB_GEMM_DBG") ? atoi(getenv("FDB_GEMM_DBG")) : 0;   // timing-study switches, results are garbage
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * gb.batch;
     dim3 grid(min(tiles, max(1, sms / splits)), 1, splits);
-    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out, a_mn, b_mn, gb, ci);
+    gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out, a_mn, b_mn, gb, ci, dbg);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -43,9 +43,9 @@ __global__ void __launch_bounds__(512) gossip_mix_peer_kernel(const __grid_const
     // ---- wait: every peer finished step k-1
     if ((int)threadIdx.x < W && (int)threadIdx.x != p.rank) {
         const unsigned* f = p.flags[p.rank] + threadIdx.x;
-        const long long t0 = globaltimer_ns();
+        SpinGuard g;
         while ((int)(ld_acquire_sys(f) - (k - 1)) < 0) {
-            if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 6); break; }
+            if (g.expired(p.spin_timeout_ns)) { if (p.error_flag) atomicExch(p.error_flag, 6); break; }
         }
     }
     __syncthreads();
@@ -75,9 +75,9 @@ __global__ void __launch_bounds__(512) gossip_mix_peer_kernel(const __grid_const
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
             const unsigned target = p.grid_base + gridDim.x;
-            const long long t0 = globaltimer_ns();
+            SpinGuard g;
             while ((int)(*reinterpret_cast<volatile unsigned*>(p.grid_sync) - target) < 0) {
-                if (globaltimer_ns() - t0 > p.spin_timeout_ns) { if (p.error_flag) atomicExch(p.error_flag, 7); break; }
+                if (g.expired(p.spin_timeout_ns)) { if (p.error_flag) atomicExch(p.error_flag, 7); break; }
             }
             __threadfence_system();
         }

@@ -109,10 +109,9 @@ FDB_DEVICE void bulk_copy_s2c(uint32_t dst_cluster_addr, uint32_t src_cta_addr, 
                  ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
 }
 FDB_DEVICE void mbar_wait_long(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = globaltimer_ns();
+    SpinGuard g;
     while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > 4000000000LL) __trap();
+        if (g.expired(4000000000LL)) __trap();
     }
 }
 FDB_DEVICE uint32_t pack_bf16(float lo, float hi) {

@@ -28,10 +28,9 @@ FDB_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // bounded wait: a protocol bug must fault the context (trap), never hang the GPU
 FDB_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = globaltimer_ns();
+    SpinGuard g;
     while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > 2000000000LL) __trap();
+        if (g.expired(2000000000LL)) __trap();
     }
 }
 FDB_DEVICE void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {

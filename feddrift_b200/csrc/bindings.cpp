@@ -823,6 +823,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("conv_tma_wgrad", &conv_tma_wgrad);
     m.def("conv_tma_dgrad", &conv_tma_dgrad);
     m.def("conv_cast_rows_bf16", &conv_cast_rows_bf16);
+    m.def("gemm_debug_counters", []() {
+        std::vector<int64_t> v(16);
+        cudaDeviceSynchronize();
+        CHECK_OK(fdb::gemm_debug_counters(reinterpret_cast<long long*>(v.data())), "gemm_debug_counters");
+        return v;
+    });
     m.def("conv_pack_t", &conv_pack_t);
     m.def("conv_igemm_dgrad", &conv_igemm_dgrad);
     m.def("conv_igemm_wgrad", &conv_igemm_wgrad);

@@ -54,6 +54,9 @@ struct GemmBatch { int batch, a_k0, a_kstride, b_k0, b_kstride; };
 //           MN-major 64-pixel × 64-channel im2col boxes, one per 64-wide column group of the N tile.
 struct ConvIm { int mode, S, cchunks, ntaps, Q, PQ, stride, pad_h, pad_w, flip, bcols; };
 
+// FDB_GEMM_DBG bit 3: CTA 0 accumulates SM-clock cycles per pipeline role / wait site (read back with gemm_debug_counters())
+__device__ long long g_gemm_dbg[16];
+
 template <int BN> struct GemmCfg {
     static constexpr uint32_t kStageBytesB = BN * BK * 2;
     static constexpr uint32_t kTmemCols = 2 * BN;  // double-buffered accumulator (256 or 512 columns)
@@ -84,7 +87,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tmem_empty = tmem_full + 2;       // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp index in a uniform register
     const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
     // batched mode (gb.batch > 1; both operands MN-major, M % 128 == 0, K % 64 == 0): batch bt multiplies the reduction rows
     // [a_k0 + bt·a_kstride, +K) of A' with [b_k0 + bt·b_kstride, +K) of B' into rows [bt·M, bt·M + M) of D — one launch for
@@ -116,8 +119,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        if (lane == 0 && nkb > 0) {  // ===== TMA producer
+        if (nkb > 0) {  // ===== TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues
             uint32_t it = 0;
+            const bool prof = (dbg & 8) && blockIdx.x == 0;
+            long long c_wait = 0, c_all0 = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int bt = tile / tiles_per_batch, rem = tile - bt * tiles_per_batch;
                 const int m_blk = rem % m_tiles, n_blk = rem / m_tiles;
@@ -135,10 +140,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(empty_bar + s, ph ^ 1);
+                    const long long w0 = prof ? clock64() : 0;
+                    if (!(dbg & 16)) mbar_wait(empty_bar + s, ph ^ 1);   // bit 4 (with bit 0): free-running ring, no stage release
+                    if (prof) c_wait += clock64() - w0;
                     uint8_t* sa = smem_a + s * kStageBytesA;
                     uint8_t* sb = smem_b + s * Cfg::kStageBytesB;
-                    if (dbg & 1) { mbar_arrive(full_bar + s); continue; }   // FDB_GEMM_DBG bit 0: pipeline without operand loads (timing study)
+                    if (dbg & 1) { if (elect_one()) mbar_arrive(full_bar + s); continue; }   // FDB_GEMM_DBG bit 0: pipeline without operand loads (timing study)
+                    if (!elect_one()) continue;
                     if (ci.mode == 1) {
                         mbar_expect_tx(full_bar + s, kStageBytesA + Cfg::kStageBytesB);
                         const int tap = kb / ci.cchunks, cc = kb - tap * ci.cchunks;
@@ -183,45 +191,61 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
+            if (prof && lane == 0) { g_gemm_dbg[0] = c_wait; g_gemm_dbg[1] = clock64() - c_all0; g_gemm_dbg[2] = it; }
         }
     } else if (warp == 1) {
-        if (lane == 0 && nkb > 0) {  // ===== MMA issuer (single thread)
+        if (nkb > 0) {  // ===== MMA issuer: uniform loop over the whole warp, one elected lane issues tcgen05.mma / commit
             uint32_t it = 0, tl = 0;
+            const bool prof = (dbg & 8) && blockIdx.x == 0;
+            long long c_wfull = 0, c_wacc = 0, c_all0 = prof ? clock64() : 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+                const long long a0 = prof ? clock64() : 0;
                 mbar_wait(tmem_empty + acc, aph ^ 1);   // epilogue has drained this accumulator
+                if (prof) c_wacc += clock64() - a0;
                 tcgen05_fence_after();
                 const uint32_t d_addr = tmem_base + acc * BN;
                 const uint32_t idesc = Cfg::kIdesc | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
+                const uint64_t desc_a0 = a_mn ? make_smem_desc_mn(smem_u32(smem_a)) : make_smem_desc(smem_u32(smem_a));
+                const uint64_t desc_b0 = b_mn ? make_smem_desc_mn(smem_u32(smem_b)) : make_smem_desc(smem_u32(smem_b));
+                const uint32_t a_kstep = a_mn ? (2048u >> 4) : ((UMMA_K * 2u) >> 4), b_kstep = b_mn ? (2048u >> 4) : ((UMMA_K * 2u) >> 4);
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const long long f0 = prof ? clock64() : 0;
                     mbar_wait(full_bar + s, ph);
-                    tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + s * kStageBytesA);
-                    const uint32_t b_addr = smem_u32(smem_b + s * Cfg::kStageBytesB);
+                    if (prof) c_wfull += clock64() - f0;
+                    if (!(dbg & 32)) tcgen05_fence_after();
+                    // stage-0 descriptors + (stage offset >> 4) in the 14-bit start-address field; per UMMA_K step the start address
+                    // moves by 32 B (K-major: 16 elements along the row) or 2048 B (MN-major: 16 K-rows = two 1024-B atoms)
+                    const uint64_t da0 = desc_a0 + (uint64_t)((s * kStageBytesA) >> 4);
+                    const uint64_t db0 = desc_b0 + (uint64_t)((s * Cfg::kStageBytesB) >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                    {
-                        // K-major: 16 K-elements = 32 B along the row; MN-major: 16 K-rows = two 1024-B atoms
-                        const uint64_t da = a_mn ? make_smem_desc_mn(a_addr + k * 2048) : make_smem_desc(a_addr + k * UMMA_K * 2);
-                        const uint64_t db = b_mn ? make_smem_desc_mn(b_addr + k * 2048) : make_smem_desc(b_addr + k * UMMA_K * 2);
-                        if (!(dbg & 2)) umma_f16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);   // bit 1: no MMAs
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t da = da0 + (uint64_t)(k * a_kstep), db = db0 + (uint64_t)(k * b_kstep);
+                            if (!(dbg & 2)) umma_f16(d_addr, da, db, idesc, (kb | k) != 0 ? 1u : 0u);   // bit 1: no MMAs
+                        }
+                        if (!(dbg & 16)) tcgen05_commit(empty_bar + s);  // frees the smem stage once these MMAs retire
                     }
-                    tcgen05_commit(empty_bar + s);  // frees the smem stage once these MMAs retire
                 }
-                tcgen05_commit(tmem_full + acc);    // accumulator complete → epilogue
+                if (elect_one()) tcgen05_commit(tmem_full + acc);    // accumulator complete → epilogue
             }
+            if (prof && lane == 0) { g_gemm_dbg[3] = c_wfull; g_gemm_dbg[4] = c_wacc; g_gemm_dbg[5] = clock64() - c_all0; g_gemm_dbg[6] = tl; }
         }
     } else if (warp >= 4 && nkb > 0) {
         // ===== epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) == output rows of the tile
         const int q = warp - 4;
         uint32_t tl = 0, chunk_it = 0;
+        const bool prof = (dbg & 8) && blockIdx.x == 0 && q == 0;
+        long long c_wtm = 0, c_all0 = prof ? clock64() : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             const int bt = tile / tiles_per_batch, rem = tile - bt * tiles_per_batch;
             const int m_blk = rem % m_tiles, n_blk = rem / m_tiles;
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+            const long long e0 = prof ? clock64() : 0;
             mbar_wait(tmem_full + acc, aph);
+            if (prof) c_wtm += clock64() - e0;
             tcgen05_fence_after();
             const int row = m_blk * BM + q * 32 + lane;
             if (tma_out) {
@@ -238,7 +262,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (n_blk * BN + c0 >= N) break;   // warp-uniform
                     const int col0 = colg + n_blk * BN + c0;
                     uint8_t* buf = staging + (q * 2 + (chunk_it & 1)) * 4096;
-                    if (lane == 0 && chunk_it >= 2) tma_store_wait_read<1>();   // the store that last read this buffer is done
+                    if (chunk_it >= 2) tma_store_wait_read<1>();   // (all lanes; only the electing lane owns bulk groups) the store that last read this buffer is done
                     __syncwarp();
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0;
@@ -282,7 +306,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && !(dbg & 4)) {   // bit 2: no output stores
+                    if (!(dbg & 4) && elect_one()) {   // bit 2: no output stores
                         if (ci.mode == 2) tma_reduce_add_3d(&map_d, buf, col0, row0, bt);   // wgrad always accumulates into slice g
                         else if (splits > 1) tma_reduce_add_2d(&map_d, buf, col0, row0);
                         else tma_store_2d(&map_d, buf, col0, row0);
@@ -332,7 +356,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + acc);   // 4 epilogue warps → the MMA warp may reuse the buffer
         }
-        if (tma_out && lane == 0) tma_store_wait_all();   // smem must outlive the in-flight bulk stores
+        if (prof && lane == 0) { g_gemm_dbg[7] = c_wtm; g_gemm_dbg[8] = clock64() - c_all0; }
+        if (tma_out) tma_store_wait_all();   // smem must outlive the in-flight bulk stores (a no-op for lanes without bulk groups)
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -475,6 +500,10 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, void* D, co
     dim3 grid(min(tiles, max(1, sms / splits)), 1, splits);
     gemm_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma, mb, md, D, bias, M, N, K, relu, out_fp32, splits, tma_out, a_mn, b_mn, gb, ci, dbg);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+int gemm_debug_counters(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_gemm_dbg, sizeof(long long) * 16) == cudaSuccess ? 0 : -4;
 }
 
 // number of K-splits gemm_launch will use for this problem (callers that want a bf16 output pre-allocate the fp32

@@ -80,6 +80,7 @@ int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* b
                         int Q, int pad, int stride, int dgrad, int relu, int groups, cudaStream_t stream);
 int conv_tma_wgrad_launch(const void* xb, const void* dyb, float* dw_ohwi, int N, int H, int W, int C, int Cout, int R, int S, int P, int Q,
                           int pad, int stride, int groups, long long gstride, cudaStream_t stream);
+int gemm_debug_counters(long long* out16);   // FDB_GEMM_DBG=8 cycle counters of CTA 0 (gemm_tc.cu)
 int conv_cast_rows_bf16_launch(const float* x, long long row_stride, void* out, int rows, long long n, cudaStream_t stream);
 // lstm_tc.cu : persistent cluster-resident 2-layer LSTM(256) forward / BPTT over many (client, model) pairs per launch
 struct LstmArgs {

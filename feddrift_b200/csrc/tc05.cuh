@@ -9,6 +9,16 @@ namespace fdb {
 
 // ---------------------------------------------------------------- PTX wrappers
 FDB_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// One lane of a CONVERGED warp.  The single-thread roles (TMA producer, tcgen05.mma issuer) run their loops with all 32 lanes
+// in uniform control flow and issue under `if (elect_one())`: addresses, descriptors and coordinates then live in uniform
+// registers and UTMALDG / UTCHMMA / UTCBAR are issued directly.  Under `if (lane == 0)` the same operands are per-lane vector
+// values and every issue is wrapped in an R2UR + ELECT + BRA.U.ANY serialisation loop (≈ 60 cycles each — with 4 MMAs and a
+// commit per 64-wide k-block that made the issue thread, not the tensor pipe, the bound of the short-K convolution tiles).
+FDB_DEVICE bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 FDB_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

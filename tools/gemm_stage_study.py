@@ -35,8 +35,16 @@ for name, (N, HW, C, Co) in {"conv64": (32, 56, 64, 64), "conv128": (32, 28, 128
     xb = torch.randn(N, HW, HW, C, device="cuda").bfloat16()
     wq = (torch.randn(Co, 3, 3, C, device="cuda") / (9 * C) ** 0.5).bfloat16()
     r[name + "_us"] = timeit(lambda: ext.conv_tma_fwd(xb, wq, None, 1, 1, False, 1))
+    if r["dbg"] & 8:
+        c = ext.gemm_debug_counters()
+        r[name + "_cycles"] = {"producer_wait_empty": c[0], "producer_total": c[1], "kblocks": c[2], "mma_wait_full": c[3],
+                               "mma_wait_acc": c[4], "mma_total": c[5], "tiles": c[6], "epi_wait_acc_full": c[7], "epi_total": c[8]}
 for n in (1024, 4096):
     A = torch.randn(n, n, device="cuda").bfloat16()
     B = torch.randn(n, n, device="cuda").bfloat16()
     r[f"gemm{n}_us"] = timeit(lambda: ext.gemm_tn_bias_act(A, B, None, False, False))
+    if r["dbg"] & 8:
+        c = ext.gemm_debug_counters()
+        r[f"gemm{n}_cycles"] = {"producer_wait_empty": c[0], "producer_total": c[1], "kblocks": c[2], "mma_wait_full": c[3],
+                                "mma_wait_acc": c[4], "mma_total": c[5], "tiles": c[6], "epi_wait_acc_full": c[7], "epi_total": c[8]}
 print(json.dumps(r), flush=True)

@@ -158,7 +158,7 @@ lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int pair = blockIdx.x / CL;
-    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), l = tid & 31;   // uniform warp index
     const int T = a.T, E = a.E;
 
     // ---- shared memory carve-up
@@ -241,39 +241,44 @@ lstm2_fwd_kernel(const __grid_constant__ LstmArgs a) {
     const uint32_t bytes_each = NB * U * 2;
 
     if (grp == 2) {
-        // =================================================== MMA issuer (one elected lane)
-        if (l == 0) {
+        // =================================================== MMA issuer: the whole warp walks the phase loop in uniform control flow,
+        // one elected lane issues (operands in uniform registers: no R2UR/ELECT serialisation loop around every UTCHMMA)
+        {
             long long seg[3] = {0, 0, 0}, tprev = clock64();
             for (int p = 0; p <= T; ++p) {
                 const bool doL1 = p < T, doL2 = p >= 1;
                 // arm this phase's inbound barrier first (the slices of phase p land in hbar[p&1])
-                if (p < T) mbar_expect_tx(hbar + (p & 1), CL * bytes_each * ((doL1 ? 1u : 0u) + (doL2 ? 1u : 0u)));
+                if (p < T && elect_one()) mbar_expect_tx(hbar + (p & 1), CL * bytes_each * ((doL1 ? 1u : 0u) + (doL2 ? 1u : 0u)));
                 if (p >= 1) mbar_wait_long(hbar + ((p - 1) & 1), ((p - 1) >> 1) & 1);   // h1_{p-1} (and h2_{p-2}) from all 8 CTAs
                 if (dbg) { const long long tn = clock64(); seg[0] += tn - tprev; tprev = tn; }
                 tcgen05_fence_after();
                 const uint32_t h1prev = smem_u32(H1s + ((p + 1) & 1) * NB * H);     // h1_{p-1}
-                if (doL1) {
+                const uint64_t d_h1 = make_desc_nosw(h1prev), d_x = make_desc_nosw(smem_u32(Xs + (p & 1) * NB * KX));
+                if (doL1 && elect_one()) {
                     // two accumulators: k-steps alternate; the x step joins accumulator 1
 #pragma unroll
                     for (int s = 0; s < 16; ++s)
-                        umma_ts_f16(tmem + D1_COL + 16 * (s & 1), tmem + A1_COL + 8 * s, make_desc_nosw(h1prev + s * 2 * kLBO), kIdesc, s > 1 ? 1u : 0u);
-                    umma_ts_f16(tmem + D1_COL + 16, tmem + A1_XCOL, make_desc_nosw(smem_u32(Xs + (p & 1) * NB * KX)), kIdesc, 1u);
+                        umma_ts_f16(tmem + D1_COL + 16 * (s & 1), tmem + A1_COL + 8 * s, d_h1 + (uint64_t)((s * 2 * kLBO) >> 4), kIdesc, s > 1 ? 1u : 0u);
+                    umma_ts_f16(tmem + D1_COL + 16, tmem + A1_XCOL, d_x, kIdesc, 1u);
                     tcgen05_commit(mma_bar + 0);
                 }
                 if (doL2) {
                     const uint32_t h2prev = smem_u32(H2s + (p & 1) * NB * H);       // h2_{p-2}
-                    // four accumulators: (h1 even, h1 odd, h2 even, h2 odd) k-steps, issued round-robin
+                    const uint64_t d_h2 = make_desc_nosw(h2prev);
+                    if (elect_one()) {
+                        // four accumulators: (h1 even, h1 odd, h2 even, h2 odd) k-steps, issued round-robin
 #pragma unroll
-                    for (int s = 0; s < 16; ++s) {
-                        umma_ts_f16(tmem + D2_COL + 16 * (s & 1), tmem + A2_COL + 8 * s, make_desc_nosw(h1prev + s * 2 * kLBO), kIdesc, s > 1 ? 1u : 0u);
-                        umma_ts_f16(tmem + D2_COL + 32 + 16 * (s & 1), tmem + A2_COL + 128 + 8 * s, make_desc_nosw(h2prev + s * 2 * kLBO), kIdesc,
-                                    s > 1 ? 1u : 0u);
+                        for (int s = 0; s < 16; ++s) {
+                            umma_ts_f16(tmem + D2_COL + 16 * (s & 1), tmem + A2_COL + 8 * s, d_h1 + (uint64_t)((s * 2 * kLBO) >> 4), kIdesc, s > 1 ? 1u : 0u);
+                            umma_ts_f16(tmem + D2_COL + 32 + 16 * (s & 1), tmem + A2_COL + 128 + 8 * s, d_h2 + (uint64_t)((s * 2 * kLBO) >> 4), kIdesc,
+                                        s > 1 ? 1u : 0u);
+                        }
+                        tcgen05_commit(mma_bar + 1);
                     }
-                    tcgen05_commit(mma_bar + 1);
                 }
                 if (dbg) { const long long tn = clock64(); seg[1] += tn - tprev; tprev = tn; }
             }
-            if (dbg) { a.dbg[0] = seg[0]; a.dbg[1] = seg[1]; }
+            if (dbg && l == 0) { a.dbg[0] = seg[0]; a.dbg[1] = seg[1]; }
         }
     } else {
         // =================================================== epilogue / cell groups (layer = grp)
@@ -395,7 +400,7 @@ lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     const int pair = blockIdx.x / CL;
-    const int tid = threadIdx.x, warp = tid >> 5, l = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), l = tid & 31;   // uniform warp index
     const int T = a.T;
 
     // ---- shared memory: inbox [2 bufs][8 src][3 kinds][NB][32] fp32, out staging [2 bufs][3 kinds][8 dst][NB][32] fp32,
@@ -457,33 +462,37 @@ lstm2_bwd_kernel(const __grid_constant__ LstmArgs a) {
     const int NP = (int)gridDim.x / CL;
 
     if (grp == 2) {
-        // =================================================== MMA issuer
-        if (l == 0) {
+        // =================================================== MMA issuer (uniform loop, one elected lane issues — see the forward kernel)
+        {
+            const uint64_t d_g2 = make_desc_nosw(smem_u32(dGs + NB * 128)), d_g1 = make_desc_nosw(smem_u32(dGs));
             for (int p = T - 1, it = 0; p >= 0; --p, ++it) {
                 const bool doL1 = p + 1 <= T - 1;
-                mbar_expect_tx(ibar + (it & 1), (uint32_t)(CL * (doL1 ? 3 : 2) * BLK * 4));   // this phase's inbound partial blocks
-                const uint32_t g2 = smem_u32(dGs + NB * 128), g1 = smem_u32(dGs);
+                if (elect_one()) mbar_expect_tx(ibar + (it & 1), (uint32_t)(CL * (doL1 ? 3 : 2) * BLK * 4));   // this phase's inbound partial blocks
                 mbar_wait_long(gbar + 0, it & 1);          // dG of layer 2 (time p) is in shared memory
                 tcgen05_fence_after();
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        umma_ts_f16(tmem + BD_REC2 + 16 * h, tmem + BT_HH2 + 64 * h + 8 * s, make_desc_nosw(g2 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
-                        umma_ts_f16(tmem + BD_IN1 + 16 * h, tmem + BT_IH2 + 64 * h + 8 * s, make_desc_nosw(g2 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
-                    }
-                }
-                tcgen05_commit(mma_bar + 0);
-                if (doL1) {
-                    mbar_wait_long(gbar + 1, (it - 1) & 1);   // dG of layer 1 (time p+1)
-                    tcgen05_fence_after();
+                if (elect_one()) {
 #pragma unroll
                     for (int s = 0; s < 8; ++s) {
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            umma_ts_f16(tmem + BD_REC1 + 16 * h, tmem + BT_HH1 + 64 * h + 8 * s, make_desc_nosw(g1 + s * 2 * kLBO), kIdesc, s > 0 ? 1u : 0u);
+                        for (int h = 0; h < 2; ++h) {
+                            umma_ts_f16(tmem + BD_REC2 + 16 * h, tmem + BT_HH2 + 64 * h + 8 * s, d_g2 + (uint64_t)((s * 2 * kLBO) >> 4), kIdesc, s > 0 ? 1u : 0u);
+                            umma_ts_f16(tmem + BD_IN1 + 16 * h, tmem + BT_IH2 + 64 * h + 8 * s, d_g2 + (uint64_t)((s * 2 * kLBO) >> 4), kIdesc, s > 0 ? 1u : 0u);
+                        }
                     }
-                    tcgen05_commit(mma_bar + 1);
+                    tcgen05_commit(mma_bar + 0);
+                }
+                if (doL1) {
+                    mbar_wait_long(gbar + 1, (it - 1) & 1);   // dG of layer 1 (time p+1)
+                    tcgen05_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                umma_ts_f16(tmem + BD_REC1 + 16 * h, tmem + BT_HH1 + 64 * h + 8 * s, d_g1 + (uint64_t)((s * 2 * kLBO) >> 4), kIdesc, s > 0 ? 1u : 0u);
+                        }
+                        tcgen05_commit(mma_bar + 1);
+                    }
                 }
             }
         }

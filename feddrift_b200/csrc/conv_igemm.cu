@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(cv::kFwdThreads, 1) conv_igemm_kernel(const __
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     int2* rinfo = reinterpret_cast<int2*>(tmem_ptr_smem + 4);      // [128] per-row gather origin of the current tile
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
     const int PQ = a.P * a.Q;
     const long long Mtot = (long long)a.N * PQ;
     const int m_tiles = (int)((Mtot + BM - 1) / BM), n_tiles = a.Kout / BN;
@@ -197,8 +197,9 @@ __global__ void __launch_bounds__(cv::kFwdThreads, 1) conv_igemm_kernel(const __
             }
         }
     } else if (warp == 8) {
-        if (lane == 0) {
-            // ===================================================== MMA issuer
+        {
+            // ===================================================== MMA issuer: uniform loop over the warp, one elected lane issues
+            // (operands in uniform registers — tc05.cuh::elect_one)
             uint32_t it = 0, tl = 0;
             for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++tl) {
                 const int sp = work % splits;
@@ -213,14 +214,17 @@ __global__ void __launch_bounds__(cv::kFwdThreads, 1) conv_igemm_kernel(const __
                     mbar_wait(full_bar + s, ph);
                     tcgen05_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + s * A_STRIDE), b_addr = smem_u32(smem_b + s * B_BYTES);
+                    const uint64_t da0 = make_desc_kmajor_nosw(a_addr, LBO_A, SBO);
+                    const uint64_t db0 = use_tma ? make_smem_desc(b_addr) : make_desc_kmajor_nosw(b_addr, LBO_B, SBO);
+                    const uint32_t bstep = use_tma ? (32u >> 4) : ((2 * LBO_B) >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < CK / 16; ++k)
-                        umma_f16(d_addr, make_desc_kmajor_nosw(a_addr + k * 2 * LBO_A, LBO_A, SBO),
-                                 use_tma ? make_smem_desc(b_addr + k * 32) : make_desc_kmajor_nosw(b_addr + k * 2 * LBO_B, LBO_B, SBO), kIdesc,
-                                 (kidx != k_lo || k != 0) ? 1u : 0u);
-                    tcgen05_commit(empty_bar + s);
+                        for (int k = 0; k < CK / 16; ++k)
+                            umma_f16(d_addr, da0 + (uint64_t)((k * 2 * LBO_A) >> 4), db0 + (uint64_t)(k * bstep), kIdesc, (kidx != k_lo || k != 0) ? 1u : 0u);
+                        tcgen05_commit(empty_bar + s);
+                    }
                 }
-                tcgen05_commit(tmem_full + acc);
+                if (elect_one()) tcgen05_commit(tmem_full + acc);
             }
         }
     } else {
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(cv::kFwdThreads, 1) conv_wgrad_kernel(const __
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done_bar + 1);
     int2* pinfo = reinterpret_cast<int2*>(tmem_ptr_smem + 4);     // [2 groups][64] per-pixel gather origin of the group's stage
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
     const int PQ = a.P * a.Q, RSC = a.R * a.S * a.C;
     const long long Mtot = (long long)a.N * PQ;
     const int m_tiles = (RSC + BM - 1) / BM;
@@ -573,20 +577,22 @@ __global__ void __launch_bounds__(cv::kFwdThreads, 1) conv_wgrad_kernel(const __
             mbar_arrive(full_bar + s);
         }
     } else if (warp == 8) {
-        if (lane == 0) {
+        {
             for (int ci = 0; ci < nch; ++ci) {
                 const int s = ci % STAGES;
                 const uint32_t ph = (ci / STAGES) & 1;
                 mbar_wait(full_bar + s, ph);
                 tcgen05_fence_after();
                 const uint32_t a_addr = smem_u32(smem_a + s * A_BYTES), b_addr = smem_u32(smem_b + s * B_BYTES);
+                const uint64_t da0 = make_desc_kmajor_nosw(a_addr, LBO, SBO), db0 = make_desc_kmajor_nosw(b_addr, LBO, SBO);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < PK / 16; ++k)
-                    umma_f16(tmem_base, make_desc_kmajor_nosw(a_addr + k * 2 * LBO, LBO, SBO), make_desc_kmajor_nosw(b_addr + k * 2 * LBO, LBO, SBO),
-                             kIdesc, (ci | k) != 0 ? 1u : 0u);
-                tcgen05_commit(empty_bar + s);
+                    for (int k = 0; k < PK / 16; ++k)
+                        umma_f16(tmem_base, da0 + (uint64_t)((k * 2 * LBO) >> 4), db0 + (uint64_t)((k * 2 * LBO) >> 4), kIdesc, (ci | k) != 0 ? 1u : 0u);
+                    tcgen05_commit(empty_bar + s);
+                }
             }
-            tcgen05_commit(done_bar);
+            if (elect_one()) tcgen05_commit(done_bar);
         }
     } else if (nch > 0) {
         // ===================================================== epilogue: lane = row j of the tile, reduce-add into dW[k][j]

@@ -239,7 +239,17 @@ def applicable(sim, feat_mask) -> bool:
         return False
     ok = sim.__dict__.get("_stackable")
     if ok is None:
-        ok = sim._stackable = bool(sim.data.X.dtype.is_floating_point and stackable(sim.bank.template))
+        ok = bool(sim.data.X.dtype.is_floating_point and stackable(sim.bank.template))
+        if ok and sim.device.type == "cuda" and os.environ.get("FDB_STACKED") != "force":
+            # on the GPU stacking pays when the body convolutions run on the grouped tcgen05 kernels; a body layer they do not
+            # cover (e.g. the MNIST CNN's 32→64 conv) would fall to the library's grouped convolution, which loops over the
+            # groups (profiles/cfg3_stacked_profile_r2.txt) — the per-pair graph executor is faster there
+            for mod in stack_module(sim.bank.template, 2).modules():
+                if isinstance(mod, StackedConv2d) and mod.in_channels >= 16 and not (
+                        mod.in_channels % 64 == 0 and mod.out_channels % 64 == 0 and mod.groups == 1 and mod.dilation == (1, 1)
+                        and mod.kernel_size[0] == mod.kernel_size[1] and mod.padding[0] == mod.padding[1] and mod.stride[0] == mod.stride[1]):
+                    ok = False
+        sim._stackable = ok
     return ok
 
 

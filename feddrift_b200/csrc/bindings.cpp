@@ -358,6 +358,45 @@ std::vector<Tensor> group_norm_fwd_train(Tensor x, int64_t groups, c10::optional
     return {y, mean, rstd};
 }
 // -> (dx, dgamma [C], dbeta [C])
+// Training-mode BatchNorm over a channels_last activation given as its NHWC view x [..., C] (misc.cu::bn_nhwc_*): the running
+// statistics are updated in place; -> (y, mean, rstd)
+std::vector<Tensor> bn_nhwc_fwd(Tensor x, Tensor y, c10::optional<Tensor> w, c10::optional<Tensor> b, c10::optional<Tensor> run_mean,
+                                c10::optional<Tensor> run_var, double eps, double momentum) {
+    CHECK_CUDA_F32(x); CHECK_CUDA_F32(y);
+    TORCH_CHECK(x.is_contiguous() && x.dim() >= 2 && y.is_contiguous() && y.sizes() == x.sizes(), "bn_nhwc_fwd: contiguous [..., C] input / output");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int C = (int)x.size(-1);
+    const long long rows = x.numel() / C;
+    auto mean = torch::empty({C}, x.options()), rstd = torch::empty({C}, x.options()), sums = torch::empty({2, C}, x.options());
+    Tensor wc, bc;
+    if (w.has_value() && w->defined()) { wc = w->contiguous(); TORCH_CHECK(wc.numel() == C && wc.scalar_type() == torch::kFloat32, "bn weight"); }
+    if (b.has_value() && b->defined()) { bc = b->contiguous(); TORCH_CHECK(bc.numel() == C && bc.scalar_type() == torch::kFloat32, "bn bias"); }
+    float *rm = nullptr, *rv = nullptr;
+    if (run_mean.has_value() && run_mean->defined()) {
+        TORCH_CHECK(run_var.has_value() && run_mean->is_contiguous() && run_var->is_contiguous() && run_mean->numel() == C && run_var->numel() == C, "bn running stats");
+        rm = run_mean->data_ptr<float>(); rv = run_var->data_ptr<float>();
+    }
+    CHECK_OK(fdb::bn_nhwc_fwd_launch(x.data_ptr<float>(), wc.defined() ? wc.data_ptr<float>() : nullptr, bc.defined() ? bc.data_ptr<float>() : nullptr,
+                                     y.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(), rm, rv, sums.data_ptr<float>(), rows, C,
+                                     (float)eps, (float)momentum, cur_stream()), "bn_nhwc_fwd");
+    return {mean, rstd};
+}
+// -> (dx, dweight, dbias)
+std::vector<Tensor> bn_nhwc_bwd(Tensor x, Tensor dy, c10::optional<Tensor> w, Tensor mean, Tensor rstd) {
+    CHECK_CUDA_F32(x); CHECK_CUDA_F32(dy);
+    TORCH_CHECK(x.is_contiguous() && dy.is_contiguous() && x.sizes() == dy.sizes(), "bn_nhwc_bwd: contiguous x / dy of equal shape");
+    c10::cuda::CUDAGuard guard(x.device());
+    const int C = (int)x.size(-1);
+    const long long rows = x.numel() / C;
+    auto dx = torch::empty_like(x);
+    auto dw = torch::empty({C}, x.options()), db = torch::empty({C}, x.options()), sums = torch::empty({2, C}, x.options());
+    Tensor wc;
+    if (w.has_value() && w->defined()) wc = w->contiguous();
+    CHECK_OK(fdb::bn_nhwc_bwd_launch(x.data_ptr<float>(), dy.data_ptr<float>(), wc.defined() ? wc.data_ptr<float>() : nullptr, mean.data_ptr<float>(),
+                                     rstd.data_ptr<float>(), dx.data_ptr<float>(), dw.data_ptr<float>(), db.data_ptr<float>(), sums.data_ptr<float>(),
+                                     rows, C, cur_stream()), "bn_nhwc_bwd");
+    return {dx, dw, db};
+}
 std::vector<Tensor> group_norm_bwd(Tensor x, Tensor dy, c10::optional<Tensor> w, Tensor mean, Tensor rstd, int64_t groups) {
     CHECK_CUDA_F32(x); CHECK_CUDA_F32(dy); CHECK_CUDA_F32(mean); CHECK_CUDA_F32(rstd);
     TORCH_CHECK(x.is_contiguous() && dy.is_contiguous() && x.sizes() == dy.sizes(), "group_norm_bwd: contiguous x / dy of equal shape");
@@ -804,6 +843,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("group_norm_fwd", &group_norm_fwd);
     m.def("group_norm_fwd_train", &group_norm_fwd_train);
     m.def("group_norm_bwd", &group_norm_bwd);
+    m.def("bn_nhwc_fwd", &bn_nhwc_fwd);
+    m.def("bn_nhwc_bwd", &bn_nhwc_bwd);
     m.def("gemm_tn_bias_act", &gemm_tn_bias_act);
     m.def("gemm_tn_bias_act_peer", &gemm_tn_bias_act_peer);
     m.def("gemm_bias_act", &gemm_bias_act);

@@ -47,6 +47,10 @@ int kd_kl_launch(const float* s, const float* t, int B, int K, float T, float* l
 int vfl_bce_launch(const float* parts, const float* y, int K, int B, float* loss1, float* grad, cudaStream_t stream);
 int group_norm_fwd_launch(const float* x, float* y, const float* w, const float* b, int N, int C, int HW, int G, float eps,
                           cudaStream_t stream, float* mean_out = nullptr, float* rstd_out = nullptr);
+int bn_nhwc_fwd_launch(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, float* run_mean, float* run_var,
+                       float* sums, long long rows, int C, float eps, float momentum, cudaStream_t stream);
+int bn_nhwc_bwd_launch(const float* x, const float* dy, const float* w, const float* mean, const float* rstd, float* dx, float* dw, float* db,
+                       float* sums, long long rows, int C, cudaStream_t stream);
 int group_norm_bwd_launch(const float* x, const float* dy, const float* w, const float* mean, const float* rstd, float* dx, float* dg_part,
                           float* db_part, int N, int C, int HW, int G, cudaStream_t stream);
 // gemm_tc.cu : D[M,N] (fp32 or bf16) = act(A[M,K] · B[N,K]^T + bias[N]); A,B bf16 row-major (K contiguous)

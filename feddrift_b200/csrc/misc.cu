@@ -1,4 +1,6 @@
 // K14 (FedGKT distillation loss), K15 (vertical-FL logit sum + BCE gradient), K16 (GroupNorm forward).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -137,6 +139,109 @@ __global__ void __launch_bounds__(256) group_norm_bwd_kernel(const float* __rest
 int group_norm_bwd_launch(const float* x, const float* dy, const float* w, const float* mean, const float* rstd, float* dx, float* dg_part,
                           float* db_part, int N, int C, int HW, int G, cudaStream_t stream) {
     group_norm_bwd_kernel<<<N * G, 256, 0, stream>>>(x, dy, w, mean, rstd, dx, dg_part, db_part, C, HW, G);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
+// ------------------------------------------------------------------------------------------------ NHWC batch normalisation
+// Training-mode BatchNorm2d over a channels_last tensor viewed as X[rows = N·H·W][C] — the normalisation of the pair-stacked
+// networks (sim/stacked.py), where C = npairs·channels runs into the ten-thousands while rows shrink to a few hundred (cuDNN's
+// NHWC kernels take 200–300 µs per call there).  Two passes per direction, both coalesced along C:
+//   stats : grid (C/32, row splits), block 32 channels × 8 row lanes; per-channel Σx, Σx² (forward) or Σdy, Σdy·x̂ (backward)
+//           reduced through shared memory and atomically added into a zeroed [2][C] buffer;
+//   apply : elementwise y = (x − μ)·rstd·γ + β (also writes μ / rstd and the running statistics), or
+//           dx = γ·rstd·(dy − Σdy/R − x̂·Σdy·x̂/R).
+__global__ void __launch_bounds__(256) bn_nhwc_stats_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ sums, long long rows, int C,
+                                                            int rows_per_split) {
+    __shared__ float sh[2][8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = min(rows, r0 + rows_per_split);
+    float s0 = 0.f, s1 = 0.f;
+    if (c < C) {
+        if (dy == nullptr) {
+            // sums of the data SHIFTED by the channel's first value (the same shift in every row split): E[(x−K)²] − E[x−K]² does
+            // not cancel catastrophically when the variance is small against the mean
+            const float K = __ldg(x + c);
+            for (long long r = r0 + rl; r < r1; r += 8) { const float v = __ldg(x + r * C + c) - K; s0 += v; s1 = fmaf(v, v, s1); }
+        } else {
+            const float mu = mean[c], rs = rstd[c];
+            for (long long r = r0 + rl; r < r1; r += 8) {
+                const float g = __ldg(dy + r * C + c), xh = (__ldg(x + r * C + c) - mu) * rs;
+                s0 += g; s1 = fmaf(g, xh, s1);
+            }
+        }
+    }
+    sh[0][rl][cl] = s0; sh[1][rl][cl] = s1;
+    __syncthreads();
+    if (rl < 2 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[rl][i][cl];
+        atomicAdd(sums + (size_t)rl * C + c, t);
+    }
+}
+// apply kernels: thread = one channel (coalesced along C), blockIdx.y strides over the rows — no index arithmetic per element
+__global__ void __launch_bounds__(256) bn_nhwc_fwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ sums, const float* __restrict__ w,
+                                                                const float* __restrict__ b, float* __restrict__ y, float* __restrict__ mean,
+                                                                float* __restrict__ rstd, float* __restrict__ run_mean, float* __restrict__ run_var,
+                                                                long long rows, int C, float eps, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float inv = 1.f / (float)rows;
+    const float ms = sums[c] * inv;                                  // mean of the shifted data
+    const float mu = ms + __ldg(x + c);
+    const float var = fmaxf(fmaf(-ms, ms, sums[C + c] * inv), 0.f);
+    const float rs = rsqrtf(var + eps);
+    const float g = (w ? w[c] : 1.f) * rs, be = fmaf(-mu, g, b ? b[c] : 0.f);      // y = x·g + be
+    if (blockIdx.y == 0) {                             // publish the statistics once per channel
+        mean[c] = mu; rstd[c] = rs;
+        if (run_mean) {
+            const float unb = rows > 1 ? var * ((float)rows / (float)(rows - 1)) : var;
+            run_mean[c] = fmaf(momentum, mu - run_mean[c], run_mean[c]);
+            run_var[c] = fmaf(momentum, unb - run_var[c], run_var[c]);
+        }
+    }
+    for (long long r = blockIdx.y; r < rows; r += gridDim.y) y[r * C + c] = fmaf(__ldg(x + r * C + c), g, be);
+}
+__global__ void __launch_bounds__(256) bn_nhwc_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ sums,
+                                                                const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float inv = 1.f / (float)rows;
+    const float mu = mean[c], rs = rstd[c], sdy = sums[c], sdyx = sums[C + c];
+    const float k = (w ? w[c] : 1.f) * rs, a = sdy * inv, bb = sdyx * inv;
+    if (blockIdx.y == 0) { if (dw) dw[c] = sdyx; if (db) db[c] = sdy; }
+    for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+        const float xh = (__ldg(x + r * C + c) - mu) * rs;
+        dx[r * C + c] = k * (__ldg(dy + r * C + c) - a - xh * bb);
+    }
+}
+static void bn_stats_launch(const float* x, const float* dy, const float* mean, const float* rstd, float* sums, long long rows, int C, cudaStream_t stream) {
+    const int cblocks = (C + 31) / 32;
+    int splits = (int)std::max<long long>(1, std::min<long long>((2 * 148 + cblocks - 1) / cblocks, (rows + 63) / 64));
+    const int rps = (int)((rows + splits - 1) / splits);
+    splits = (int)((rows + rps - 1) / rps);
+    cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)C, stream);
+    bn_nhwc_stats_kernel<<<dim3(cblocks, splits), 256, 0, stream>>>(x, dy, mean, rstd, sums, rows, C, rps);
+}
+int bn_nhwc_fwd_launch(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd, float* run_mean, float* run_var,
+                       float* sums, long long rows, int C, float eps, float momentum, cudaStream_t stream) {
+    if (rows <= 0 || C <= 0) return -5;
+    bn_stats_launch(x, nullptr, nullptr, nullptr, sums, rows, C, stream);
+    const int cb = (C + 255) / 256;
+    const dim3 grid(cb, (unsigned)std::max<long long>(1, std::min<long long>(rows, (148 * 8 + cb - 1) / cb)));
+    bn_nhwc_fwd_apply_kernel<<<grid, 256, 0, stream>>>(x, sums, w, b, y, mean, rstd, run_mean, run_var, rows, C, eps, momentum);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+int bn_nhwc_bwd_launch(const float* x, const float* dy, const float* w, const float* mean, const float* rstd, float* dx, float* dw, float* db,
+                       float* sums, long long rows, int C, cudaStream_t stream) {
+    if (rows <= 0 || C <= 0) return -5;
+    bn_stats_launch(x, dy, mean, rstd, sums, rows, C, stream);
+    const int cb = (C + 255) / 256;
+    const dim3 grid(cb, (unsigned)std::max<long long>(1, std::min<long long>(rows, (148 * 8 + cb - 1) / cb)));
+    bn_nhwc_bwd_apply_kernel<<<grid, 256, 0, stream>>>(x, dy, sums, w, mean, rstd, dx, dw, db, rows, C);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

@@ -226,6 +226,39 @@ class _GroupNormFn(torch.autograd.Function):
         return dx, (dg if weight is not None else None), (db if ctx.has_bias else None), None, None
 
 
+class _BatchNormNhwcFn(torch.autograd.Function):
+    """Training-mode BatchNorm2d on a channels_last activation (csrc/misc.cu::bn_nhwc_*): 2 coalesced passes per direction, the
+    running statistics are updated in place by the forward kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run_mean, run_var, eps, momentum):
+        xh = x.float().contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)       # NHWC view (free for channels_last)
+        w = weight.detach().reshape(-1).contiguous() if weight is not None else None
+        b = bias.detach().reshape(-1).contiguous() if bias is not None else None
+        # the result is a fresh NCHW-logical channels_last tensor (NOT a view of a kernel output: ReLU(inplace=True) follows in
+        # the torchvision blocks); the kernel writes through its NHWC view
+        y = torch.empty_like(x, dtype=torch.float32, memory_format=torch.channels_last)
+        mean, rstd = _ext.load().bn_nhwc_fwd(xh, y.permute(0, 2, 3, 1), w, b, run_mean, run_var, float(eps), float(momentum))
+        ctx.save_for_backward(xh, w, mean, rstd)
+        ctx.wshape = weight.shape if weight is not None else None
+        ctx.has_bias = bias is not None
+        ctx.bshape = bias.shape if bias is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xh, w, mean, rstd = ctx.saved_tensors
+        g = gy.float().contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+        dx, dw, db = _ext.load().bn_nhwc_bwd(xh, g, w, mean, rstd)
+        return (dx.permute(0, 3, 1, 2), dw.view(ctx.wshape) if ctx.wshape is not None else None,
+                db.view(ctx.bshape) if ctx.has_bias else None, None, None, None, None)
+
+
+def batch_norm_train_nhwc(x, weight, bias, run_mean, run_var, eps: float, momentum: float):
+    """Training-mode batch norm of a 4-D CUDA tensor through the NHWC kernels (weight / bias may be any shape with C elements)."""
+    return _BatchNormNhwcFn.apply(x, weight, bias, run_mean, run_var, float(eps), float(momentum))
+
+
 def group_norm(x, groups: int, weight=None, bias=None, eps: float = 1e-5):
     if native(x):
         if torch.is_grad_enabled() and (x.requires_grad or (weight is not None and weight.requires_grad)):

@@ -116,3 +116,49 @@ def test_flat_arena_layout_aligns_big_tensors_and_round_trips():
         assert all(torch.equal(back[k].float(), v.float()) for k, v in sd.items()), name
     mlp = create_model("fnn", 2, 3)   # SEA fnn: dense W1 | b1 | W2 | b2 (the fused kernel's layout), P = 38
     assert mu.flat_size(mlp) == 38 and [s[3] for s in mu.flat_spec(mlp)] == [0, 18, 24, 36]
+
+
+def test_tensor_core_conv_weights_are_stored_channels_last_in_the_flat_rows():
+    """models.utils.ohwi_stored: eligible conv weights live in the rows as (O, kh, kw, I); unflatten returns logical OIHW views with
+    channels_last strides; stems / 1x1 / depthwise filters stay in logical order; ModelBank consumes them through TcConv2d."""
+    import torch
+    from torch import nn
+    from feddrift_b200.models.utils import flat_spec, flat_view, flatten_state_dict, ohwi_stored, unflatten_to_state_dict
+    from feddrift_b200.ops.conv import TcConv2d
+    from feddrift_b200.parallel.arena import ModelBank
+    assert ohwi_stored((64, 32, 3, 3)) and ohwi_stored((128, 64, 5, 5))
+    assert not ohwi_stored((64, 3, 3, 3)) and not ohwi_stored((128, 64, 1, 1)) and not ohwi_stored((64, 1, 3, 3)) and not ohwi_stored((64, 32, 1, 7))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Conv2d(3, 32, 3, padding=1)
+            self.body = nn.Conv2d(32, 64, 3, padding=1)
+            self.head = nn.Linear(64, 5)
+
+        def forward(self, x):
+            return self.head(self.body(self.stem(x)).mean((2, 3)))
+    torch.manual_seed(0)
+    net = Net()
+    sd = net.state_dict()
+    flat = flatten_state_dict(sd)
+    spec = {k: (shape, off, n) for k, shape, _, off, n in flat_spec(net)}
+    shape, off, n = spec["body.weight"]
+    assert torch.equal(flat[off:off + n], sd["body.weight"].permute(0, 2, 3, 1).reshape(-1))      # (O, kh, kw, I) in the row
+    shape, off, n = spec["stem.weight"]
+    assert torch.equal(flat[off:off + n], sd["stem.weight"].reshape(-1))                          # logical order
+    back = unflatten_to_state_dict(flat, flat_spec(net))
+    for k in sd:
+        assert torch.equal(back[k], sd[k])
+    assert back["body.weight"].is_contiguous(memory_format=torch.channels_last) and not back["body.weight"].is_contiguous()
+    assert torch.equal(flat_view(back["body.weight"]), flat[spec["body.weight"][1]:spec["body.weight"][1] + spec["body.weight"][2]])
+    bank = ModelBank(net, 2)
+    assert isinstance(bank.template.body, TcConv2d) and isinstance(bank.template.stem, nn.Conv2d) and not isinstance(bank.template.stem, TcConv2d)
+    assert list(bank.template.state_dict().keys()) == list(sd.keys())
+    mod = bank.module(1)
+    x = torch.randn(2, 3, 6, 6)
+    net2 = Net()
+    net2.load_state_dict(bank.state_dict(1))
+    assert torch.allclose(mod(x), net2(x), atol=1e-5)
+    mod(x).sum().backward()                                                                        # CPU backward through the channels_last view
+    assert mod.body.weight.grad is not None

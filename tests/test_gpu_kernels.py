@@ -241,3 +241,29 @@ def test_modp_matmul_montgomery_exact(p):
     want = [[sum((int(A[i, k]) % p) * (int(B[k, j]) % p) for k in range(K)) % p for j in range(N)] for i in range(M)]
     got = ops.modp_matmul(A.cuda(), B.cuda(), p).cpu()
     assert got.tolist() == want
+
+
+
+@pytest.mark.parametrize("shape", [(4, 96, 5, 7), (32, 2048, 8, 8), (3, 4100, 1, 1)])
+def test_batch_norm_nhwc_train_matches_torch(shape):
+    """misc.cu::bn_nhwc_*: forward, running statistics and backward of training-mode BatchNorm on channels_last tensors."""
+    from feddrift_b200 import ops
+    torch.manual_seed(0)
+    N, C, H, W = shape
+    x = (torch.randn(N, C, H, W, device="cuda") * 2 + 0.5).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = torch.randn(C, device="cuda").requires_grad_(True)
+    b = torch.randn(C, device="cuda").requires_grad_(True)
+    rm0, rv0 = torch.randn(C, device="cuda"), torch.rand(C, device="cuda") + 0.5
+    rm_ref, rv_ref, rm, rv = rm0.clone(), rv0.clone(), rm0.clone(), rv0.clone()
+    ref = F.batch_norm(x, rm_ref, rv_ref, w, b, True, 0.1, 1e-5)
+    dy = torch.randn_like(ref)
+    gx, gw, gb = torch.autograd.grad(ref, (x, w, b), dy)
+    w2 = w.detach().view(2, C // 2).clone().requires_grad_(True) if C % 2 == 0 else w.detach().clone().requires_grad_(True)
+    got = ops.batch_norm_train_nhwc(x, w2, b, rm, rv, 1e-5, 0.1)
+    hx, hw, hb = torch.autograd.grad(got, (x, w2, b), dy)
+    tol = 2e-4
+    assert (got - ref).abs().max().item() < tol * (1 + ref.abs().max().item())
+    assert (rm - rm_ref).abs().max().item() < 1e-5 and (rv - rv_ref).abs().max().item() < 1e-4 * (1 + rv_ref.abs().max().item())
+    assert (hx - gx).abs().max().item() < tol * (1 + gx.abs().max().item())
+    assert (hw.reshape(-1) - gw).abs().max().item() < tol * (1 + gw.abs().max().item())
+    assert (hb - gb).abs().max().item() < tol * (1 + gb.abs().max().item())

@@ -14,7 +14,18 @@ from typing import Dict
 
 import torch
 
-FORMAT_VERSION = 1
+FORMAT_VERSION = 2      # 2: tensor-core conv weights are stored (O, kh, kw, I) in the rows (models.utils.ohwi_stored); 1: logical order
+
+
+def upgrade_theta_v1(theta: torch.Tensor, spec) -> torch.Tensor:
+    """Rows written by format 1 (every tensor in logical order) → the current row layout."""
+    from ..models.utils import ohwi_stored
+    out = theta.clone()
+    for _, shape, _, off, n in spec:
+        if ohwi_stored(shape):
+            seg = theta[:, off:off + n].reshape(theta.shape[0], *shape)
+            out[:, off:off + n] = seg.permute(0, 1, 3, 4, 2).reshape(theta.shape[0], -1)
+    return out
 
 
 def save(sim, path: str) -> str:
@@ -71,9 +82,10 @@ def load(path: str) -> Dict:
 def resume(sim, path: str) -> int:
     """Restore ``sim`` from a checkpoint; returns the next time step to run."""
     blob = load(path)
-    if blob["version"] != FORMAT_VERSION:
+    if blob["version"] not in (1, FORMAT_VERSION):
         raise ValueError(f"checkpoint version {blob['version']} != {FORMAT_VERSION}")
-    sim.bank.theta.copy_(blob["theta"].to(sim.bank.device))
+    theta = blob["theta"] if blob["version"] == FORMAT_VERSION else upgrade_theta_v1(blob["theta"], sim.bank.spec)
+    sim.bank.theta.copy_(theta.to(sim.bank.device))
     sim.algo.load_state_dict(blob["algo"])
     sim.history = list(blob["history"])
     sim.global_round = blob["global_round"]

@@ -162,3 +162,23 @@ def test_tensor_core_conv_weights_are_stored_channels_last_in_the_flat_rows():
     assert torch.allclose(mod(x), net2(x), atol=1e-5)
     mod(x).sum().backward()                                                                        # CPU backward through the channels_last view
     assert mod.body.weight.grad is not None
+
+
+def test_checkpoint_v1_rows_are_upgraded_to_the_channels_last_row_layout():
+    import torch
+    from torch import nn
+    from feddrift_b200.models.utils import flat_spec, flatten_state_dict
+    from feddrift_b200.sim.checkpoint import upgrade_theta_v1
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Conv2d(3, 32, 3)
+            self.b = nn.Conv2d(32, 64, 3)
+            self.fc = nn.Linear(64, 4)
+    net = Net()
+    sd = net.state_dict()
+    v1 = torch.cat([v.reshape(-1) for v in sd.values()])          # format 1: every tensor in logical order, dense (offsets aligned here)
+    spec = flat_spec(net)
+    assert all(spec[i][3] + spec[i][4] == spec[i + 1][3] for i in range(len(spec) - 1))
+    assert torch.equal(upgrade_theta_v1(v1[None], spec)[0], flatten_state_dict(sd))

@@ -609,17 +609,6 @@ void lstm_head(Tensor params, Tensor row_off, int64_t off_fcw, int64_t off_fcb, 
 }
 
 // ---------------------------------------------------------------------------------- implicit-GEMM convolution (conv_igemm.cu)
-// -> (bf16 [K][R][S][C] for the forward kernel, bf16 [C][R][S][K] for the data-gradient kernel) in ONE launch
-std::vector<Tensor> conv_pack_weights(Tensor w) {
-    CHECK_CUDA_F32(w);
-    TORCH_CHECK(w.dim() == 4 && w.is_contiguous(), "conv weights must be contiguous OIHW");
-    c10::cuda::CUDAGuard guard(w.device());
-    const int K = (int)w.size(0), C = (int)w.size(1), R = (int)w.size(2), S = (int)w.size(3);
-    auto o0 = torch::empty({K, R, S, C}, w.options().dtype(torch::kBFloat16));
-    auto o1 = torch::empty({C, R, S, K}, w.options().dtype(torch::kBFloat16));
-    CHECK_OK(fdb::conv_pack_weights_both_launch(w.data_ptr<float>(), o0.data_ptr(), o1.data_ptr(), K, C, R, S, cur_stream()), "conv_pack_weights");
-    return {o0, o1};
-}
 // x: NHWC fp32 [N, H, W, C]; wq: packed bf16 [K][R][S][C]; -> y NHWC fp32 [N, P, Q, K] = act(conv(x, w) + bias)
 Tensor conv_igemm_fwd(Tensor x, Tensor wq, c10::optional<Tensor> bias, int64_t stride, int64_t pad_h, int64_t pad_w, bool relu) {
     CHECK_CUDA_F32(x);
@@ -857,7 +846,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("lstm2_backward", &lstm2_backward);
     m.def("lstm_head", &lstm_head);
     m.def("lstm_small_grads", &lstm_small_grads);
-    m.def("conv_pack_weights", &conv_pack_weights);
     m.def("conv_igemm_fwd", &conv_igemm_fwd);
     m.def("conv_cast_bf16", &conv_cast_bf16);
     m.def("conv_tma_fwd", &conv_tma_fwd);

@@ -1,4 +1,7 @@
-// conv_igemm — implicit-GEMM 2-D convolution on tcgen05 (forward and data-gradient), NHWC activations.
+// conv_igemm — implicit-GEMM 2-D convolution on tcgen05 with SOFTWARE-GATHER producers (forward, data gradient, weight gradient),
+// NHWC activations.  These kernels cover the layers whose channel counts are multiples of 32 but not 64 (the MNIST CNN's 32→64
+// convolution); everything with Cin % 64 == 0 runs on the GEMM mainloop with the TMA-im2col producer (gemm_tc.cu conv modes,
+// 2–4× faster).  The file also holds the small helpers both paths share (bf16 casts, the [K][RS][C] → [C][RS][K] transpose).
 //
 // Reference: cuDNN fp32 `nn.Conv2d` (fedml_api/model/cv/cnn.py:110-117, torchvision resnet18 blocks main_fedavg.py:219-223).
 // Round 1 used an EXPLICIT im2col (9× activation blow-up through HBM) + GEMM and lost to cuDNN; here the im2col matrix never
@@ -9,13 +12,15 @@
 //   D[pixel, c_in ] = Σ_{r,s,k} dY[n, (iy + pad − r)/st, (ix + pad − s)/st, k] · W'[c_in][r][s][k]   (mode 1, dgrad: taps whose
 //                                                                              source row/col is not an integer are skipped)
 //
-// Persistent, warp-specialised:
-//   warps 0-3  PRODUCERS — one thread per output pixel of the 128-pixel tile: per K-chunk (one filter tap × CK channels) the
-//              thread loads its pixel's CK fp32 channels (contiguous in NHWC; zero for padding), converts to bf16 and stores
-//              them as 16-byte pieces into the no-swizzle K-major core-matrix layout tcgen05 reads; the same warps copy the
-//              weight tile (bf16 [Kout][R][S][C], packed once per step by conv_pack_weights_kernel); a 4-stage mbarrier ring;
-//   warp 4     single-thread tcgen05.mma issuer (UMMA 128×BN×16, accumulator double-buffered in TMEM);
-//   warps 5-8  epilogue: tcgen05.ld → bias / ReLU → fp32 NHWC rows (each thread owns one pixel: 128-byte row segments).
+// Persistent, warp-specialised (416 threads):
+//   warps 0-7  PRODUCERS (two groups of 4 warps working on alternate stages) — one thread per output pixel of the 128-pixel
+//              tile: per K-chunk (one filter tap × CK channels) the thread loads its pixel's CK fp32 channels (contiguous in
+//              NHWC; zero for padding; per-pixel origins from a shared-memory row table), converts to bf16 and stores them as
+//              16-byte pieces into the no-swizzle K-major core-matrix layout tcgen05 reads; the weight tile (bf16
+//              [Kout][R][S][C] = the cast channels_last parameter) arrives by TMA (CK = 64) or is copied by the same warps;
+//              a 4-stage mbarrier ring;
+//   warp 8     tcgen05.mma issuer: warp-uniform loop, one elected lane issues (UMMA 128×BN×16, accumulator double-buffered in TMEM);
+//   warps 9-12 epilogue: tcgen05.ld → bias / ReLU → fp32 NHWC rows (each thread owns one pixel: 128-byte row segments).
 // fp32 activations in / out (the networks keep fp32 master activations, like the reference), bf16 tensor-core operands,
 // fp32 accumulation.  All waits are bounded (trap).
 #include <algorithm>
@@ -272,74 +277,6 @@ __global__ void __launch_bounds__(cv::kFwdThreads, 1) conv_igemm_kernel(const __
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
 }
 
-// fp32 OIHW weights [K][C][R][S] → bf16 tap-major tiles.  mode 0: out[k][r][s][c] (forward); mode 1: out[c][r][s][k] (dgrad)
-__global__ void conv_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int K, int C, int R, int S, int mode) {
-    const long long total = (long long)K * C * R * S;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long t = i;
-        int inner, s, r, outer;
-        if (mode == 0) { inner = (int)(t % C); t /= C; s = (int)(t % S); t /= S; r = (int)(t % R); outer = (int)(t / R);
-                         out[i] = __float2bfloat16(w[(((size_t)outer * C + inner) * R + r) * S + s]); }
-        else           { inner = (int)(t % K); t /= K; s = (int)(t % S); t /= S; r = (int)(t % R); outer = (int)(t / R);
-                         out[i] = __float2bfloat16(w[(((size_t)inner * C + outer) * R + r) * S + s]); }
-    }
-}
-
-// both packs in one launch: out0 = [k][r][s][c] (forward), out1 = [c][r][s][k] (dgrad)
-__global__ void conv_pack_weights_both_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out0, __nv_bfloat16* __restrict__ out1,
-                                              int K, int C, int R, int S) {
-    const long long total = (long long)K * C * R * S;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long t = i;                                         // i indexes the OIHW source: coalesced reads
-        const int s = (int)(t % S); t /= S;
-        const int r = (int)(t % R); t /= R;
-        const int c = (int)(t % C);
-        const int k = (int)(t / C);
-        const __nv_bfloat16 v = __float2bfloat16(w[i]);
-        out0[(((size_t)k * R + r) * S + s) * C + c] = v;
-        out1[(((size_t)c * R + r) * S + s) * K + k] = v;
-    }
-}
-// tiled variant (R·S ≤ 11): one block per (32 k × 32 c) tile — coalesced reads of the OIHW rows, the two transposes go through
-// shared memory, both outputs are written in 64-byte runs.  The pack runs once per optimizer step on every conv layer, i.e. its
-// cost is proportional to the parameter count, not to the batch.
-__global__ void conv_pack_weights_tiled_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out0, __nv_bfloat16* __restrict__ out1,
-                                               int K, int C, int RS) {
-    extern __shared__ float tile[];                         // [32 k][32·RS + 1]
-    const int pitch = 32 * RS + 1, kt = (K + 31) / 32, ct = (C + 31) / 32;
-    for (int blk = blockIdx.x; blk < kt * ct; blk += gridDim.x) {
-        const int k0 = (blk / ct) * 32, c0 = (blk % ct) * 32, kw = min(32, K - k0), cw = min(32, C - c0);
-        const int seg = cw * RS;
-        for (int i = threadIdx.x; i < 32 * seg; i += blockDim.x) {
-            const int kk = i / seg, t = i - kk * seg;
-            if (kk < kw) tile[kk * pitch + t] = __ldg(w + ((size_t)(k0 + kk) * C + c0) * RS + t);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 32 * RS * 32; i += blockDim.x) {
-            const int c = i & 31, rs = (i >> 5) % RS, kk = i / (32 * RS);
-            if (kk < kw && c < cw) out0[((size_t)(k0 + kk) * RS + rs) * C + c0 + c] = __float2bfloat16(tile[kk * pitch + c * RS + rs]);
-        }
-        for (int i = threadIdx.x; i < 32 * RS * 32; i += blockDim.x) {
-            const int kk = i & 31, rs = (i >> 5) % RS, c = i / (32 * RS);
-            if (kk < kw && c < cw) out1[((size_t)(c0 + c) * RS + rs) * K + k0 + kk] = __float2bfloat16(tile[kk * pitch + c * RS + rs]);
-        }
-        __syncthreads();
-    }
-}
-int conv_pack_weights_both_launch(const float* w, void* out0, void* out1, int K, int C, int R, int S, cudaStream_t stream) {
-    const long long total = (long long)K * C * R * S;
-    if (R * S <= 11) {
-        const int tiles = ((K + 31) / 32) * ((C + 31) / 32);
-        const size_t smem = (size_t)32 * (32 * R * S + 1) * sizeof(float);
-        conv_pack_weights_tiled_kernel<<<std::min(tiles, 148 * 8), 256, smem, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out0),
-                                                                                      reinterpret_cast<__nv_bfloat16*>(out1), K, C, R * S);
-        return cudaGetLastError() == cudaSuccess ? 0 : -4;
-    }
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-    conv_pack_weights_both_kernel<<<blocks, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out0), reinterpret_cast<__nv_bfloat16*>(out1), K, C, R, S);
-    return cudaGetLastError() == cudaSuccess ? 0 : -4;
-}
-
 // fp32 → bf16 cast of a contiguous tensor (the TMA-im2col path consumes bf16 NHWC operands); with `gate` the value is zeroed where
 // gate ≤ 0 — the ReLU backward mask fused into the cast of dY.  8 elements per thread: two 16-byte loads, one 16-byte store.
 __global__ void conv_cast_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gate, __nv_bfloat16* __restrict__ out, long long n8,
@@ -400,35 +337,6 @@ int conv_cast_rows_bf16_launch(const float* x, long long row_stride, void* out, 
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
-// dW[k][c][r][s] (+)= src[k][r][s][c]: the TMA wgrad GEMM produces the gradient in the packed (O, H, W, I) order.  One block per
-// (k, 64-channel chunk): both the source rows and the destination range are contiguous, the transpose happens in shared memory.
-__global__ void conv_ohwi_to_oihw_kernel(const float* __restrict__ src, float* __restrict__ dst, int K, int C, int RS, int accumulate) {
-    extern __shared__ float tile[];                         // [RS][65]
-    const int cchunks = (C + 63) / 64;
-    for (int blk = blockIdx.x; blk < K * cchunks; blk += gridDim.x) {
-        const int k = blk / cchunks, c0 = (blk - k * cchunks) * 64, cw = min(64, C - c0);
-        for (int i = threadIdx.x; i < RS * 64; i += blockDim.x) {
-            const int rs = i >> 6, c = i & 63;
-            if (c < cw) tile[rs * 65 + c] = __ldg(src + ((size_t)k * RS + rs) * C + c0 + c);
-        }
-        __syncthreads();
-        float* out = dst + ((size_t)k * C + c0) * RS;
-        for (int j = threadIdx.x; j < cw * RS; j += blockDim.x) {
-            const int c = j / RS, rs = j - c * RS;
-            const float v = tile[rs * 65 + c];
-            out[j] = accumulate ? out[j] + v : v;
-        }
-        __syncthreads();
-    }
-}
-int conv_ohwi_to_oihw_launch(const float* src, float* dst, int K, int C, int RS, int accumulate, cudaStream_t stream) {
-    const int blocks = std::min(K * ((C + 63) / 64), 148 * 16);
-    const size_t smem = (size_t)RS * 65 * sizeof(float);
-    if (smem > 48 * 1024) return -5;
-    conv_ohwi_to_oihw_kernel<<<blocks, 256, smem, stream>>>(src, dst, K, C, RS, accumulate);
-    return cudaGetLastError() == cudaSuccess ? 0 : -4;
-}
-
 // bf16 [K][RS][C] → bf16 [C][RS][K] (32×32 tiles through shared memory), for the strided layers' software-gather data gradient
 __global__ void conv_pack_t_kernel(const __nv_bfloat16* __restrict__ wq, __nv_bfloat16* __restrict__ out, int K, int C, int RS) {
     __shared__ __nv_bfloat16 tile[32][33];
@@ -450,13 +358,6 @@ __global__ void conv_pack_t_kernel(const __nv_bfloat16* __restrict__ wq, __nv_bf
 int conv_pack_t_launch(const void* wq, void* out, int K, int C, int RS, cudaStream_t stream) {
     const int tiles = ((K + 31) / 32) * ((C + 31) / 32) * RS;
     conv_pack_t_kernel<<<std::min(tiles, 148 * 16), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(wq), reinterpret_cast<__nv_bfloat16*>(out), K, C, RS);
-    return cudaGetLastError() == cudaSuccess ? 0 : -4;
-}
-
-int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream) {
-    const long long total = (long long)K * C * R * S;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-    conv_pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out), K, C, R, S, mode);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

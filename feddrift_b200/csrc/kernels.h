@@ -74,10 +74,7 @@ struct ConvArgs {
 int make_kmajor_sw128_map(void* map_out /* CUtensorMap* */, const void* base, int rows, int cols, int box_rows);   // gemm_tc.cu
 int conv_igemm_launch(const ConvArgs& a, cudaStream_t stream);
 int conv_wgrad_launch(const ConvArgs& a, cudaStream_t stream);
-int conv_pack_weights_both_launch(const float* w, void* out0, void* out1, int K, int C, int R, int S, cudaStream_t stream);
-int conv_pack_weights_launch(const float* w, void* out, int K, int C, int R, int S, int mode, cudaStream_t stream);
 int conv_cast_bf16_launch(const float* x, const float* gate, void* out, long long n, cudaStream_t stream);
-int conv_ohwi_to_oihw_launch(const float* src, float* dst, int K, int C, int RS, int accumulate, cudaStream_t stream);
 int conv_pack_t_launch(const void* wq, void* out, int K, int C, int RS, cudaStream_t stream);
 // gemm_tc.cu: implicit-GEMM convolution on the GEMM mainloop with a TMA-im2col producer (bf16 NHWC operands)
 int conv_tma_fwd_launch(const void* xb, const void* wq, float* y, const float* bias, int N, int H, int W, int C, int Cout, int R, int S, int P,

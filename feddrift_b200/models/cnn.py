@@ -6,9 +6,10 @@ with NO ReLU between the convs, maxpool2, dropout .25, fc 9216→128 ReLU,
 dropout .5, fc →10, **Softmax before CrossEntropy**; flat 784 input reshaped).
 The fully-connected layers are :class:`~feddrift_b200.ops.linear.TcLinear` (tcgen05 GEMM with fused bias/ReLU
 epilogue on sm_100a, plain ``F.linear`` on CPU).  The 32→64 convolutions are
-:class:`~feddrift_b200.ops.conv.TcConv2d`: implicit-GEMM forward / dgrad / wgrad kernels on tcgen05
-(``csrc/conv_igemm.cu``; ``FDB_NO_TC_CONV=1`` routes them to the library conv for A/B measurements).  The 1-channel stem
-convolution (9 or 25 multiply-adds per output) stays a library call.
+:class:`~feddrift_b200.ops.conv.TcConv2d`: implicit-GEMM forward / wgrad on the software-gather tcgen05 kernels
+(``csrc/conv_igemm.cu``; Cin = 32) and the data gradient on the TMA-im2col GEMM mode (``csrc/gemm_tc.cu``; Cout = 64);
+``FDB_NO_TC_CONV=1`` routes them to the library conv for A/B measurements.  The 1-channel stem convolution (9 or 25
+multiply-adds per output) stays a library call.
 """
 from __future__ import annotations
 

@@ -5,7 +5,9 @@ the same counter-based RNG, per-pair optimizer state that persists across rounds
 train/test evaluation with optional ensembles) but built from separate native kernels so it works for every
 architecture and for algorithms that must look at raw client updates before aggregating (CFL):
 
-* local step: bank-bound ``nn.Module`` forward/backward (TcLinear → tcgen05 GEMM; convs/LSTMs → library kernels),
+* local step: LSTM federations → ``sim/lstm_exec.py`` (all pairs per launch on the persistent LSTM kernels); stackable conv
+  nets → ``sim/stacked.py`` (all pairs in one channel-stacked network on the grouped implicit-GEMM kernels); everything else
+  per pair: bank-bound ``nn.Module`` forward/backward (TcLinear → tcgen05 GEMM, TcConv2d → implicit-GEMM convolution),
   gradients land in a flat scratch row, ``ops.adam_amsgrad_rows_`` / ``ops.sgd_rows_`` update the client row;
 * aggregation: ``ops.cluster_aggregate_`` over the ``[C, M, P]`` client arena (K1);
 * evaluation: clients are grouped by the model they are scored with → one batched forward per (model, split), per-client

@@ -115,6 +115,8 @@ class StackedBatchNorm2d(_Stacked):
 
     def __init__(self, bn, npairs: int):
         super().__init__()
+        if bn.momentum is None and bn.track_running_stats:
+            raise TypeError("cumulative-average BatchNorm (momentum=None) is not pair-stacked")   # per-pair path keeps its semantics
         self.npairs, self.num_features, self.eps, self.momentum = npairs, bn.num_features, bn.eps, bn.momentum
         self.track = bn.track_running_stats
         self.register_parameter("weight", None)

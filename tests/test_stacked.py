@@ -87,6 +87,9 @@ def test_stackable_rejects_unsupported_layers():
             return self.emb(x)
     assert not S.stackable(Odd())
     assert S.stackable(cnn.CNN_DropOut())
+    cma = resnet.ResNet(resnet.BasicBlock, [1], 10, widths=(8,))
+    cma.bn1.momentum = None                                   # cumulative moving average: semantics the stacked BN does not reproduce
+    assert not S.stackable(cma)
     with pytest.raises(TypeError):
         S.stack_module(Odd(), 2)
 

@@ -332,7 +332,8 @@ def convert_convs_(module: nn.Module) -> nn.Module:
     by a :class:`TcConv2d` with the same parameter values; state-dict keys, shapes and values are unchanged.  Used for the torchvision / model-zoo networks so that their 3×3 and
     1×1 body convolutions run on the implicit-GEMM tcgen05 kernels (stems with 1 or 3 input channels stay library convs)."""
     for name, child in list(module.named_children()):
-        if type(child) is nn.Conv2d and child.padding_mode == "zeros" and not isinstance(child.padding, str) and \
+        if isinstance(child, nn.Conv2d) and type(child).forward is nn.Conv2d.forward and child.padding_mode == "zeros" \
+                and not isinstance(child.padding, str) and \
                 (igemm_eligible(child.in_channels, child.out_channels, _pair(child.stride), _pair(child.dilation), child.groups)
                  or _ohwi(child.weight.shape)):
             tc = TcConv2d(child.in_channels, child.out_channels, child.kernel_size, child.stride, child.padding, child.dilation,

@@ -302,9 +302,32 @@ class _Stage:
                 self.params[:, self.spec[key][1]] += float(bn.steps if steps is None else steps)
 
 
+def max_pairs_per_pass(P: int) -> int:
+    """How many pairs are stacked at once: the staged rows (parameters, gradients, three Adam moments) of one pass stay below
+    ``FDB_STACKED_MAX_GB`` (default 24 GB of the 180 GB HBM; activations scale with the same count)."""
+    budget = float(os.environ.get("FDB_STACKED_MAX_GB", "24")) * (1 << 30)
+    return max(1, int(budget // (5 * 4 * max(P, 1))))
+
+
 def train_pairs(sim, pairs: List, seed: int, rnd: int, E: int, use_adam: bool, lr: float, wd: float) -> bool:
     """``pairs``: list of ``(c, m, sampler)``.  Runs the E local steps of every pair; returns False (nothing done) when the pairs
-    draw different batch sizes — the caller then takes the per-pair path."""
+    draw different batch sizes — the caller then takes the per-pair path.  Large federations are processed in passes of at most
+    :func:`max_pairs_per_pass` pairs (equal-sized passes, so at most two staging sets are ever alive)."""
+    cap = max_pairs_per_pass(sim.bank.P)
+    if len(pairs) > cap:
+        npass = (len(pairs) + cap - 1) // cap
+        per = (len(pairs) + npass - 1) // npass
+        chunks = [pairs[i:i + per] for i in range(0, len(pairs), per)]
+        if not _train_pass(sim, chunks[0], seed, rnd, E, use_adam, lr, wd):
+            return False                                  # nothing was modified: the caller takes the per-pair path for all pairs
+        for ch in chunks[1:]:
+            if not _train_pass(sim, ch, seed, rnd, E, use_adam, lr, wd):
+                raise RuntimeError("pair-stacked training: batch sizes differ between passes of one round")
+        return True
+    return _train_pass(sim, pairs, seed, rnd, E, use_adam, lr, wd)
+
+
+def _train_pass(sim, pairs: List, seed: int, rnd: int, E: int, use_adam: bool, lr: float, wd: float) -> bool:
     bank, cl, dev = sim.bank, sim.clients, sim.device
     C, M, P = sim.C, sim.M, bank.P
     npairs = len(pairs)
@@ -323,9 +346,13 @@ def train_pairs(sim, pairs: List, seed: int, rnd: int, E: int, use_adam: bool, l
     if B == 0 or any(len(a) != B for row in sel for a in row):
         return False
     gidx = torch.from_numpy(np.asarray(sel, dtype=np.int64).transpose(1, 0, 2).copy()).to(dev, non_blocking=True)   # [E, npairs, B]
-    st: Optional[_Stage] = sim.__dict__.get("_stack_stage")
-    if st is None or st.npairs != npairs:
-        st = sim._stack_stage = _Stage(sim, npairs)
+    stages = sim.__dict__.setdefault("_stack_stages", {})           # per pair count (a chunked round has ≤ 2 distinct counts)
+    st: Optional[_Stage] = stages.get(npairs)
+    if st is None:
+        if len(stages) >= 2:
+            stages.clear()
+        st = stages[npairs] = _Stage(sim, npairs)
+    sim._stack_stage = st
     rows = torch.tensor([c * M + m for c, m, _ in pairs], dtype=torch.int64, device=dev)
     ms = torch.tensor([m for _, m, _ in pairs], dtype=torch.int64, device=dev)
     CM = C * M

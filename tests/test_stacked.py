@@ -94,10 +94,12 @@ def test_stackable_rejects_unsupported_layers():
         S.stack_module(Odd(), 2)
 
 
-def _run_round(stacked_on: bool, optimizer: str = "sgd"):
+def _run_round(stacked_on: bool, optimizer: str = "sgd", max_gb: str = None):
     from feddrift_b200.sim import DriftSim, make_args
     from feddrift_b200.utils.metrics import MetricsSink
     os.environ["FDB_STACKED"] = "1" if stacked_on else "0"
+    if max_gb is not None:
+        os.environ["FDB_STACKED_MAX_GB"] = max_gb
     try:
         a = make_args(model="cnn", dataset="MNIST", client_num_in_total=4, client_num_per_round=4, concept_drift_algo="win-1",
                       concept_drift_algo_arg="", concept_num=2, change_points="A", sample_num=16, batch_size=8, comm_round=1,
@@ -109,6 +111,7 @@ def _run_round(stacked_on: bool, optimizer: str = "sgd"):
         return sim.bank.theta.clone(), sim.clients.params.clone(), sim.clients.step.clone()
     finally:
         os.environ.pop("FDB_STACKED", None)
+        os.environ.pop("FDB_STACKED_MAX_GB", None)
 
 
 def test_round_through_stacked_executor_equals_per_pair_executor():
@@ -123,3 +126,18 @@ def test_round_through_stacked_executor_equals_per_pair_executor():
     a0, _, st0 = _run_round(False, "adam")
     assert torch.equal(st1, st0) and int(st1.max()) == 2
     assert (a1 - a0).abs().max().item() < 0.05
+
+
+def test_large_federations_are_stacked_in_memory_bounded_passes():
+    """FDB_STACKED_MAX_GB caps the staged rows: 4 pairs of the 1.2 M-parameter CNN under a 0.05 GB budget → two passes of two pairs,
+    same result as one pass."""
+    from feddrift_b200.sim import stacked as S2
+    os.environ["FDB_STACKED_MAX_GB"] = "0.05"
+    try:
+        assert S2.max_pairs_per_pass(1199884) == 2
+    finally:
+        os.environ.pop("FDB_STACKED_MAX_GB", None)
+    th_one, cp_one, _ = _run_round(True)
+    th_two, cp_two, _ = _run_round(True, max_gb="0.05")
+    assert (cp_one - cp_two).abs().max().item() < 1e-5
+    assert (th_one - th_two).abs().max().item() < 1e-5
